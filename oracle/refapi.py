@@ -1,0 +1,265 @@
+"""ctypes binding of oracle/_ref/libref.so -- TEST INFRASTRUCTURE ONLY.
+
+libref.so is the UNMODIFIED reference (dwcoen1234/longfellow-zk, lib/) compiled
+in place by oracle/ref_build/Makefile behind a small extern "C" wrapper.  Only
+tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
+legs may import this module; the product (longfellow_zk_b200/) never does.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIBREF = os.path.join(_HERE, "_ref", "libref.so")
+
+GF2_128_ID = 4  # proto/circuit_io.h:24-36
+P256_ID = 1
+FID_BN254 = 100  # ref_prime.cc local ids
+FID_FP128 = 101
+FID_GOLDILOCKS = 102
+
+_lib = None
+
+
+def available():
+    return os.path.exists(LIBREF)
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        _lib = C.CDLL(LIBREF)
+        _lib.ref_circuit_load.restype = C.c_void_p
+        _lib.ref_circuit_load.argtypes = [C.c_int, C.c_char_p, C.c_size_t]
+        _lib.ref_circuit_free.argtypes = [C.c_void_p]
+        _lib.ref_zk_bench.restype = C.c_double
+        _lib.ref_merkle_commit_open.restype = C.c_size_t
+        _lib.ref_merkle_tree_len.restype = C.c_size_t
+        _lib.ref_merkle_tree_len.argtypes = [C.c_size_t]
+        _lib.ref_transcript_script.restype = C.c_size_t
+        _lib.ref_circuit_info.restype = C.c_size_t
+    return _lib
+
+
+def _u8(a):
+    return np.ascontiguousarray(a, dtype=np.uint8)
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def gf128_mul(a, b):
+    a, b = _u8(a).reshape(-1, 16), _u8(b).reshape(-1, 16)
+    out = np.empty_like(a)
+    lib().ref_gf128_mul(_p(a), _p(b), _p(out), C.c_size_t(a.shape[0]))
+    return out
+
+
+def gf128_invert(a):
+    a = _u8(a).reshape(-1, 16)
+    out = np.empty_like(a)
+    lib().ref_gf128_invert(_p(a), _p(out), C.c_size_t(a.shape[0]))
+    return out
+
+
+def gf128_of_scalar(u):
+    u = np.ascontiguousarray(u, dtype=np.uint64)
+    out = np.empty((u.shape[0], 16), np.uint8)
+    lib().ref_gf128_of_scalar(_p(u), _p(out), C.c_size_t(u.shape[0]))
+    return out
+
+
+def gf128_subfield_index(a):
+    a = _u8(a).reshape(-1, 16)
+    out = np.empty(a.shape[0], np.uint32)
+    lib().ref_gf128_subfield_index(_p(a), _p(out), C.c_size_t(a.shape[0]))
+    return out
+
+
+def gf128_constants():
+    beta = np.empty((16, 16), np.uint8)
+    pts = np.empty((6, 16), np.uint8)
+    newton = np.empty((6, 6, 16), np.uint8)
+    lib().ref_gf128_constants(_p(beta), _p(pts), _p(newton))
+    return beta, pts, newton
+
+
+def lch14(op, l, coset_or_k, B):
+    """op: 'fft' | 'ifft' | 'bidir'. B: (2^l,16) uint8; returns a new array."""
+    B = _u8(B).reshape(-1, 16).copy()
+    assert B.shape[0] == 1 << l
+    lib().ref_lch14(C.c_int({"fft": 0, "ifft": 1, "bidir": 2}[op]), C.c_size_t(l),
+                    C.c_size_t(coset_or_k), _p(B))
+    return B
+
+
+def lch14_what():
+    out = np.empty((16, 16, 16), np.uint8)
+    lib().ref_lch14_what(_p(out))
+    return out
+
+
+def lch14_interpolate(n, m, rows):
+    """rows: (nrows, m, 16) uint8 with the first n of each row valid."""
+    rows = _u8(rows).copy()
+    nrows = rows.shape[0]
+    assert rows.shape == (nrows, m, 16)
+    lib().ref_lch14_interpolate(C.c_size_t(n), C.c_size_t(m), _p(rows), C.c_size_t(nrows))
+    return rows
+
+
+def merkle_build(leaves):
+    leaves = _u8(leaves).reshape(-1, 32)
+    n = leaves.shape[0]
+    nodes = np.zeros((2 * n, 32), np.uint8)
+    root = np.zeros(32, np.uint8)
+    lib().ref_merkle_build(C.c_size_t(n), _p(leaves), _p(nodes), _p(root))
+    return root, nodes
+
+
+def merkle_commit_open(payload, rng, pos):
+    """payload: (n, len) uint8; rng: n*32 bytes; pos: list of leaf indices."""
+    payload = _u8(payload)
+    n, ln = payload.shape
+    rng = _u8(rng)
+    assert rng.size >= 32 * n
+    pos = np.ascontiguousarray(pos, dtype=np.uint64)
+    root = np.zeros(32, np.uint8)
+    nonce = np.zeros((max(len(pos), 1), 32), np.uint8)
+    cap = max(len(pos), 1) * int(lib().ref_merkle_tree_len(n))
+    path = np.zeros((cap, 32), np.uint8)
+    k = lib().ref_merkle_commit_open(C.c_size_t(n), _p(payload), C.c_size_t(ln), _p(rng),
+                                     _p(root), _p(pos), C.c_size_t(len(pos)), _p(nonce), _p(path))
+    return root, nonce[:len(pos)], path[:k]
+
+
+def transcript_script(init, script, out_cap=1 << 20):
+    out = np.zeros(out_cap, np.uint8)
+    n = lib().ref_transcript_script(C.c_char_p(init), C.c_size_t(len(init)), C.c_char_p(script),
+                                    C.c_size_t(len(script)), _p(out), C.c_size_t(out_cap))
+    return out[:n].tobytes()
+
+
+LIGERO_FIELDS = ["block_enc", "block", "dblock", "block_ext", "r", "w", "nwrow", "nqtriples",
+                 "nwqrow", "nrow", "mc_pathlen", "iq"]
+
+
+def ligero_param(field_id, nw, nq, rate=7, nreq=132, block_enc=0):
+    out = (C.c_size_t * 12)()
+    lib().ref_ligero_param(C.c_int(field_id), C.c_size_t(nw), C.c_size_t(nq), C.c_size_t(rate),
+                           C.c_size_t(nreq), C.c_size_t(block_enc), out)
+    return dict(zip(LIGERO_FIELDS, [int(x) for x in out]))
+
+
+def circuit_info(field_id, circ):
+    out = (C.c_size_t * 4096)()
+    k = lib().ref_circuit_info(C.c_int(field_id), C.c_char_p(circ), C.c_size_t(len(circ)), out,
+                               C.c_size_t(4096))
+    v = [int(x) for x in out[:k]]
+    hdr = dict(zip(["nv", "logv", "nc", "logc", "nl", "ninputs", "npub_in", "subfield_boundary",
+                    "nterms"], v[:9]))
+    hdr["layers"] = [dict(nw=v[9 + 3 * i], logw=v[10 + 3 * i], nterms=v[11 + 3 * i])
+                     for i in range(hdr["nl"])]
+    return hdr
+
+
+def _take(fn, *args):
+    circ, wit = C.POINTER(C.c_uint8)(), C.POINTER(C.c_uint8)()
+    cl, wl = C.c_size_t(), C.c_size_t()
+    rc = fn(*args, C.byref(circ), C.byref(cl), C.byref(wit), C.byref(wl))
+    assert rc == 0
+    cb = C.string_at(circ, cl.value)
+    wb = C.string_at(wit, wl.value)
+    lib().ref_free(circ)
+    lib().ref_free(wit)
+    return cb, wb
+
+
+def sha_circuit(nblocks=1):
+    """(LFC1 circuit bytes, witness bytes) of BM_ShaZK_fp2_128/nblocks."""
+    return _take(lib().ref_sha_circuit, C.c_size_t(nblocks))
+
+
+def ecdsa_circuit(nsigs=1):
+    """(LFC1 circuit bytes, witness bytes) of BM_ECDSAZKProver/nsigs."""
+    return _take(lib().ref_ecdsa_circuit, C.c_size_t(nsigs))
+
+
+class Circuit:
+    def __init__(self, field_id, circ_bytes):
+        self.field_id = field_id
+        self.h = lib().ref_circuit_load(C.c_int(field_id), C.c_char_p(circ_bytes),
+                                        C.c_size_t(len(circ_bytes)))
+        if not self.h:
+            raise ValueError("reference CircuitReader rejected the circuit")
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().ref_circuit_free(C.c_void_p(self.h))
+            self.h = None
+
+    def prove(self, witness, rng, tinit=b"test", rate=7, nreq=132, block_enc=0, dump=False):
+        """Reference ZkProver::commit+prove+ZkProof::write with replayed coins."""
+        rng = _u8(np.frombuffer(rng, np.uint8) if isinstance(rng, (bytes, bytearray)) else rng)
+        out = np.zeros(1 << 21, np.uint8)
+        out_len, used = C.c_size_t(), C.c_size_t()
+        dw = np.zeros(1 << 22, np.uint8) if dump else None
+        dt = np.zeros(1 << 26, np.uint8) if dump else None
+        dr = np.zeros(32, np.uint8) if dump else None
+        ds = np.zeros(1 << 20, np.uint8) if dump else None
+        n = lambda a: C.c_size_t(a.size if a is not None else 0)
+        pp = lambda a: _p(a) if a is not None else None
+        rc = lib().ref_zk_prove(C.c_void_p(self.h), C.c_char_p(witness), _p(rng),
+                                C.c_size_t(rng.size), C.c_char_p(tinit), C.c_size_t(len(tinit)),
+                                C.c_size_t(rate), C.c_size_t(nreq), C.c_size_t(block_enc), _p(out),
+                                C.c_size_t(out.size), C.byref(out_len), C.byref(used),
+                                pp(dw), n(dw), pp(dt), n(dt), pp(dr), pp(ds), n(ds))
+        if rc != 0:
+            raise RuntimeError(f"reference prover failed rc={rc}")
+        res = dict(proof=out[:out_len.value].tobytes(), rng_used=used.value)
+        if dump:
+            res.update(witness=dw, tableau=dt, root=dr.tobytes(), sumcheck=ds)
+        return res
+
+    def verify(self, pub, proof, tinit=b"test", rate=7, nreq=132, block_enc=0):
+        return int(lib().ref_zk_verify(C.c_void_p(self.h), C.c_char_p(pub), C.c_char_p(tinit),
+                                       C.c_size_t(len(tinit)), C.c_size_t(rate), C.c_size_t(nreq),
+                                       C.c_size_t(block_enc), C.c_char_p(proof),
+                                       C.c_size_t(len(proof))))
+
+    def bench(self, witness, rng, nthreads=1, per_thread=4, rate=7, nreq=132):
+        rng = _u8(np.frombuffer(rng, np.uint8) if isinstance(rng, (bytes, bytearray)) else rng)
+        lat = (C.c_double * per_thread)()
+        secs = lib().ref_zk_bench(C.c_void_p(self.h), C.c_char_p(witness), _p(rng),
+                                  C.c_size_t(rng.size), C.c_size_t(rate), C.c_size_t(nreq),
+                                  C.c_size_t(nthreads), C.c_size_t(per_thread), lat)
+        return float(secs), [float(x) for x in lat]
+
+
+def fft(fid, data, n, fwd=False):
+    data = _u8(data).copy()
+    assert lib().ref_fft(C.c_int(fid), _p(data), C.c_size_t(n), C.c_int(int(fwd))) == 0
+    return data
+
+
+def fft_p256_2(data, n, fwd=False):
+    data = _u8(data).copy()
+    assert lib().ref_fft_p256_2(_p(data), C.c_size_t(n), C.c_int(int(fwd))) == 0
+    return data
+
+
+def rs(fid, rows, n, m):
+    rows = _u8(rows).copy()
+    nrows = rows.shape[0]
+    assert lib().ref_rs(C.c_int(fid), _p(rows), C.c_size_t(n), C.c_size_t(m), C.c_size_t(nrows)) == 0
+    return rows
+
+
+def fp_mul(fid, a, b):
+    a, b = _u8(a), _u8(b)
+    out = np.empty_like(a)
+    kb = {FID_BN254: 32, FID_FP128: 16, FID_GOLDILOCKS: 8, P256_ID: 32}[fid]
+    assert lib().ref_fp_mul(C.c_int(fid), _p(a), _p(b), _p(out), C.c_size_t(a.size // kb)) == 0
+    return out
