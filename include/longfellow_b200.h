@@ -1,0 +1,154 @@
+/* longfellow_b200.h -- C ABI of the B200-native Longfellow prover back end.
+ *
+ * Drop-in boundary for the data-parallel prover hot path of
+ * dwcoen1234/longfellow-zk (lib/): every entry point names the reference
+ * interface it replaces (file:line under the reference's lib/).  Plain C
+ * linkage, opaque handles, plain pointers and sizes.  Field elements cross
+ * this boundary in the reference's WIRE encoding (Field::to_bytes_field:
+ * lib/algebra/fp_generic.h:378-380 de-Montgomerised little-endian kBytes;
+ * lib/gf2k/gf2_128.h:178-180 16 little-endian bytes).
+ *
+ * All functions return 0 on success and a negative lf_status otherwise;
+ * lf_last_error() gives a message for the calling thread.  There is no CPU
+ * fallback: without a CUDA device every compute entry point fails with
+ * LF_ERR_CUDA.  A context owns one CUDA stream; calls on one context are
+ * serialised on it, different contexts are independent (the reference's
+ * provers are likewise independent objects without shared mutable state).
+ */
+#ifndef LONGFELLOW_B200_H_
+#define LONGFELLOW_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Field ids: the reference's proto FieldID (lib/proto/circuit_io.h:24-36) where
+ * it defines one; >= 100 for the benchmark-only fields of
+ * lib/algebra/fft_test.cc:33-44 and lib/algebra/reed_solomon_test.cc:337-401. */
+enum lf_field {
+  LF_FIELD_P256 = 1,        /* Fp256Base, lib/algebra/fp_p256.h */
+  LF_FIELD_GF2_128 = 4,     /* GF2_128<>, lib/gf2k/gf2_128.h */
+  LF_FIELD_BN254 = 100,     /* Fp<4>, fft_test.cc:33-36 */
+  LF_FIELD_FP128 = 101,     /* Fp128, lib/algebra/fp_p128.h */
+  LF_FIELD_GOLDILOCKS = 102 /* Fp<1> 2^64-2^32+1 */
+};
+
+enum lf_status {
+  LF_OK = 0,
+  LF_ERR_ARG = -1,          /* null / out-of-range argument */
+  LF_ERR_CUDA = -2,         /* CUDA runtime failure (incl. no device) */
+  LF_ERR_FORMAT = -3,       /* malformed circuit bytes / non-canonical element */
+  LF_ERR_UNSUPPORTED = -4,  /* field or shape not built yet */
+  LF_ERR_WITNESS = -5,      /* witness does not satisfy the circuit (ZkProver::prove == false) */
+  LF_ERR_RNG = -6,          /* caller-supplied randomness exhausted */
+  LF_ERR_CAPACITY = -7      /* output buffer too small */
+};
+
+typedef struct lf_ctx lf_ctx;
+typedef struct lf_circuit lf_circuit;
+
+/* ---- context ---------------------------------------------------------- */
+/* device: CUDA ordinal.  stream: a cudaStream_t the caller owns (e.g. torch's
+ * current stream) or NULL to let the context create its own. */
+int lf_ctx_create(int device, void* stream, lf_ctx** out);
+void lf_ctx_destroy(lf_ctx* ctx);
+int lf_ctx_synchronize(lf_ctx* ctx);
+const char* lf_last_error(void);
+const char* lf_version(void);
+
+/* ---- (a1,a3) field arithmetic, element-wise: out[i] = a[i] * b[i] ------ */
+/* replaces Field::mulf (fp_generic.h:187-198, gf2_128.h:233-235); host buffers. */
+int lf_elt_mul(lf_ctx* ctx, int field_id, const void* a, const void* b, void* out, size_t n);
+
+/* ---- (a7,a9) Reed-Solomon row extension -------------------------------- */
+/* replaces InterpolatorFactory::make(n, m)->interpolate(y) batched over rows
+ * (lib/gf2k/lch14_reed_solomon.h:49-123, lib/algebra/reed_solomon.h:93-147):
+ * rows is nrows x m elements (host), the first n of each row are the
+ * evaluations at the injected points 0..n-1; entries n..m-1 are filled. */
+int lf_rs_interpolate(lf_ctx* ctx, int field_id, size_t n, size_t m, void* rows, size_t nrows);
+/* same with device-resident rows (row_stride in elements); asynchronous on the
+ * context stream */
+int lf_rs_interpolate_dev(lf_ctx* ctx, int field_id, size_t n, size_t m, void* d_rows,
+                          size_t row_stride, size_t nrows);
+
+/* ---- (a11) Merkle column commitment ------------------------------------ */
+/* replaces LigeroProver::commit's MerkleCommitment::commit(updhash, rng)
+ * (lib/merkle/merkle_commitment.h:50-64, lib/ligero/ligero_prover.h:73-76):
+ * tableau = nrow x block_enc elements (host, wire encoding); leaf j hashes
+ * nonce_j || column dblock+j; nonces = block_ext x 32 bytes supplied by the
+ * caller in leaf order (so the RandomEngine order stays with the caller).
+ * nodes_out (optional) receives the 2*block_ext heap of digests. */
+int lf_merkle_commit(lf_ctx* ctx, int field_id, size_t nrow, size_t block_enc, size_t dblock,
+                     const void* tableau, const uint8_t* nonces, uint8_t root_out[32],
+                     uint8_t* nodes_out);
+
+/* ---- circuits ---------------------------------------------------------- */
+/* lfc1: the reference's serialized circuit (lib/proto/circuit_reader.h:41-258).
+ * rate/nreq/block_enc: LigeroParam arguments (lib/zk/zk_proof.h:63-75;
+ * block_enc == 0 selects the deprecated power-of-two search of
+ * lib/ligero/ligero_param.h:152-169). */
+int lf_circuit_upload(lf_ctx* ctx, int field_id, const uint8_t* lfc1, size_t len, size_t rate,
+                      size_t nreq, size_t block_enc, lf_circuit** out);
+void lf_circuit_free(lf_circuit* c);
+
+typedef struct lf_circuit_info {
+  size_t ninputs, npub_in, nl, nterms, kbytes;
+  size_t witness_bytes;   /* ninputs * kbytes: one proof's input wires */
+  size_t rng_bytes;       /* random bytes one proof consumes (GF(2^128): exact;
+                             prime fields: without rejections -- supply slack) */
+  size_t max_proof_bytes; /* upper bound of the serialized proof */
+  size_t block_enc, block, dblock, block_ext, nrow, r, w, nwrow, nqtriples, nreq;
+  size_t nw;              /* Ligero witnesses = private inputs + pad */
+} lf_circuit_info;
+int lf_circuit_get_info(const lf_circuit* c, lf_circuit_info* info);
+
+/* ---- whole prover, batch of independent proofs -------------------------- */
+/* replaces, per proof i (lib/zk/zk_prover.h:72-149, lib/zk/zk_proof.h:90-112):
+ *     Transcript tp(tinit, tinit_len);
+ *     ZkProof zkp(circuit, rate, nreq[, block_enc]);
+ *     ZkProver prover(circuit, F, rs_factory);
+ *     prover.commit(zkp, W_i, tp, rng_i);  ok = prover.prove(zkp, W_i, tp);
+ *     zkp.write(bytes_i, F);
+ * witnesses: nproofs x ninputs elements (wire encoding).
+ * rng: nproofs x rng_stride bytes; proof i consumes rng + i*rng_stride exactly
+ *      as the reference consumes RandomEngine::bytes.
+ * proofs_out: nproofs x proof_stride bytes; proof_lens[i] = serialized length.
+ * status[i]: LF_OK or LF_ERR_WITNESS / LF_ERR_RNG / LF_ERR_CAPACITY.
+ * Host pointers; the call copies in, proves on the GPU and copies out. */
+int lf_zk_prove_batch(lf_circuit* c, size_t nproofs, const uint8_t* witnesses, const uint8_t* rng,
+                      size_t rng_stride, const uint8_t* tinit, size_t tinit_len,
+                      uint8_t* proofs_out, size_t proof_stride, size_t* proof_lens, int* status);
+/* same with every buffer resident in device memory (proof_lens/status: device
+ * uint64_t / int32_t arrays); asynchronous on the context stream. */
+int lf_zk_prove_batch_dev(lf_circuit* c, size_t nproofs, const void* d_witnesses, const void* d_rng,
+                          size_t rng_stride, const uint8_t* tinit, size_t tinit_len,
+                          void* d_proofs_out, size_t proof_stride, void* d_proof_lens,
+                          void* d_status);
+
+/* ---- stage read-back for parity tests ---------------------------------- */
+enum lf_stage {
+  LF_STAGE_WITNESS = 1,   /* Ligero witness vector, nw elements */
+  LF_STAGE_TABLEAU = 2,   /* nrow x block_enc elements */
+  LF_STAGE_ROOT = 3,      /* 32 bytes */
+  LF_STAGE_SUMCHECK = 4   /* serialized sumcheck proof */
+};
+/* copies stage data of proof `index` of the most recent batch (wire encoding) */
+int lf_zk_debug_fetch(lf_circuit* c, size_t index, int stage, uint8_t* out, size_t cap,
+                      size_t* len);
+
+/* number of kernel launches issued on behalf of this context so far */
+uint64_t lf_ctx_launch_count(const lf_ctx* ctx);
+
+/* integer-pipe micro-benchmarks (roofline denominators): returns achieved
+ * giga-operations per second of `what` on the context's device.
+ *   what = 0: IMAD.WIDE  1: LOP3  2: GF(2^128) multiply (Gmul/s)
+ *          3: SHA-256 compressions (G/s) */
+int lf_microbench(lf_ctx* ctx, int what, double* gops);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LONGFELLOW_B200_H_ */

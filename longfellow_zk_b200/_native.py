@@ -1,0 +1,74 @@
+"""ctypes loader for liblongfellow_b200.so.  There is no Python or CPU fallback:
+if the CUDA library is missing or no device is present, calls raise."""
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB = os.path.join(HERE, "liblongfellow_b200.so")
+
+_lib = None
+
+
+class LongfellowError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"longfellow_b200 error {code}: {msg}")
+        self.code = code
+
+
+class CircuitInfo(C.Structure):
+    _fields_ = [(n, C.c_size_t) for n in (
+        "ninputs", "npub_in", "nl", "nterms", "kbytes", "witness_bytes", "rng_bytes",
+        "max_proof_bytes", "block_enc", "block", "dblock", "block_ext", "nrow", "r", "w", "nwrow",
+        "nqtriples", "nreq", "nw")]
+
+
+EXPORTS = [
+    "lf_ctx_create", "lf_ctx_destroy", "lf_ctx_synchronize", "lf_last_error", "lf_version",
+    "lf_elt_mul", "lf_rs_interpolate", "lf_rs_interpolate_dev", "lf_merkle_commit",
+    "lf_circuit_upload", "lf_circuit_free", "lf_circuit_get_info", "lf_zk_prove_batch",
+    "lf_zk_prove_batch_dev", "lf_zk_debug_fetch", "lf_ctx_launch_count", "lf_microbench",
+]
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB):
+            raise ImportError(
+                f"{LIB} is missing: build it with `python -m longfellow_zk_b200.build` "
+                "(the CUDA extension is mandatory; there is no CPU fallback)")
+        L = C.CDLL(LIB)
+        L.lf_last_error.restype = C.c_char_p
+        L.lf_version.restype = C.c_char_p
+        L.lf_ctx_launch_count.restype = C.c_uint64
+        L.lf_ctx_launch_count.argtypes = [C.c_void_p]
+        L.lf_ctx_create.argtypes = [C.c_int, C.c_void_p, C.POINTER(C.c_void_p)]
+        L.lf_ctx_destroy.argtypes = [C.c_void_p]
+        L.lf_ctx_synchronize.argtypes = [C.c_void_p]
+        L.lf_elt_mul.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]
+        L.lf_rs_interpolate.argtypes = [C.c_void_p, C.c_int, C.c_size_t, C.c_size_t, C.c_void_p,
+                                        C.c_size_t]
+        L.lf_rs_interpolate_dev.argtypes = [C.c_void_p, C.c_int, C.c_size_t, C.c_size_t, C.c_void_p,
+                                            C.c_size_t, C.c_size_t]
+        L.lf_merkle_commit.argtypes = [C.c_void_p, C.c_int, C.c_size_t, C.c_size_t, C.c_size_t,
+                                       C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.lf_circuit_upload.argtypes = [C.c_void_p, C.c_int, C.c_char_p, C.c_size_t, C.c_size_t,
+                                        C.c_size_t, C.c_size_t, C.POINTER(C.c_void_p)]
+        L.lf_circuit_free.argtypes = [C.c_void_p]
+        L.lf_circuit_get_info.argtypes = [C.c_void_p, C.POINTER(CircuitInfo)]
+        L.lf_zk_prove_batch.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_size_t,
+                                        C.c_char_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p,
+                                        C.c_void_p]
+        L.lf_zk_prove_batch_dev.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_size_t,
+                                            C.c_char_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p,
+                                            C.c_void_p]
+        L.lf_zk_debug_fetch.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.c_void_p, C.c_size_t,
+                                        C.POINTER(C.c_size_t)]
+        L.lf_microbench.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_double)]
+        _lib = L
+    return _lib
+
+
+def check(rc):
+    if rc != 0:
+        raise LongfellowError(rc, lib().lf_last_error().decode())

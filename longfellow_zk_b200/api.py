@@ -1,0 +1,161 @@
+"""Host-side mirror of the reference's prover interfaces over the C ABI.
+
+Names and argument meaning follow the reference (lib/):
+  LCH14ReedSolomonFactory.make(n, m).interpolate(y)   gf2k/lch14_reed_solomon.h:112-123
+  MerkleCommitment(n).commit(...)                      merkle/merkle_commitment.h:46-64
+  ZkProver(circuit).prove_batch(...)                   zk/zk_prover.h:72-149 + zk_proof.h:90-112
+Elements are numpy uint8 arrays in the reference's wire encoding.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _native
+from ._native import LongfellowError, check  # noqa: F401
+
+FIELD_P256 = 1
+FIELD_GF2_128 = 4
+KBYTES = {FIELD_P256: 32, FIELD_GF2_128: 16}
+
+
+def _u8(a):
+    return np.ascontiguousarray(a, dtype=np.uint8)
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class Context:
+    """One CUDA device + stream (lf_ctx)."""
+
+    def __init__(self, device=0, stream=None):
+        self._h = C.c_void_p()
+        check(_native.lib().lf_ctx_create(int(device), C.c_void_p(stream) if stream else None,
+                                          C.byref(self._h)))
+
+    def close(self):
+        if self._h:
+            _native.lib().lf_ctx_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def synchronize(self):
+        check(_native.lib().lf_ctx_synchronize(self._h))
+
+    @property
+    def launch_count(self):
+        return int(_native.lib().lf_ctx_launch_count(self._h))
+
+    def elt_mul(self, field_id, a, b):
+        a, b = _u8(a), _u8(b)
+        out = np.empty_like(a)
+        check(_native.lib().lf_elt_mul(self._h, field_id, _p(a), _p(b), _p(out),
+                                       a.size // KBYTES[field_id]))
+        return out
+
+    def microbench(self, what):
+        g = C.c_double()
+        check(_native.lib().lf_microbench(self._h, int(what), C.byref(g)))
+        return g.value
+
+
+class _Interpolator:
+    def __init__(self, ctx, field_id, n, m):
+        self.ctx, self.field_id, self.n, self.m = ctx, field_id, n, m
+
+    def interpolate(self, y):
+        """y: (..., m, kBytes) uint8 with the first n of every row valid; returns
+        the rows extended to m evaluations (the reference works in place)."""
+        y = _u8(y).copy()
+        kb = KBYTES[self.field_id]
+        nrows = y.size // (self.m * kb)
+        check(_native.lib().lf_rs_interpolate(self.ctx._h, self.field_id, self.n, self.m, _p(y), nrows))
+        return y
+
+
+class LCH14ReedSolomonFactory:
+    """gf2k/lch14_reed_solomon.h:112-123 (GF(2^128))."""
+
+    def __init__(self, ctx):
+        self.ctx = ctx
+
+    def make(self, n, m):
+        return _Interpolator(self.ctx, FIELD_GF2_128, n, m)
+
+
+class MerkleCommitment:
+    """merkle/merkle_commitment.h:46-64, specialised to Ligero's column hash
+    (ligero/ligero_param.h:432-439): leaf j = SHA256(nonce_j || column dblock+j)."""
+
+    def __init__(self, ctx, field_id=FIELD_GF2_128):
+        self.ctx, self.field_id = ctx, field_id
+
+    def commit(self, tableau, nrow, block_enc, dblock, nonces, want_nodes=False):
+        tableau, nonces = _u8(tableau), _u8(nonces)
+        root = np.zeros(32, np.uint8)
+        nodes = np.zeros((2 * (block_enc - dblock), 32), np.uint8) if want_nodes else None
+        check(_native.lib().lf_merkle_commit(self.ctx._h, self.field_id, nrow, block_enc, dblock,
+                                             _p(tableau), _p(nonces), _p(root),
+                                             _p(nodes) if want_nodes else None))
+        return (root.tobytes(), nodes) if want_nodes else root.tobytes()
+
+
+class Circuit:
+    """A circuit uploaded to the device (lf_circuit): flattened quads, sumcheck
+    plans and Ligero parameters, shared by every proof of a batch."""
+
+    def __init__(self, ctx, field_id, lfc1_bytes, rate=7, nreq=132, block_enc=0):
+        self.ctx, self.field_id = ctx, field_id
+        self._h = C.c_void_p()
+        check(_native.lib().lf_circuit_upload(ctx._h, field_id, lfc1_bytes, len(lfc1_bytes), rate, nreq,
+                                              block_enc, C.byref(self._h)))
+        info = _native.CircuitInfo()
+        check(_native.lib().lf_circuit_get_info(self._h, C.byref(info)))
+        self.info = {n: int(getattr(info, n)) for n, _ in info._fields_}
+
+    def close(self):
+        if self._h:
+            _native.lib().lf_circuit_free(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class ZkProver:
+    """zk/zk_prover.h:52-198: commit + prove + ZkProof::write for a batch of
+    independent proofs of one circuit."""
+
+    def __init__(self, circuit):
+        self.c = circuit
+
+    def prove_batch(self, witnesses, rng, tinit=b"test"):
+        """witnesses: (B, ninputs*kBytes) uint8; rng: (B, >= rng_bytes) uint8.
+        Returns (list of proof bytes, status array)."""
+        info = self.c.info
+        witnesses, rng = _u8(witnesses), _u8(rng)
+        B = witnesses.shape[0]
+        assert witnesses.shape[1] == info["witness_bytes"], witnesses.shape
+        assert rng.shape[0] == B
+        stride = info["max_proof_bytes"]
+        out = np.zeros((B, stride), np.uint8)
+        lens = np.zeros(B, np.uint64)
+        status = np.zeros(B, np.int32)
+        check(_native.lib().lf_zk_prove_batch(self.c._h, B, _p(witnesses), _p(rng), rng.shape[1], tinit,
+                                              len(tinit), _p(out), stride, _p(lens), _p(status)))
+        return [out[i, :int(lens[i])].tobytes() for i in range(B)], status
+
+    def debug_fetch(self, index, stage, cap=1 << 26):
+        buf = np.zeros(cap, np.uint8)
+        n = C.c_size_t()
+        check(_native.lib().lf_zk_debug_fetch(self.c._h, index, stage, _p(buf), cap, C.byref(n)))
+        return buf[:n.value].copy()

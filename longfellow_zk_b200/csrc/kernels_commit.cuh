@@ -1,0 +1,229 @@
+// Commitment-phase kernels: Reed-Solomon row extension over GF(2^128) (LCH14
+// additive FFT) and the SHA-256 Merkle column commitment.
+//
+//   reference                                   here
+//   LCH14ReedSolomon::interpolate               k_rs_gf_rows
+//     (lib/gf2k/lch14_reed_solomon.h:49-103,
+//      lib/gf2k/lch14.h:106-237)
+//   MerkleCommitment::commit leaf loop          k_merkle_leaves
+//     (lib/merkle/merkle_commitment.h:50-64,
+//      lib/ligero/ligero_param.h:432-439)
+//   MerkleTree::build_tree                      k_merkle_tree
+//     (lib/merkle/merkle_tree.h:109-114)
+#pragma once
+#include <stdint.h>
+
+#include "field.cuh"
+#include "hash.cuh"
+
+namespace lf {
+
+// ---------------------------------------------------------------------------
+// LCH14 twiddles.  The twiddle of the butterfly at global evaluation index p
+// (bit i of p clear) in stage i is  twiddle(i, p with its low i+1 bits cleared)
+// (lch14.h:81-100), which is GF(2)-linear in the index bits, so one table
+//   T_i[u] = sum_{k : bit k of u} w_hat[i][i+1+k],   u < 2^(15-i)
+// serves every FFT size, every coset and the truncated ("bidirectional")
+// transform alike.  T_i starts at offset 65536 - 2^(16-i) of d_tw.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t tw_offset(uint32_t i) { return 65536u - (1u << (16 - i)); }
+
+// One step of the precomputed butterfly schedule of an (n -> m) extension.
+// Butterflies t in [t0,t1) of the step act at local position
+//   q = base + ((t >> stage) << (stage+1)) + (t & ((1<<stage)-1))   and q + 2^stage.
+struct RsStep {
+  uint32_t kind;   // 0 fwd, 1 bwd, 2 diag   (lch14.h:219-237)
+  uint32_t stage;
+  uint32_t base;
+  uint32_t t0, t1;
+};
+
+struct RsPlan {
+  uint32_t n, m, l, fftn;
+  uint32_t nsteps;       // schedule of BidirectionalFFT(l, n) on the first coset
+  const RsStep* steps;   // device
+};
+
+template <class F>
+__device__ __forceinline__ void rs_butterfly(typename F::Elt* B, uint32_t q, uint32_t s, uint32_t kind,
+                                             const typename F::Elt& tw) {
+  typename F::Elt b0 = B[q], b1 = B[q + s];
+  if (kind == 0) {  // fwd
+    b0 = F::add(b0, F::mul(tw, b1));
+    b1 = F::add(b1, b0);
+  } else if (kind == 1) {  // bwd
+    b1 = F::sub(b1, b0);
+    b0 = F::sub(b0, F::mul(tw, b1));
+  } else {  // diag: forward at [q+s], backward at [q]
+    typename F::Elt t = b1;
+    b1 = F::add(b1, b0);
+    b0 = F::sub(b0, F::mul(tw, t));
+  }
+  B[q] = b0;
+  B[q + s] = b1;
+}
+
+// One CTA extends one row: y[0..n) given, y[n..m) produced.  rows are
+// `row_stride` elements apart; blockIdx.y selects the batch instance
+// (batch_stride elements apart).  Dynamic shared memory: 2 * fftn elements.
+template <class F>
+__global__ void __launch_bounds__(256)
+k_rs_gf_rows(typename F::Elt* __restrict__ data, size_t row_stride, size_t batch_stride, RsPlan plan,
+             const typename F::Elt* __restrict__ d_tw) {
+  typedef typename F::Elt Elt;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  Elt* C = reinterpret_cast<Elt*>(smem_raw);
+  Elt* D = C + plan.fftn;
+  Elt* y = data + (size_t)blockIdx.y * batch_stride + (size_t)blockIdx.x * row_stride;
+  const uint32_t n = plan.n, m = plan.m, l = plan.l, fftn = plan.fftn;
+
+  for (uint32_t i = threadIdx.x; i < fftn; i += blockDim.x) C[i] = (i < n) ? y[i] : F::zero();
+  __syncthreads();
+
+  // truncated transform on the first coset (lch14.h:185-217), flattened into
+  // a host-generated schedule: after it C[0..n) are novel-basis coefficients
+  // and C[n..fftn) the missing evaluations.
+  for (uint32_t s = 0; s < plan.nsteps; ++s) {
+    const RsStep st = plan.steps[s];
+    const uint32_t half = 1u << st.stage;
+    for (uint32_t t = st.t0 + threadIdx.x; t < st.t1; t += blockDim.x) {
+      uint32_t q = st.base + ((t >> st.stage) << (st.stage + 1)) + (t & (half - 1));
+      Elt tw = d_tw[tw_offset(st.stage) + (q >> (st.stage + 1))];
+      rs_butterfly<F>(C, q, half, st.kind, tw);
+    }
+    __syncthreads();
+  }
+  for (uint32_t i = n + threadIdx.x; i < fftn && i < m; i += blockDim.x) y[i] = C[i];
+  __syncthreads();
+  for (uint32_t i = n + threadIdx.x; i < fftn; i += blockDim.x) C[i] = F::zero();
+  __syncthreads();
+
+  // remaining cosets: forward FFT of the coefficients at offset b (lch14.h:106-123)
+  for (uint32_t b = fftn; b < m; b += fftn) {
+    for (uint32_t i = threadIdx.x; i < fftn; i += blockDim.x) D[i] = C[i];
+    __syncthreads();
+    for (uint32_t st = l; st-- > 0;) {
+      const uint32_t half = 1u << st;
+      for (uint32_t t = threadIdx.x; t < fftn / 2; t += blockDim.x) {
+        uint32_t q = ((t >> st) << (st + 1)) + (t & (half - 1));
+        Elt tw = d_tw[tw_offset(st) + ((b + q) >> (st + 1))];
+        rs_butterfly<F>(D, q, half, 0, tw);
+      }
+      __syncthreads();
+    }
+    for (uint32_t i = threadIdx.x; i < fftn && b + i < m; i += blockDim.x) y[b + i] = D[i];
+    __syncthreads();
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Merkle leaves: one thread per (instance, column).  leaf_j =
+// SHA256(nonce_j || bytes(T[0][dblock+j]) || ... || bytes(T[nrow-1][dblock+j])).
+// A warp reads 32 consecutive elements of a row: 128-bit coalesced loads.
+// ---------------------------------------------------------------------------
+template <class F>
+__global__ void __launch_bounds__(128)
+k_merkle_leaves(const typename F::Elt* __restrict__ tableau, size_t tab_batch_stride, uint32_t nrow,
+                uint32_t block_enc, uint32_t dblock, uint32_t block_ext,
+                const uint8_t* __restrict__ nonces, size_t nonce_batch_stride,
+                uint32_t* __restrict__ nodes /* [batch][2*block_ext][8] big-endian digest words */,
+                size_t nodes_batch_stride) {
+  uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= block_ext) return;
+  const typename F::Elt* T = tableau + (size_t)blockIdx.y * tab_batch_stride + dblock + j;
+  const uint32_t* nz = reinterpret_cast<const uint32_t*>(nonces + (size_t)blockIdx.y * nonce_batch_stride + 32ull * j);
+  uint32_t h[8], w[16];
+  sha256_iv(h);
+#pragma unroll
+  for (int k = 0; k < 8; ++k) w[k] = bswap32(nz[k]);
+  constexpr int EW = F::kWords;        // words per element
+  constexpr int PER = 16 / EW;         // elements per 64-byte block
+  uint32_t pos = 8;                    // words filled in w (always a multiple of EW)
+  uint64_t total = 32 + (uint64_t)nrow * F::kBytes;
+  uint32_t i = 0;
+  // first block: nonce + (8/EW) elements
+  {
+#pragma unroll
+    for (int e = 0; e < 8 / EW; ++e) {
+      if (i < nrow) {
+        uint32_t ww[EW];
+        F::to_wire(ww, T[(size_t)i * block_enc]);
+#pragma unroll
+        for (int k = 0; k < EW; ++k) w[8 + e * EW + k] = bswap32(ww[k]);
+        ++i;
+        pos += EW;
+      }
+    }
+  }
+  while (pos == 16) {
+    sha256_compress(h, w);
+    pos = 0;
+#pragma unroll
+    for (int e = 0; e < PER; ++e) {
+      if (i < nrow) {
+        uint32_t ww[EW];
+        F::to_wire(ww, T[(size_t)i * block_enc]);
+#pragma unroll
+        for (int k = 0; k < EW; ++k) w[e * EW + k] = bswap32(ww[k]);
+        ++i;
+        pos += EW;
+      }
+    }
+  }
+  // padding: pos in {0, EW, .., 16-EW} words are valid
+#pragma unroll
+  for (int k = 0; k < 16; ++k)
+    if ((uint32_t)k >= pos) w[k] = 0;
+#pragma unroll
+  for (int k = 0; k < 16; ++k)
+    if ((uint32_t)k == pos) w[k] = 0x80000000u;
+  if (pos >= 14) {
+    sha256_compress(h, w);
+#pragma unroll
+    for (int k = 0; k < 16; ++k) w[k] = 0;
+  }
+  w[14] = (uint32_t)((total * 8) >> 32);
+  w[15] = (uint32_t)(total * 8);
+  sha256_compress(h, w);
+  uint32_t* out = nodes + (size_t)blockIdx.y * nodes_batch_stride + 8ull * (block_ext + j);
+#pragma unroll
+  for (int k = 0; k < 8; ++k) out[k] = h[k];
+}
+
+// node i = SHA256(node 2i || node 2i+1); digests kept as 8 big-endian words
+__device__ __forceinline__ void merkle_hash2(uint32_t* __restrict__ nodes, uint32_t i) {
+  uint32_t h[8], w[16];
+  sha256_iv(h);
+  const uint4* c = reinterpret_cast<const uint4*>(nodes + 16ull * i);
+  uint4 a0 = c[0], a1 = c[1], a2 = c[2], a3 = c[3];
+  w[0] = a0.x; w[1] = a0.y; w[2] = a0.z; w[3] = a0.w;
+  w[4] = a1.x; w[5] = a1.y; w[6] = a1.z; w[7] = a1.w;
+  w[8] = a2.x; w[9] = a2.y; w[10] = a2.z; w[11] = a2.w;
+  w[12] = a3.x; w[13] = a3.y; w[14] = a3.z; w[15] = a3.w;
+  sha256_compress(h, w);
+  w[0] = 0x80000000u;
+#pragma unroll
+  for (int k = 1; k < 15; ++k) w[k] = 0;
+  w[15] = 512;
+  sha256_compress(h, w);
+  uint4* o = reinterpret_cast<uint4*>(nodes + 8ull * i);
+  o[0] = make_uint4(h[0], h[1], h[2], h[3]);
+  o[1] = make_uint4(h[4], h[5], h[6], h[7]);
+}
+
+// One CTA per instance walks the heap level by level (arbitrary n: the nodes
+// of one level are i in [2^d, 2^(d+1)) below n; their children are either
+// deeper inner nodes or leaves).
+__global__ void __launch_bounds__(256)
+k_merkle_tree(uint32_t* __restrict__ nodes, size_t nodes_batch_stride, uint32_t n) {
+  uint32_t* N = nodes + (size_t)blockIdx.x * nodes_batch_stride;
+  if (n < 2) return;
+  int top = 31 - __clz(n - 1);  // deepest level that has an inner node
+  for (int d = top; d >= 0; --d) {
+    uint32_t lo = 1u << d, hi = min(2u << d, n);
+    for (uint32_t i = lo + threadIdx.x; i < hi; i += blockDim.x) merkle_hash2(N, i);
+    __syncthreads();
+  }
+}
+
+}  // namespace lf

@@ -1,0 +1,482 @@
+// liblongfellow_b200.so -- single translation unit: device kernels + host
+// engine + C ABI (include/longfellow_b200.h).  No CPU fallback: every compute
+// entry point needs a CUDA device.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <map>
+#include <memory>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "../../include/longfellow_b200.h"
+#include "field.cuh"
+#include "hash.cuh"
+#include "kernels_commit.cuh"
+
+namespace lf {
+
+// ---------------------------------------------------------------- errors
+static thread_local std::string g_err;
+static int fail(int code, const std::string& msg) {
+  g_err = msg;
+  return code;
+}
+#define LF_CUDA(expr)                                                                    \
+  do {                                                                                   \
+    cudaError_t e__ = (expr);                                                            \
+    if (e__ != cudaSuccess)                                                              \
+      return fail(LF_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e__));     \
+  } while (0)
+
+// ---------------------------------------------------------------- GF host tables
+// All computed with the same gf128.cuh code the kernels run.
+struct GfHost {
+  gf128 g;
+  gf128 beta[16];
+  gf128 what[16][16];
+  GfConsts consts;
+  std::vector<gf128> tw;  // 65535 twiddles, see kernels_commit.cuh
+
+  GfHost() {
+    // gf2_128.h:369-391 subfield_generator
+    gf128 x = gf_zero();
+    x.w[0] = 2;
+    gf128 r = x;
+    for (int i = 4; i < 7; ++i) {
+      gf128 s = r;
+      for (int j = 0; j < (1 << i); ++j) s = gf_mul(s, s);
+      r = gf_mul(r, s);
+    }
+    g = r;
+    beta[0] = gf_one();
+    for (int i = 1; i < 16; ++i) beta[i] = gf_mul(beta[i - 1], g);
+    memset(&consts, 0, sizeof(consts));
+    for (int i = 0; i < 16; ++i) consts.beta[i] = beta[i];
+    // gf2_128.h:451-493 beta_ref
+    uint32_t u[16][4];
+    uint32_t linv[16];
+    for (int i = 0; i < 16; ++i) {
+      for (int k = 0; k < 4; ++k) u[i][k] = beta[i].w[k];
+      linv[i] = 1u << i;
+    }
+    auto bit = [](const uint32_t* v, int j) { return (v[j >> 5] >> (j & 31)) & 1u; };
+    int rnk = 0;
+    for (int j = 0; rnk < 16 && j < 128; ++j) {
+      int piv = -1;
+      for (int i = rnk; i < 16; ++i)
+        if (bit(u[i], j)) {
+          piv = i;
+          break;
+        }
+      if (piv < 0) continue;
+      for (int k = 0; k < 4; ++k) std::swap(u[rnk][k], u[piv][k]);
+      std::swap(linv[rnk], linv[piv]);
+      consts.sub_ldnz[rnk] = (uint32_t)j;
+      for (int i1 = rnk + 1; i1 < 16; ++i1)
+        if (bit(u[i1], j)) {
+          for (int k = 0; k < 4; ++k) u[i1][k] ^= u[rnk][k];
+          linv[i1] ^= linv[rnk];
+        }
+      ++rnk;
+    }
+    for (int i = 0; i < 16; ++i) {
+      for (int k = 0; k < 4; ++k) consts.sub_u[i][k] = u[i][k];
+      consts.sub_linv[i] = linv[i];
+    }
+    // gf2_128.h:121-137 evaluation points 0, 1, g and Newton denominators
+    consts.evalpt[0] = gf_zero();
+    consts.evalpt[1] = gf_one();
+    consts.evalpt[2] = g;
+    for (int i = 1; i < 3; ++i)
+      for (int k = 2; k >= i; --k)
+        consts.newton[k][i] = gf_inv(gf_add(consts.evalpt[k], consts.evalpt[k - i]));
+    // poly.h:125-137 dot_interpolation identity_[k] (Newton form of Lagrange basis)
+    for (int k = 0; k < 3; ++k) {
+      gf128 t[3] = {gf_zero(), gf_zero(), gf_zero()};
+      t[k] = gf_one();
+      for (int i = 1; i < 3; ++i)
+        for (int kk = 2; kk >= i; --kk) t[kk] = gf_mul(gf_add(t[kk], t[kk - 1]), consts.newton[kk][i]);
+      for (int i = 0; i < 3; ++i) consts.lag_id[k][i] = t[i];
+    }
+    // lch14.h:45-77 w_hat
+    for (int j = 0; j < 16; ++j) what[0][j] = beta[j];
+    for (int i = 0; i + 1 < 16; ++i)
+      for (int j = 0; j < 16; ++j) what[i + 1][j] = gf_mul(what[i][j], gf_add(what[i][j], what[i][i]));
+    for (int i = 0; i < 16; ++i) {
+      gf128 sc = gf_inv(what[i][i]);
+      for (int j = 0; j < 16; ++j) what[i][j] = gf_mul(sc, what[i][j]);
+    }
+    // T_i[u] = sum_k bit_k(u) w_hat[i][i+1+k]   (lch14.h:81-100)
+    tw.assign(65536, gf_zero());
+    for (uint32_t i = 0; i < 16; ++i) {
+      uint32_t off = 65536u - (1u << (16 - i));
+      uint32_t cnt = 1u << (15 - i);
+      tw[off] = gf_zero();
+      for (uint32_t v = 1; v < cnt; ++v) {
+        uint32_t low = v & (0u - v);
+        uint32_t k = (uint32_t)__builtin_ctz(low);
+        tw[off + v] = gf_add(tw[off + (v ^ low)], what[i][i + 1 + k]);
+      }
+    }
+  }
+};
+static const GfHost& gf_host() {
+  static const GfHost h;
+  return h;
+}
+
+// LCH14 BidirectionalFFT(l, k) flattened into butterfly steps (lch14.h:185-217)
+static void emit(std::vector<RsStep>& out, uint32_t kind, uint32_t stage, uint32_t base, uint32_t t0,
+                 uint32_t t1) {
+  if (t0 < t1) out.push_back(RsStep{kind, stage, base, t0, t1});
+}
+static void gen_bidir(std::vector<RsStep>& out, uint32_t i, uint32_t base, uint32_t k) {
+  if (i-- > 0) {
+    uint32_t s = 1u << i;
+    if (k < s) {
+      emit(out, 0, i, base, k, s);
+      gen_bidir(out, i, base, k);
+      emit(out, 2, i, base, 0, k);
+      for (uint32_t j = i; j-- > 0;) emit(out, 0, j, base + s, 0, s / 2);  // FFT(i, coset+s, B+s)
+    } else {
+      for (uint32_t j = 0; j < i; ++j) emit(out, 1, j, base, 0, s / 2);  // IFFT(i, coset, B)
+      emit(out, 2, i, base, k - s, s);
+      gen_bidir(out, i, base + s, k - s);
+      emit(out, 1, i, base, 0, k - s);
+    }
+  }
+}
+
+struct RsPlanHost {
+  RsPlan plan;
+  RsStep* d_steps = nullptr;
+};
+
+}  // namespace lf
+
+using namespace lf;
+
+// ---------------------------------------------------------------- context
+struct lf_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  gf128* d_tw = nullptr;
+  std::map<std::pair<size_t, size_t>, RsPlanHost> rs_plans;
+  uint64_t launches = 0;
+  int sm_count = 0;
+};
+
+namespace lf {
+
+static int ctx_rs_plan(lf_ctx* ctx, size_t n, size_t m, RsPlanHost** out) {
+  auto key = std::make_pair(n, m);
+  auto it = ctx->rs_plans.find(key);
+  if (it == ctx->rs_plans.end()) {
+    RsPlanHost ph;
+    uint32_t l = 0, fftn = 1;
+    while (fftn < n) {
+      fftn <<= 1;
+      ++l;
+    }
+    std::vector<RsStep> steps;
+    gen_bidir(steps, l, 0, (uint32_t)n);
+    ph.plan.n = (uint32_t)n;
+    ph.plan.m = (uint32_t)m;
+    ph.plan.l = l;
+    ph.plan.fftn = fftn;
+    ph.plan.nsteps = (uint32_t)steps.size();
+    if (!steps.empty()) {
+      LF_CUDA(cudaMalloc(&ph.d_steps, steps.size() * sizeof(RsStep)));
+      LF_CUDA(cudaMemcpyAsync(ph.d_steps, steps.data(), steps.size() * sizeof(RsStep),
+                              cudaMemcpyHostToDevice, ctx->stream));
+      LF_CUDA(cudaStreamSynchronize(ctx->stream));
+    }
+    ph.plan.steps = ph.d_steps;
+    it = ctx->rs_plans.emplace(key, ph).first;
+  }
+  *out = &it->second;
+  return 0;
+}
+
+// rows: device, GF(2^128).  grid = (nrows, nbatch)
+static int launch_rs_gf(lf_ctx* ctx, gf128* d_rows, size_t row_stride, size_t nrows, size_t batch_stride,
+                        size_t nbatch, size_t n, size_t m) {
+  if (n == 0 || m < n || m > 65536) return fail(LF_ERR_ARG, "rs: need 0 < n <= m <= 65536");
+  if (nrows == 0 || nbatch == 0 || m == n) return 0;
+  RsPlanHost* ph;
+  int rc = ctx_rs_plan(ctx, n, m, &ph);
+  if (rc) return rc;
+  size_t smem = 2 * (size_t)ph->plan.fftn * sizeof(gf128);
+  if (smem > 200 * 1024) return fail(LF_ERR_UNSUPPORTED, "rs: n > 4096 over GF(2^128) not built yet");
+  static bool attr_set = false;
+  if (!attr_set) {
+    LF_CUDA(cudaFuncSetAttribute(k_rs_gf_rows<FGf128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 200 * 1024));
+    attr_set = true;
+  }
+  dim3 grid((unsigned)nrows, (unsigned)nbatch);
+  k_rs_gf_rows<FGf128><<<grid, 256, smem, ctx->stream>>>(d_rows, row_stride, batch_stride, ph->plan,
+                                                         ctx->d_tw);
+  ctx->launches++;
+  LF_CUDA(cudaGetLastError());
+  return 0;
+}
+
+static int launch_merkle_gf(lf_ctx* ctx, const gf128* d_tab, size_t tab_batch_stride, uint32_t nrow,
+                            uint32_t block_enc, uint32_t dblock, const uint8_t* d_nonces,
+                            size_t nonce_batch_stride, uint32_t* d_nodes, size_t nodes_batch_stride,
+                            size_t nbatch) {
+  uint32_t block_ext = block_enc - dblock;
+  dim3 grid((block_ext + 127) / 128, (unsigned)nbatch);
+  k_merkle_leaves<FGf128><<<grid, 128, 0, ctx->stream>>>(d_tab, tab_batch_stride, nrow, block_enc, dblock,
+                                                         block_ext, d_nonces, nonce_batch_stride, d_nodes,
+                                                         nodes_batch_stride);
+  ctx->launches++;
+  LF_CUDA(cudaGetLastError());
+  k_merkle_tree<<<(unsigned)nbatch, 256, 0, ctx->stream>>>(d_nodes, nodes_batch_stride, block_ext);
+  ctx->launches++;
+  LF_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ---------------------------------------------------------------- micro kernels
+template <class F>
+__global__ void k_elt_mul(const typename F::Elt* a, const typename F::Elt* b, typename F::Elt* out,
+                          size_t n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = F::mul(a[i], b[i]);
+}
+
+__global__ void k_bench_imad(uint64_t* out, int iters) {
+  uint32_t a = threadIdx.x * 2654435761u + 1, b = blockIdx.x * 40503u + 7;
+  uint64_t acc0 = a, acc1 = b, acc2 = a ^ b, acc3 = a + b;
+  for (int i = 0; i < iters; ++i) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      acc0 = (uint64_t)(uint32_t)acc0 * b + acc0;
+      acc1 = (uint64_t)(uint32_t)acc1 * a + acc1;
+      acc2 = (uint64_t)(uint32_t)acc2 * b + acc2;
+      acc3 = (uint64_t)(uint32_t)acc3 * a + acc3;
+    }
+  }
+  out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = acc0 ^ acc1 ^ acc2 ^ acc3;
+}
+__global__ void k_bench_lop3(uint32_t* out, int iters) {
+  uint32_t a = threadIdx.x * 2654435761u + 1, b = blockIdx.x * 40503u + 7, c = a ^ 0x5bd1e995u;
+  uint32_t x0 = a, x1 = b, x2 = c, x3 = a + b;
+  for (int i = 0; i < iters; ++i) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      x0 = (x0 & x1) ^ (~x0 & x2) ^ b;
+      x1 = (x1 & x2) ^ (~x1 & x3) ^ c;
+      x2 = (x2 & x3) ^ (~x2 & x0) ^ a;
+      x3 = (x3 & x0) ^ (~x3 & x1) ^ b;
+    }
+  }
+  out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = x0 ^ x1 ^ x2 ^ x3;
+}
+__global__ void k_bench_gfmul(gf128* out, int iters) {
+  gf128 a, b;
+  a.w[0] = threadIdx.x * 2654435761u + 1; a.w[1] = blockIdx.x + 3; a.w[2] = 0x9e3779b9u; a.w[3] = threadIdx.x;
+  b.w[0] = 0x85ebca6bu; b.w[1] = threadIdx.x ^ 0xc2b2ae35u; b.w[2] = blockIdx.x; b.w[3] = 0x27d4eb2fu;
+  for (int i = 0; i < iters; ++i) {
+    a = gf_mul(a, b);
+    b = gf_mul(b, a);
+  }
+  out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = gf_add(a, b);
+}
+__global__ void k_bench_sha(uint32_t* out, int iters) {
+  uint32_t h[8], w[16];
+  sha256_iv(h);
+  for (int i = 0; i < iters; ++i) {
+#pragma unroll
+    for (int k = 0; k < 16; ++k) w[k] = h[k & 7] + threadIdx.x + k;
+    sha256_compress(h, w);
+  }
+  out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = h[0] ^ h[7];
+}
+
+}  // namespace lf
+
+// ================================================================ C ABI
+extern "C" {
+
+const char* lf_last_error(void) { return g_err.c_str(); }
+const char* lf_version(void) { return "longfellow_b200 0.1 (sm_100a)"; }
+
+int lf_ctx_create(int device, void* stream, lf_ctx** out) {
+  if (!out) return fail(LF_ERR_ARG, "lf_ctx_create: out is null");
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    return fail(LF_ERR_CUDA, std::string("no CUDA device: ") + cudaGetErrorString(e) +
+                                 " (this library has no CPU fallback)");
+  if (device < 0 || device >= ndev) return fail(LF_ERR_ARG, "lf_ctx_create: bad device ordinal");
+  LF_CUDA(cudaSetDevice(device));
+  std::unique_ptr<lf_ctx> c(new lf_ctx);
+  c->device = device;
+  if (stream) {
+    c->stream = (cudaStream_t)stream;
+  } else {
+    LF_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    c->own_stream = true;
+  }
+  LF_CUDA(cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device));
+  const GfHost& h = gf_host();
+  LF_CUDA(cudaMalloc(&c->d_tw, h.tw.size() * sizeof(gf128)));
+  LF_CUDA(cudaMemcpy(c->d_tw, h.tw.data(), h.tw.size() * sizeof(gf128), cudaMemcpyHostToDevice));
+  LF_CUDA(cudaMemcpyToSymbol(c_gf, &h.consts, sizeof(GfConsts)));
+  *out = c.release();
+  return 0;
+}
+
+void lf_ctx_destroy(lf_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  for (auto& kv : ctx->rs_plans) cudaFree(kv.second.d_steps);
+  cudaFree(ctx->d_tw);
+  if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+int lf_ctx_synchronize(lf_ctx* ctx) {
+  if (!ctx) return fail(LF_ERR_ARG, "null ctx");
+  LF_CUDA(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+uint64_t lf_ctx_launch_count(const lf_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int lf_elt_mul(lf_ctx* ctx, int field_id, const void* a, const void* b, void* out, size_t n) {
+  if (!ctx || !a || !b || !out) return fail(LF_ERR_ARG, "lf_elt_mul: null argument");
+  if (field_id != LF_FIELD_GF2_128) return fail(LF_ERR_UNSUPPORTED, "lf_elt_mul: field not built yet");
+  if (n == 0) return 0;
+  LF_CUDA(cudaSetDevice(ctx->device));
+  gf128 *da, *db, *dc;
+  LF_CUDA(cudaMalloc(&da, n * 16));
+  LF_CUDA(cudaMalloc(&db, n * 16));
+  LF_CUDA(cudaMalloc(&dc, n * 16));
+  LF_CUDA(cudaMemcpyAsync(da, a, n * 16, cudaMemcpyHostToDevice, ctx->stream));
+  LF_CUDA(cudaMemcpyAsync(db, b, n * 16, cudaMemcpyHostToDevice, ctx->stream));
+  k_elt_mul<FGf128><<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(da, db, dc, n);
+  ctx->launches++;
+  LF_CUDA(cudaGetLastError());
+  LF_CUDA(cudaMemcpyAsync(out, dc, n * 16, cudaMemcpyDeviceToHost, ctx->stream));
+  LF_CUDA(cudaStreamSynchronize(ctx->stream));
+  cudaFree(da);
+  cudaFree(db);
+  cudaFree(dc);
+  return 0;
+}
+
+int lf_rs_interpolate_dev(lf_ctx* ctx, int field_id, size_t n, size_t m, void* d_rows, size_t row_stride,
+                          size_t nrows) {
+  if (!ctx || !d_rows) return fail(LF_ERR_ARG, "lf_rs_interpolate_dev: null argument");
+  if (field_id != LF_FIELD_GF2_128) return fail(LF_ERR_UNSUPPORTED, "rs: field not built yet");
+  if (row_stride < m) return fail(LF_ERR_ARG, "rs: row_stride < m");
+  LF_CUDA(cudaSetDevice(ctx->device));
+  return launch_rs_gf(ctx, (gf128*)d_rows, row_stride, nrows, 0, 1, n, m);
+}
+
+int lf_rs_interpolate(lf_ctx* ctx, int field_id, size_t n, size_t m, void* rows, size_t nrows) {
+  if (!ctx || !rows) return fail(LF_ERR_ARG, "lf_rs_interpolate: null argument");
+  if (field_id != LF_FIELD_GF2_128) return fail(LF_ERR_UNSUPPORTED, "rs: field not built yet");
+  if (nrows == 0) return 0;
+  LF_CUDA(cudaSetDevice(ctx->device));
+  size_t bytes = nrows * m * 16;
+  gf128* d;
+  LF_CUDA(cudaMalloc(&d, bytes));
+  LF_CUDA(cudaMemcpyAsync(d, rows, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  int rc = launch_rs_gf(ctx, d, m, nrows, 0, 1, n, m);
+  if (rc == 0) {
+    LF_CUDA(cudaMemcpyAsync(rows, d, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    LF_CUDA(cudaStreamSynchronize(ctx->stream));
+  }
+  cudaFree(d);
+  return rc;
+}
+
+int lf_merkle_commit(lf_ctx* ctx, int field_id, size_t nrow, size_t block_enc, size_t dblock,
+                     const void* tableau, const uint8_t* nonces, uint8_t root_out[32], uint8_t* nodes_out) {
+  if (!ctx || !tableau || !nonces || !root_out) return fail(LF_ERR_ARG, "lf_merkle_commit: null argument");
+  if (field_id != LF_FIELD_GF2_128) return fail(LF_ERR_UNSUPPORTED, "merkle: field not built yet");
+  if (block_enc <= dblock || nrow == 0) return fail(LF_ERR_ARG, "merkle: need block_enc > dblock, nrow > 0");
+  LF_CUDA(cudaSetDevice(ctx->device));
+  size_t block_ext = block_enc - dblock;
+  gf128* d_tab;
+  uint8_t* d_nonce;
+  uint32_t* d_nodes;
+  LF_CUDA(cudaMalloc(&d_tab, nrow * block_enc * 16));
+  LF_CUDA(cudaMalloc(&d_nonce, block_ext * 32));
+  LF_CUDA(cudaMalloc(&d_nodes, 2 * block_ext * 32));
+  LF_CUDA(cudaMemsetAsync(d_nodes, 0, 2 * block_ext * 32, ctx->stream));
+  LF_CUDA(cudaMemcpyAsync(d_tab, tableau, nrow * block_enc * 16, cudaMemcpyHostToDevice, ctx->stream));
+  LF_CUDA(cudaMemcpyAsync(d_nonce, nonces, block_ext * 32, cudaMemcpyHostToDevice, ctx->stream));
+  int rc = launch_merkle_gf(ctx, d_tab, 0, (uint32_t)nrow, (uint32_t)block_enc, (uint32_t)dblock, d_nonce,
+                            0, d_nodes, 0, 1);
+  if (rc == 0) {
+    std::vector<uint32_t> nodes(2 * block_ext * 8);
+    LF_CUDA(cudaMemcpyAsync(nodes.data(), d_nodes, nodes.size() * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    LF_CUDA(cudaStreamSynchronize(ctx->stream));
+    // digests are kept as big-endian words on the device
+    auto put = [&](uint8_t* dst, size_t node) {
+      for (int k = 0; k < 8; ++k) {
+        uint32_t x = nodes[8 * node + k];
+        dst[4 * k] = (uint8_t)(x >> 24);
+        dst[4 * k + 1] = (uint8_t)(x >> 16);
+        dst[4 * k + 2] = (uint8_t)(x >> 8);
+        dst[4 * k + 3] = (uint8_t)x;
+      }
+    };
+    put(root_out, block_ext == 1 ? 1 : 1);
+    if (nodes_out)
+      for (size_t i = 0; i < 2 * block_ext; ++i) put(nodes_out + 32 * i, i);
+  }
+  cudaFree(d_tab);
+  cudaFree(d_nonce);
+  cudaFree(d_nodes);
+  return rc;
+}
+
+int lf_microbench(lf_ctx* ctx, int what, double* gops) {
+  if (!ctx || !gops) return fail(LF_ERR_ARG, "lf_microbench: null argument");
+  LF_CUDA(cudaSetDevice(ctx->device));
+  const int blocks = ctx->sm_count * 8, threads = 256;
+  void* d;
+  LF_CUDA(cudaMalloc(&d, (size_t)blocks * threads * 16));
+  cudaEvent_t e0, e1;
+  LF_CUDA(cudaEventCreate(&e0));
+  LF_CUDA(cudaEventCreate(&e1));
+  int iters = what == 0 ? 4096 : what == 1 ? 4096 : what == 2 ? 256 : 256;
+  double ops_per_thread = what == 0 ? 32.0 * iters : what == 1 ? 32.0 * 3 * iters : what == 2 ? 2.0 * iters : 1.0 * iters;
+  float best = 1e30f;
+  for (int rep = 0; rep < 4; ++rep) {
+    LF_CUDA(cudaEventRecord(e0, ctx->stream));
+    if (what == 0) k_bench_imad<<<blocks, threads, 0, ctx->stream>>>((uint64_t*)d, iters);
+    else if (what == 1) k_bench_lop3<<<blocks, threads, 0, ctx->stream>>>((uint32_t*)d, iters);
+    else if (what == 2) k_bench_gfmul<<<blocks, threads, 0, ctx->stream>>>((gf128*)d, iters);
+    else if (what == 3) k_bench_sha<<<blocks, threads, 0, ctx->stream>>>((uint32_t*)d, iters);
+    else return fail(LF_ERR_ARG, "lf_microbench: unknown benchmark");
+    ctx->launches++;
+    LF_CUDA(cudaEventRecord(e1, ctx->stream));
+    LF_CUDA(cudaEventSynchronize(e1));
+    float ms;
+    LF_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    if (rep > 0 && ms < best) best = ms;
+  }
+  *gops = ops_per_thread * blocks * threads / (best * 1e-3) / 1e9;
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(d);
+  return 0;
+}
+
+}  // extern "C"
+#include "zk_stub.inc"

@@ -1,0 +1,83 @@
+// Host-side unit check of the header-only device primitives (gf128.cuh,
+// hash.cuh compiled as plain C++).  Reads test vectors on stdin, writes results
+// on stdout; driven by tests/test_device_primitives_host.py which compares the
+// output with the oracle.  This exercises the SAME source the kernels compile,
+// here on the CPU where there is no GPU to debug on.
+#define __host__
+#define __device__
+#define __forceinline__ inline
+#define LF_HD
+#include <cstdio>
+#include <cstring>
+#include <vector>
+
+#include "../../longfellow_zk_b200/csrc/gf128.cuh"
+#include "../../longfellow_zk_b200/csrc/hash.cuh"
+
+using namespace lf;
+
+int main(int argc, char** argv) {
+  if (argc < 2) return 2;
+  std::vector<uint8_t> in;
+  uint8_t tmp[4096];
+  size_t k;
+  while ((k = fread(tmp, 1, sizeof(tmp), stdin)) > 0) in.insert(in.end(), tmp, tmp + k);
+  if (!strcmp(argv[1], "gfmul")) {  // pairs of 16-byte elements -> products
+    for (size_t i = 0; i + 32 <= in.size(); i += 32) {
+      gf128 a, b;
+      memcpy(a.w, &in[i], 16);
+      memcpy(b.w, &in[i + 16], 16);
+      gf128 c = gf_mul(a, b);
+      fwrite(c.w, 1, 16, stdout);
+    }
+  } else if (!strcmp(argv[1], "gfinv")) {
+    for (size_t i = 0; i + 16 <= in.size(); i += 16) {
+      gf128 a;
+      memcpy(a.w, &in[i], 16);
+      gf128 c = gf_inv(a);
+      fwrite(c.w, 1, 16, stdout);
+    }
+  } else if (!strcmp(argv[1], "sha")) {  // digest of stdin
+    Sha256 s;
+    s.init();
+    s.update(in.data(), (uint32_t)in.size());
+    uint32_t d[8];
+    s.snapshot(d);
+    for (int i = 0; i < 8; ++i) {
+      uint32_t x = bswap32(d[i]);
+      fwrite(&x, 1, 4, stdout);
+    }
+  } else if (!strcmp(argv[1], "aes")) {  // key(32) || blocks
+    Aes256 a;
+    uint32_t key[8];
+    memcpy(key, in.data(), 32);
+    a.init(key);
+    for (size_t i = 32; i + 16 <= in.size(); i += 16) {
+      uint32_t x[4], y[4];
+      memcpy(x, &in[i], 16);
+      a.encrypt(x, y);
+      fwrite(y, 1, 16, stdout);
+    }
+  } else if (!strcmp(argv[1], "transcript")) {
+    // same script language as oracle (GF(2^128) elements); init = "test"
+    Transcript t;
+    t.init((const uint8_t*)"test", 4);
+    size_t p = 0;
+    auto rd32 = [&]() { uint32_t v; memcpy(&v, &in[p], 4); p += 4; return v; };
+    while (p < in.size()) {
+      char op = (char)in[p++];
+      if (op == 'B') { uint32_t n = rd32(); t.write_bytes(&in[p], n); p += n; }
+      else if (op == 'Z') { t.write0(rd32()); }
+      else if (op == 'E') { uint32_t w[4]; memcpy(w, &in[p], 16); p += 16; t.write_elt_words(w, 4); }
+      else if (op == 'A') { uint32_t n = rd32(); t.begin_array(n);
+        for (uint32_t i = 0; i < n; ++i) { uint32_t w[4]; memcpy(w, &in[p], 16); p += 16; t.elt_words(w, 4); } }
+      else if (op == 'R') { uint32_t n = rd32(); std::vector<uint8_t> o(n); t.bytes(o.data(), n); fwrite(o.data(), 1, n, stdout); }
+      else if (op == 'N') { uint32_t r = t.nat(rd32()); fwrite(&r, 1, 4, stdout); }
+      else if (op == 'G') { uint32_t n = rd32(); for (uint32_t i = 0; i < n; ++i) { uint32_t w[4]; t.words(w, 4); fwrite(w, 1, 16, stdout); } }
+      else return 3;
+    }
+  } else {
+    return 2;
+  }
+  return 0;
+}
