@@ -54,6 +54,10 @@ struct FGf128 {
   __host__ __device__ static __forceinline__ void mac(Acc& a, const Elt& x, const Elt& y) {
     gf_mac(a.t, x, y);
   }
+  // a += x (an element, i.e. x * 1)
+  __host__ __device__ static __forceinline__ void acc_add_elt(Acc& a, const Elt& x) {
+    a.t[0] ^= x.w[0]; a.t[1] ^= x.w[1]; a.t[2] ^= x.w[2]; a.t[3] ^= x.w[3];
+  }
   __host__ __device__ static __forceinline__ void acc_add(Acc& a, const Acc& b) {
 #pragma unroll
     for (int i = 0; i < 8; ++i) a.t[i] ^= b.t[i];

@@ -131,11 +131,19 @@ k_merkle_leaves(const typename F::Elt* __restrict__ tableau, size_t tab_batch_st
   uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= block_ext) return;
   const typename F::Elt* T = tableau + (size_t)blockIdx.y * tab_batch_stride + dblock + j;
-  const uint32_t* nz = reinterpret_cast<const uint32_t*>(nonces + (size_t)blockIdx.y * nonce_batch_stride + 32ull * j);
+  const uint8_t* nzb = nonces + (size_t)blockIdx.y * nonce_batch_stride + 32ull * j;
   uint32_t h[8], w[16];
   sha256_iv(h);
+  if ((reinterpret_cast<uintptr_t>(nzb) & 3) == 0) {
+    const uint32_t* nz = reinterpret_cast<const uint32_t*>(nzb);
 #pragma unroll
-  for (int k = 0; k < 8; ++k) w[k] = bswap32(nz[k]);
+    for (int k = 0; k < 8; ++k) w[k] = bswap32(nz[k]);
+  } else {
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+      w[k] = ((uint32_t)nzb[4 * k] << 24) | ((uint32_t)nzb[4 * k + 1] << 16) | ((uint32_t)nzb[4 * k + 2] << 8) |
+             (uint32_t)nzb[4 * k + 3];
+  }
   constexpr int EW = F::kWords;        // words per element
   constexpr int PER = 16 / EW;         // elements per 64-byte block
   uint32_t pos = 8;                    // words filled in w (always a multiple of EW)

@@ -1,0 +1,902 @@
+// Batched ZK prover kernels (one batch = many independent proofs of one
+// circuit; blockIdx.y or blockIdx.x selects the proof).
+//
+//   reference                                           here
+//   ZkProver::fill_pad (zk/zk_prover.h:152-188)          k_zk_witness
+//   LigeroProver::layout_* (ligero_prover.h:171-279)     k_zk_layout
+//   initialize_sumcheck_fiat_shamir (zk_common.h:163)    k_zk_transcript_init
+//   ProverLayers::eval_circuit (prover_layers.h:52-98)   k_zk_eval_layer
+//   ProverLayers::prove/layer (prover_layers.h:114-271)  k_zk_sumcheck
+//   ZkCommon::verifier_constraints + LigeroProver::prove k_lig_*
+//   ZkProof::write (zk/zk_proof.h:90-184)                k_zk_serialize
+#pragma once
+#include <stdint.h>
+
+#include "field.cuh"
+#include "hash.cuh"
+#include "zk_types.cuh"
+
+namespace lf {
+
+// ----------------------------------------------------------------------------
+// field-specific sampling from a byte stream
+// ----------------------------------------------------------------------------
+// GF(2^128): 16 bytes are an element (gf2_128.h:182-190)
+__device__ __forceinline__ gf128 gf_from_bytes(const uint8_t* p) {
+  gf128 e;
+  if ((reinterpret_cast<uintptr_t>(p) & 3) == 0) {
+    const uint32_t* q = reinterpret_cast<const uint32_t*>(p);
+    e.w[0] = q[0]; e.w[1] = q[1]; e.w[2] = q[2]; e.w[3] = q[3];
+  } else {
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      e.w[k] = (uint32_t)p[4 * k] | ((uint32_t)p[4 * k + 1] << 8) | ((uint32_t)p[4 * k + 2] << 16) |
+               ((uint32_t)p[4 * k + 3] << 24);
+  }
+  return e;
+}
+__device__ __forceinline__ gf128 ts_elt(Transcript* ts, FGf128*) {
+  gf128 e;
+  ts->words(e.w, 4);
+  return e;
+}
+__device__ __forceinline__ void ts_write_elt(Transcript* ts, const gf128& e) { ts->write_elt_words(e.w, 4); }
+__device__ __forceinline__ void ts_array_elt(Transcript* ts, const gf128& e) { ts->elt_words(e.w, 4); }
+
+// ----------------------------------------------------------------------------
+// k_zk_witness: Ligero witness = private inputs || pad (zk_prover.h:78-96,152-188)
+// pad of layer i: 4*logw+2 random elements in order (round, hand, k in {0,2}),
+// then wc[0], wc[1]; then the product wc[0]*wc[1].
+// ----------------------------------------------------------------------------
+template <class F>
+__global__ void k_zk_witness(ZkDims d, ZkBufs<typename F::Elt> b, const LayerDesc* __restrict__ layers) {
+  typedef typename F::Elt Elt;
+  const size_t p = blockIdx.y;
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= d.nw) return;
+  Elt* wit = b.wit + p * d.nw;
+  const uint8_t* rng = b.rng + p * b.rng_stride;
+  if (i < d.n_witness) {
+    const uint8_t* w = b.witness_in + p * b.witness_stride + (size_t)(i + d.npub) * F::kBytes;
+    wit[i] = gf_from_bytes(w);
+    return;
+  }
+  uint32_t q = i - d.n_witness;  // index inside the pad block
+  if (q >= d.pad_size) {
+    wit[i] = F::zero();
+    return;
+  }
+  // locate the layer (nl is small)
+  uint32_t ly = 0;
+  while (ly + 1 < d.nl && layers[ly + 1].pad_off <= q) ++ly;
+  uint32_t j = q - layers[ly].pad_off, cnt = 4 * layers[ly].logw + 2;
+  if (j < cnt) {
+    wit[i] = gf_from_bytes(rng + (size_t)(layers[ly].sc_off + j) * F::kBytes);
+  } else {
+    Elt a = gf_from_bytes(rng + (size_t)(layers[ly].sc_off + cnt - 2) * F::kBytes);
+    Elt c = gf_from_bytes(rng + (size_t)(layers[ly].sc_off + cnt - 1) * F::kBytes);
+    wit[i] = F::mul(a, c);
+  }
+}
+
+// ----------------------------------------------------------------------------
+// k_zk_layout: message part of every tableau row (ligero_prover.h:171-279).
+// row_rng[i] = byte offset of row i's randomness; row_sub[i] != 0 marks rows
+// whose blinding is sampled from the subfield.  One CTA per (row, proof).
+// ----------------------------------------------------------------------------
+template <class F>
+__global__ void __launch_bounds__(256)
+k_zk_layout(ZkDims d, ZkBufs<typename F::Elt> b, const uint32_t* __restrict__ row_rng,
+            const uint8_t* __restrict__ row_sub, const uint32_t* __restrict__ lqc /* [nq][3] */) {
+  typedef typename F::Elt Elt;
+  const size_t p = blockIdx.y;
+  const uint32_t row = blockIdx.x;
+  Elt* T = b.tableau + (p * d.nrow + row) * (size_t)d.block_enc;
+  const Elt* wit = b.wit + p * d.nw;
+  const uint8_t* rng = b.rng + p * b.rng_stride + row_rng[row];
+  __shared__ Elt red[8];
+  if (row == 0) {  // ILDT: block random elements
+    for (uint32_t j = threadIdx.x; j < d.block; j += blockDim.x) T[j] = gf_from_bytes(rng + (size_t)j * F::kBytes);
+  } else if (row == 1) {  // IDOT: dblock random, then T[r] -= sum of the W part
+    Elt s = F::zero();
+    for (uint32_t j = threadIdx.x; j < d.dblock; j += blockDim.x) {
+      Elt e = gf_from_bytes(rng + (size_t)j * F::kBytes);
+      T[j] = e;
+      if (j >= d.r && j < d.r + d.w) s = F::add(s, e);
+    }
+    // block reduction of s
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      Elt t;
+#pragma unroll
+      for (int k = 0; k < F::kWords; ++k) t.w[k] = __shfl_xor_sync(0xffffffffu, s.w[k], o);
+      s = F::add(s, t);
+    }
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      Elt tot = red[0];
+      for (uint32_t k = 1; k < blockDim.x / 32; ++k) tot = F::add(tot, red[k]);
+      T[d.r] = F::sub(gf_from_bytes(rng + (size_t)d.r * F::kBytes), tot);
+    }
+  } else if (row == 2) {  // IQUAD: dblock random with the W part cleared
+    for (uint32_t j = threadIdx.x; j < d.dblock; j += blockDim.x) {
+      Elt e = gf_from_bytes(rng + (size_t)j * F::kBytes);
+      T[j] = (j >= d.r && j < d.r + d.w) ? F::zero() : e;
+    }
+  } else if (row < d.iq) {  // witness rows
+    uint32_t i = row - d.iw;
+    bool sub = row_sub[row] != 0;
+    for (uint32_t j = threadIdx.x; j < d.block; j += blockDim.x) {
+      Elt e;
+      if (j < d.r) {
+        if (sub) {
+          const uint8_t* q = rng + 2 * (size_t)j;
+          e = F::of_sub16((uint32_t)q[0] | ((uint32_t)q[1] << 8));
+        } else {
+          e = gf_from_bytes(rng + (size_t)j * F::kBytes);
+        }
+      } else {
+        uint32_t k = i * d.w + (j - d.r);
+        e = (k < d.nw) ? wit[k] : F::zero();
+      }
+      T[j] = e;
+    }
+  } else {  // quadratic rows: x_i, y_i, z_i
+    uint32_t t = row - d.iq;
+    uint32_t which = t / d.nqtriples, i = t % d.nqtriples;
+    for (uint32_t j = threadIdx.x; j < d.block; j += blockDim.x) {
+      Elt e;
+      if (j < d.r) {
+        e = gf_from_bytes(rng + (size_t)j * F::kBytes);
+      } else {
+        uint32_t k = i * d.w + (j - d.r);
+        e = (k < d.nq) ? wit[lqc[3 * k + which]] : F::zero();
+      }
+      T[j] = e;
+    }
+  }
+}
+
+// ----------------------------------------------------------------------------
+// k_zk_transcript_init: Transcript(tinit) ; write(root) ; then
+// initialize_sumcheck_fiat_shamir (zk_common.h:163-180).  One thread per proof.
+// ----------------------------------------------------------------------------
+template <class F>
+__global__ void k_zk_transcript_init(ZkDims d, ZkBufs<typename F::Elt> b, const uint8_t* __restrict__ tinit,
+                                     const uint8_t* __restrict__ circuit_id, size_t nproofs) {
+  size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= nproofs) return;
+  Transcript ts;
+  ts.init(tinit, d.tinit_len);
+  // ligero_transcript.h:31-34 write_commitment: root digest is node 1
+  const uint32_t* root = b.nodes + p * (size_t)(2 * d.block_ext * 8) + 8;
+  uint32_t rw[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) rw[k] = bswap32(root[k]);
+  ts.write_bytes_words(rw, 8);
+  ts.write_bytes(circuit_id, 32);
+  for (uint32_t i = 0; i < d.npub; ++i) {
+    typename F::Elt e = gf_from_bytes(b.witness_in + p * b.witness_stride + (size_t)i * F::kBytes);
+    ts_write_elt(&ts, e);
+  }
+  ts_write_elt(&ts, F::zero());
+  ts.write0(d.nterms);
+  *reinterpret_cast<Transcript*>(b.ts + p * sizeof(Transcript)) = ts;
+}
+
+// ----------------------------------------------------------------------------
+// k_zk_eval_layer: V[g] = sum over the quad terms of gate g of v * W[l] * W[r]
+// (prover_layers.h:278-305), gathered through the CSR-by-gate plan.  Assert-zero
+// terms (v == 0) are checked; a violation marks the proof LF_ERR_WITNESS.
+// ----------------------------------------------------------------------------
+template <class F>
+__global__ void __launch_bounds__(128)
+k_zk_eval_layer(ZkDims d, ZkBufs<typename F::Elt> b, const uint32_t* __restrict__ arena, LayerDesc L,
+                const typename F::Elt* __restrict__ consts, int is_output) {
+  typedef typename F::Elt Elt;
+  const size_t p = blockIdx.y;
+  uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= L.nout) return;
+  const Elt* W = b.wl + p * d.wl_elts + L.w_off;
+  const uint32_t* off = arena + L.ev_off;
+  const uint32_t *h0 = arena + L.ev_h0, *h1 = arena + L.ev_h1, *vi = arena + L.ev_vi;
+  typename F::Acc acc;
+  F::acc_zero(acc);
+  bool bad = false;
+  for (uint32_t t = off[g]; t < off[g + 1]; ++t) {
+    uint32_t v = vi[t];
+    Elt x = F::mul(W[h1[t]], W[h0[t]]);
+    if (v & kViZero) {
+      bad |= !F::is_zero(x);
+    } else if (v & kViOne) {
+      F::acc_add_elt(acc, x);
+    } else {
+      F::mac(acc, consts[v & kViMask], x);
+    }
+  }
+  Elt out = F::reduce(acc);
+  if (is_output) {
+    bad |= !F::is_zero(out);  // zk_prover.h:117-122: all outputs must be zero
+  } else {
+    b.wl[p * d.wl_elts + L.out_off + g] = out;
+  }
+  if (bad) b.status[p] = -5;
+}
+
+// ----------------------------------------------------------------------------
+// k_zk_sumcheck: the whole layered sumcheck of one proof in one persistent CTA,
+// Fiat-Shamir transcript included (thread 0), so that the 2*sum(logw)
+// sequential rounds never leave the SM.
+// ----------------------------------------------------------------------------
+template <class F>
+struct ScShared {
+  Transcript ts;
+  typename F::Elt G[2][40];   // bindings of the previous layer (Proof::kMaxBindings)
+  typename F::Elt red[2][8];  // per-warp partials of a0, a2
+  typename F::Elt r, alpha, beta, sum, wc[2];
+  int fail;
+};
+
+template <class F>
+__device__ __forceinline__ typename F::Elt warp_sum(typename F::Elt s) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    typename F::Elt t;
+#pragma unroll
+    for (int k = 0; k < F::kWords; ++k) t.w[k] = __shfl_xor_sync(0xffffffffu, s.w[k], o);
+    s = F::add(s, t);
+  }
+  return s;
+}
+
+// serial part of one round, thread 0 only (prover_layers.h:244-251,320-329,
+// transcript_sumcheck.h:63-79, poly.h:59-98)
+template <class F>
+__device__ __noinline__ void sc_round_serial(ScShared<F>* sh, typename F::Elt a0, typename F::Elt a2,
+                                            const typename F::Elt* pad /* hp[hand][round] k=0,2 */,
+                                            typename F::Elt* proof0, typename F::Elt* proof2,
+                                            typename F::Elt* hb_out) {
+  typedef typename F::Elt Elt;
+  // coefficients (eq0 == 1 because logc == 0)
+  Elt c0 = a0, c2 = a2;
+  Elt c1 = F::sub(F::sub(F::sub(sh->sum, c0), c0), c2);
+  Elt ev[3];
+  ev[0] = c0;                                       // p(0)
+  ev[1] = F::add(F::add(c0, c1), c2);               // p(1)
+  Elt x2 = F::evalpt(2);
+  ev[2] = F::add(F::mul(F::add(F::mul(c2, x2), c1), x2), c0);  // p(evalpt 2)
+  Elt p0 = F::sub(ev[0], pad[0]), p2 = F::sub(ev[2], pad[1]);
+  *proof0 = p0;
+  *proof2 = p2;
+  ts_write_elt(&sh->ts, p0);
+  ts_write_elt(&sh->ts, p2);
+  Elt rnd = ts_elt(&sh->ts, (F*)nullptr);
+  *hb_out = rnd;
+  // sum = evals.eval_lagrange(rnd)
+  Elt t[3] = {ev[0], ev[1], ev[2]};
+#pragma unroll
+  for (int i = 1; i < 3; ++i)
+#pragma unroll
+    for (int k = 2; k >= i; --k) t[k] = F::mul(F::sub(t[k], t[k - 1]), F::newton(k, i));
+  Elt e = t[2];
+  e = F::add(F::mul(e, F::sub(rnd, F::evalpt(1))), t[1]);
+  e = F::add(F::mul(e, F::sub(rnd, F::evalpt(0))), t[0]);
+  sh->sum = e;
+  sh->r = rnd;
+}
+
+template <class F>
+__global__ void __launch_bounds__(256)
+k_zk_sumcheck(ZkDims d, ZkBufs<typename F::Elt> b, const uint32_t* __restrict__ arena,
+              const LayerDesc* __restrict__ layers, const StepDesc* __restrict__ steps,
+              const typename F::Elt* __restrict__ consts) {
+  typedef typename F::Elt Elt;
+  typedef typename F::Acc Acc;
+  __shared__ ScShared<F> sh;
+  const size_t p = blockIdx.x;
+  const uint32_t tid = threadIdx.x, nth = blockDim.x;
+  if (b.status[p] != 0) return;  // witness already rejected by eval_circuit
+
+  Elt* wl = b.wl + p * d.wl_elts;
+  Elt* whbuf = b.wh + p * 4 * (size_t)d.max_nw;
+  Elt* hqbuf = b.hq + p * 2 * (size_t)d.max_hq;
+  Elt* E0 = b.eq + p * 2 * (size_t)d.max_eq;
+  Elt* E1 = E0 + d.max_eq;
+  Elt* sc = b.sc + p * d.sc_elts;
+  const Elt* wit = b.wit + p * d.nw;
+  Elt* hbs = b.hb + p * d.nhb;
+
+  if (tid == 0) {
+    sh.ts = *reinterpret_cast<const Transcript*>(b.ts + p * sizeof(Transcript));
+    sh.ts.have_prf = 0;  // Transcript::clone() carries only the hash (transcript.h:86)
+    // begin_circuit: Q[40] then G[40] (transcript_sumcheck.h:49-52)
+    for (int i = 0; i < 40; ++i) (void)ts_elt(&sh.ts, (F*)nullptr);
+    for (int i = 0; i < 40; ++i) {
+      Elt g = ts_elt(&sh.ts, (F*)nullptr);
+      sh.G[0][i] = g;
+      sh.G[1][i] = g;
+    }
+    sh.wc[0] = F::zero();
+    sh.wc[1] = F::zero();
+    sh.fail = 0;
+  }
+  __syncthreads();
+
+  uint32_t logv = d.logv;
+  for (uint32_t ly = 0; ly < d.nl; ++ly) {
+    const LayerDesc L = layers[ly];
+    if (tid == 0) {
+      sh.alpha = ts_elt(&sh.ts, (F*)nullptr);
+      sh.beta = ts_elt(&sh.ts, (F*)nullptr);
+      b.alphas[p * d.nl + ly] = sh.alpha;
+      sh.sum = F::add(sh.wc[0], F::mul(sh.alpha, sh.wc[1]));
+      E0[0] = F::one();
+      E1[0] = sh.alpha;
+    }
+    __syncthreads();
+    // EQ tables: E0[i] = EQ(G0, i), E1[i] = alpha * EQ(G1, i)  (eqs.h:46-78)
+    for (uint32_t l = 0; l < logv; ++l) {
+      const uint32_t S = 1u << l;
+      const Elt g0 = sh.G[0][l], g1 = sh.G[1][l];
+      for (uint32_t i = tid; i < 2 * S; i += nth) {
+        uint32_t k = i & (S - 1);
+        if (i < S) {
+          Elt v = E0[k], hi = F::mul(v, g0);
+          E0[k] = F::sub(v, hi);
+          E0[k + S] = hi;
+        } else {
+          Elt v = E1[k], hi = F::mul(v, g1);
+          E1[k] = F::sub(v, hi);
+          E1[k + S] = hi;
+        }
+      }
+      __syncthreads();
+    }
+    // Quad::bind_g (quad.h:152-185): initial HQuad values
+    {
+      const uint32_t* off = arena + L.bg_off;
+      const uint32_t *tg = arena + L.bg_g, *tv = arena + L.bg_vi;
+      const Elt beta = sh.beta;
+      for (uint32_t k = tid; k < L.nhq0; k += nth) {
+        Acc acc;
+        F::acc_zero(acc);
+        for (uint32_t t = off[k]; t < off[k + 1]; ++t) {
+          uint32_t g = tg[t], v = tv[t];
+          Elt dot = F::add(E0[g], E1[g]);
+          if (v & kViOne) F::acc_add_elt(acc, dot);
+          else F::mac(acc, (v & kViZero) ? beta : consts[v & kViMask], dot);
+        }
+        hqbuf[k] = F::reduce(acc);
+      }
+    }
+    __syncthreads();
+
+    const Elt* wcur[2] = {wl + L.w_off, wl + L.w_off};
+    uint32_t wpar[2] = {0, 0};
+    uint32_t hqpar = 0;
+    const Elt* pad = wit + d.n_witness + L.pad_off;
+
+    for (uint32_t t = 0; t < 2 * L.logw; ++t) {
+      const StepDesc S = steps[L.step0 + t];
+      const uint32_t hand = t & 1, oh = hand ^ 1, round = t >> 1;
+      const Elt* Wh = wcur[hand];
+      const Elt* Wo = wcur[oh];
+      const Elt* HQ = hqbuf + (size_t)hqpar * d.max_hq;
+      const uint32_t* roff = arena + S.row_off;
+      const uint32_t *rc = arena + S.row_c, *rp = arena + S.row_p1;
+      // QW[l] = sum_r Q[l,r] W[r] fused with the two dot products of
+      // ProverLayers::evaluations (prover_layers.h:230-243,357-402)
+      Acc a0, a2;
+      F::acc_zero(a0);
+      F::acc_zero(a2);
+      const uint32_t npair = (S.n0 + 1) / 2;
+      for (uint32_t i = tid; i < npair; i += nth) {
+        Acc q0;
+        F::acc_zero(q0);
+        for (uint32_t e = roff[2 * i]; e < roff[2 * i + 1]; ++e) F::mac(q0, HQ[rc[e]], Wo[rp[e]]);
+        Elt qw0 = F::reduce(q0), w0 = Wh[2 * i];
+        if (2 * i + 1 < S.n0) {
+          Acc q1;
+          F::acc_zero(q1);
+          for (uint32_t e = roff[2 * i + 1]; e < roff[2 * i + 2]; ++e) F::mac(q1, HQ[rc[e]], Wo[rp[e]]);
+          Elt qw1 = F::reduce(q1), w1 = Wh[2 * i + 1];
+          F::mac(a0, qw0, w0);
+          F::mac(a2, F::sub(qw1, qw0), F::sub(w1, w0));
+        } else {
+          F::mac(a0, qw0, w0);
+          F::mac(a2, qw0, w0);
+        }
+      }
+      {
+        Elt s0 = warp_sum<F>(F::reduce(a0)), s2 = warp_sum<F>(F::reduce(a2));
+        if ((tid & 31) == 0) {
+          sh.red[0][tid >> 5] = s0;
+          sh.red[1][tid >> 5] = s2;
+        }
+      }
+      __syncthreads();
+      if (tid == 0) {
+        Elt s0 = sh.red[0][0], s2 = sh.red[1][0];
+        for (uint32_t k = 1; k < nth / 32; ++k) {
+          s0 = F::add(s0, sh.red[0][k]);
+          s2 = F::add(s2, sh.red[1][k]);
+        }
+        // pad order: (round, hand, k in {0,2}); proof order: (round, k, hand)
+        sc_round_serial<F>(&sh, s0, s2, pad + 4 * round + 2 * hand, sc + L.sc_off + 4 * round + hand,
+                           sc + L.sc_off + 4 * round + 2 + hand, hbs + L.hb_off + t);
+        sh.G[hand][round] = sh.r;
+      }
+      __syncthreads();
+      const Elt r = sh.r;
+      // Dense::bind (dense.h:70-89)
+      Elt* Wn = whbuf + (size_t)(2 * hand + wpar[hand]) * d.max_nw;
+      for (uint32_t i = tid; i < npair; i += nth) {
+        Elt f0 = Wh[2 * i];
+        Wn[i] = (2 * i + 1 < S.n0) ? affine<F>(r, f0, Wh[2 * i + 1]) : affine_nz_z<F>(r, f0);
+      }
+      // HQuad::bind_h (hquad.h:89-123) through the merge plan
+      Elt* HQn = hqbuf + (size_t)(hqpar ^ 1) * d.max_hq;
+      const uint32_t* mg = arena + S.merge;
+      for (uint32_t j = tid; j < S.n_out; j += nth) {
+        uint32_t m = mg[j], src = m >> 2, kind = m & 3;
+        Elt v0 = HQ[src];
+        HQn[j] = kind == 0 ? affine<F>(r, v0, HQ[src + 1])
+                           : (kind == 1 ? affine_nz_z<F>(r, v0) : affine_z_nz<F>(r, v0));
+      }
+      __syncthreads();
+      wcur[hand] = Wn;
+      wpar[hand] ^= 1;
+      hqpar ^= 1;
+    }
+    // end of layer (prover_layers.h:263-270,331-344)
+    if (tid == 0) {
+      Elt hquad = hqbuf[(size_t)hqpar * d.max_hq];
+      Elt w0 = wcur[0][0], w1 = wcur[1][0];
+      Elt expect = F::mul(hquad, F::mul(w0, w1));
+      if (!F::eq(expect, sh.sum)) sh.fail = 1;
+      sh.wc[0] = w0;
+      sh.wc[1] = w1;
+      b.bq[p * d.nl + ly] = hquad;
+      Elt t0 = F::sub(w0, pad[4 * L.logw]), t1 = F::sub(w1, pad[4 * L.logw + 1]);
+      sc[L.sc_off + 4 * L.logw] = t0;
+      sc[L.sc_off + 4 * L.logw + 1] = t1;
+      sh.ts.begin_array(2);
+      ts_array_elt(&sh.ts, t0);
+      ts_array_elt(&sh.ts, t1);
+    }
+    __syncthreads();
+    logv = L.logw;
+  }
+  if (tid == 0) {
+    *reinterpret_cast<Transcript*>(b.ts + p * sizeof(Transcript)) = sh.ts;
+    if (sh.fail) b.status[p] = -100;  // internal inconsistency: never expected
+  }
+}
+
+// ----------------------------------------------------------------------------
+// k_lig_challenges: thread 0 of one CTA per proof.  alpha of the input
+// constraint (zk_common.h:131), write(hash_of_A) (zk_prover.h:143,
+// ligero_prover.h:91-95), then u_ldt, alphal, alphaq, u_quad which the
+// reference draws back to back from one PRF stream (ligero_prover.h:97-125).
+// chal layout: [0] alpha_in | u_ldt[nwqrow] | alphal[nl+1] | alphaq[3nq] | u_quad[nqtriples]
+// ----------------------------------------------------------------------------
+template <class F>
+__global__ void k_lig_challenges(ZkDims d, ZkBufs<typename F::Elt> b, size_t nproofs) {
+  size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= nproofs || b.status[p] != 0) return;
+  Transcript* gts = reinterpret_cast<Transcript*>(b.ts + p * sizeof(Transcript));
+  Transcript ts = *gts;
+  typename F::Elt* chal = b.chal + p * (size_t)(1 + d.nchal);
+  chal[0] = ts_elt(&ts, (F*)nullptr);
+  uint32_t hashA[8] = {0xefbeaddeu, 0, 0, 0, 0, 0, 0, 0};  // bytes de ad be ef 00 ...
+  ts.write_bytes_words(hashA, 8);
+  for (uint32_t i = 0; i < d.nchal; ++i) chal[1 + i] = ts_elt(&ts, (F*)nullptr);
+  *gts = ts;
+}
+
+// EQ table over the input wires, bindings = hand challenges of the last layer
+// (zk_common.h:412-413): E0 = EQ(hb[0]), E1 = EQ(hb[1]); one CTA per proof.
+template <class F>
+__global__ void __launch_bounds__(256)
+k_lig_input_eq(ZkDims d, ZkBufs<typename F::Elt> b, LayerDesc last) {
+  typedef typename F::Elt Elt;
+  const size_t p = blockIdx.x;
+  if (b.status[p] != 0) return;
+  Elt* E0 = b.eq + p * 2 * (size_t)d.max_eq;
+  Elt* E1 = E0 + d.max_eq;
+  const Elt* hb = b.hb + p * d.nhb + last.hb_off;  // [2*round + hand]
+  if (threadIdx.x == 0) {
+    E0[0] = F::one();
+    E1[0] = F::one();
+  }
+  __syncthreads();
+  for (uint32_t l = 0; l < last.logw; ++l) {
+    const uint32_t S = 1u << l;
+    const Elt g0 = hb[2 * l], g1 = hb[2 * l + 1];
+    for (uint32_t i = threadIdx.x; i < 2 * S; i += blockDim.x) {
+      uint32_t k = i & (S - 1);
+      if (i < S) {
+        Elt v = E0[k], hi = F::mul(v, g0);
+        E0[k] = F::sub(v, hi);
+        E0[k + S] = hi;
+      } else {
+        Elt v = E1[k], hi = F::mul(v, g1);
+        E1[k] = F::sub(v, hi);
+        E1[k + S] = hi;
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// Poly<3>::dot_interpolation::coef (poly.h:139-146): lag[k] = L_k(x)
+template <class F>
+__device__ __forceinline__ void lagrange3(const typename F::Elt& x, typename F::Elt lag[3]) {
+  typedef typename F::Elt Elt;
+  Elt d0 = F::sub(x, F::evalpt(0)), d1 = F::sub(x, F::evalpt(1));
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    Elt e = F::lag_id(k, 2);
+    e = F::add(F::mul(e, d1), F::lag_id(k, 1));
+    e = F::add(F::mul(e, d0), F::lag_id(k, 0));
+    lag[k] = e;
+  }
+}
+
+// ----------------------------------------------------------------------------
+// k_lig_avec: the inner-product vector A of LigeroCommon::inner_product_vector
+// (ligero_param.h:382-421) assembled directly from the symbolic sumcheck
+// verifier (zk_common.h:49-136,291-439) instead of materialising the sparse
+// constraint list:  for layer ly with rounds t = 2*round+hand and Lagrange
+// weights lag_t = coef(hb_t), the coefficient of
+//    poly pad (t,0):  (lag_t[0] - lag_t[1]) * P_t      poly pad (t,2): lag_t[2] * P_t
+//    claim pad of the previous layer: (1, alpha_ly, 0) * P_{-1}
+//    claim pad of this layer: (-eqq*wc[1], -eqq*wc[0], -eqq)
+// with P_t = prod_{t' > t} lag_t'[1], each multiplied by alphal[ly].
+// One CTA per proof; A is zero-filled first.
+// ----------------------------------------------------------------------------
+template <class F>
+__global__ void __launch_bounds__(256)
+k_lig_avec(ZkDims d, ZkBufs<typename F::Elt> b, const LayerDesc* __restrict__ layers) {
+  typedef typename F::Elt Elt;
+  const size_t p = blockIdx.x;
+  if (b.status[p] != 0) return;
+  const uint32_t tid = threadIdx.x, nth = blockDim.x;
+  Elt* A = b.avec + p * (size_t)d.nwqrow * d.w;
+  const Elt* chal = b.chal + p * (size_t)(1 + d.nchal);
+  const Elt alpha_in = chal[0];
+  const Elt* alphal = chal + 1 + d.nwqrow;
+  const Elt* alphaq = alphal + (d.nl + 1);
+  const Elt* hb = b.hb + p * d.nhb;
+  const Elt* sc = b.sc + p * d.sc_elts;
+  const Elt* bq = b.bq + p * d.nl;
+  const Elt* alphas = b.alphas + p * d.nl;
+  Elt* lagbuf = reinterpret_cast<Elt*>(b.scratch + p * b.scratch_words);  // [nhb][4]: lag0,lag1,lag2,P
+  const Elt* E0 = b.eq + p * 2 * (size_t)d.max_eq;
+  const Elt* E1 = E0 + d.max_eq;
+
+  const uint32_t na = d.nwqrow * d.w;
+  for (uint32_t i = tid; i < na; i += nth) {
+    Elt v = F::zero();
+    if (i < d.n_witness) {
+      // input constraint (zk_common.h:414-421): b_i = eq0[i] + alpha * eq1[i]
+      uint32_t k = i + d.npub;
+      v = F::mul(F::add(E0[k], F::mul(alpha_in, E1[k])), alphal[d.nl]);
+    }
+    A[i] = v;
+  }
+  // Lagrange weights of every round
+  for (uint32_t t = tid; t < d.nhb; t += nth) {
+    Elt lag[3];
+    lagrange3<F>(hb[t], lag);
+    lagbuf[4 * t + 0] = lag[0];
+    lagbuf[4 * t + 1] = lag[1];
+    lagbuf[4 * t + 2] = lag[2];
+  }
+  __syncthreads();
+  // suffix products per layer (one thread per layer; 2*logw sequential multiplies)
+  for (uint32_t ly = tid; ly < d.nl; ly += nth) {
+    const LayerDesc L = layers[ly];
+    Elt P = F::one();
+    for (uint32_t t = 2 * L.logw; t-- > 0;) {
+      lagbuf[4 * (L.hb_off + t) + 3] = P;
+      P = F::mul(P, lagbuf[4 * (L.hb_off + t) + 1]);
+    }
+    // P is now P_{-1}.  claim pads: combine this layer's finalize terms with
+    // the next layer's first() terms (or the input constraint after the last)
+    const Elt eqq = bq[ly];
+    const Elt wc0 = sc[L.sc_off + 4 * L.logw], wc1 = sc[L.sc_off + 4 * L.logw + 1];
+    const Elt al = alphal[ly];
+    uint32_t cp = d.n_witness + L.pad_off + 4 * L.logw;
+    // this layer's own terms (zk_common.h:381-384)
+    Elt c0 = F::neg(F::mul(F::mul(eqq, wc1), al));
+    Elt c1 = F::neg(F::mul(F::mul(eqq, wc0), al));
+    Elt c2 = F::neg(F::mul(eqq, al));
+    // stash P_{-1} for the previous layer's claim pads
+    lagbuf[4 * L.hb_off + 0] = lagbuf[4 * L.hb_off + 0];  // (no-op; keeps layout explicit)
+    // quadratic routing (ligero_param.h:408-419): A[lqc.x] -= alphaq[i][0] ...
+    if (ly < d.nq) {
+      c0 = F::sub(c0, alphaq[3 * ly + 0]);
+      c1 = F::sub(c1, alphaq[3 * ly + 1]);
+      c2 = F::sub(c2, alphaq[3 * ly + 2]);
+    }
+    A[cp + 0] = F::add(A[cp + 0], c0);
+    A[cp + 1] = F::add(A[cp + 1], c1);
+    A[cp + 2] = F::add(A[cp + 2], c2);
+    // store P_{-1} * alphal[ly] and alpha_ly for the pass below
+    Elt* extra = lagbuf + 4 * (size_t)d.nhb + 2 * ly;
+    extra[0] = F::mul(P, al);
+    extra[1] = F::mul(F::mul(P, al), alphas[ly]);
+  }
+  __syncthreads();
+  // previous-layer claim pads (cb.first, zk_common.h:330-335) and the input constraint tail
+  for (uint32_t ly = tid; ly <= d.nl; ly += nth) {
+    if (ly == 0) continue;  // layer 0 does not refer to CLAIM_PAD[-1] (zk_common.h:390-391)
+    const LayerDesc Lp = layers[ly - 1];
+    uint32_t cp = d.n_witness + Lp.pad_off + 4 * Lp.logw;
+    Elt c0, c1;
+    if (ly < d.nl) {
+      const Elt* extra = lagbuf + 4 * (size_t)d.nhb + 2 * ly;
+      c0 = extra[0];
+      c1 = extra[1];
+    } else {
+      // zk_common.h:433-436: (-1, -alpha) * alphal[nl]
+      c0 = F::neg(alphal[d.nl]);
+      c1 = F::neg(F::mul(alpha_in, alphal[d.nl]));
+    }
+    A[cp + 0] = F::add(A[cp + 0], c0);
+    A[cp + 1] = F::add(A[cp + 1], c1);
+  }
+  // poly pads
+  for (uint32_t t = tid; t < d.nhb; t += nth) {
+    // find the layer of round t
+    uint32_t ly = 0;
+    while (ly + 1 < d.nl && layers[ly + 1].hb_off <= t) ++ly;
+    const LayerDesc L = layers[ly];
+    uint32_t tt = t - L.hb_off;
+    Elt P = F::mul(lagbuf[4 * t + 3], alphal[ly]);
+    uint32_t base = d.n_witness + L.pad_off + 2 * tt;
+    A[base + 0] = F::mul(F::sub(lagbuf[4 * t + 0], lagbuf[4 * t + 1]), P);
+    A[base + 1] = F::mul(lagbuf[4 * t + 2], P);
+  }
+  // quadratic rows Ax, Ay, Az (ligero_param.h:402-418)
+  for (uint32_t i = tid; i < d.nq; i += nth) {
+    uint32_t ax = d.nwrow * d.w;
+    A[ax + i] = alphaq[3 * i + 0];
+    A[ax + d.nqtriples * d.w + i] = alphaq[3 * i + 1];
+    A[ax + 2 * d.nqtriples * d.w + i] = alphaq[3 * i + 2];
+  }
+}
+
+// Aext rows for dot_proof (ligero_param.h:423-430): [0^r | A_i[w]], one CTA per (row, proof)
+template <class F>
+__global__ void k_lig_aext(ZkDims d, ZkBufs<typename F::Elt> b) {
+  const size_t p = blockIdx.y;
+  if (b.status[p] != 0) return;
+  const uint32_t i = blockIdx.x;
+  typename F::Elt* X = b.aext + (p * d.nwqrow + i) * (size_t)d.dblock;
+  const typename F::Elt* A = b.avec + p * (size_t)d.nwqrow * d.w + (size_t)i * d.w;
+  for (uint32_t j = threadIdx.x; j < d.block; j += blockDim.x) X[j] = (j < d.r) ? F::zero() : A[j - d.r];
+}
+
+// y_ldt, y_dot, y_quad (ligero_prover.h:281-344): one thread per column.
+// y layout: [0,block) ldt | [block, block+dblock) dot | [block+dblock, block+2*dblock) quad
+template <class F>
+__global__ void __launch_bounds__(128)
+k_lig_columns(ZkDims d, ZkBufs<typename F::Elt> b) {
+  typedef typename F::Elt Elt;
+  const size_t p = blockIdx.y;
+  if (b.status[p] != 0) return;
+  uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= d.dblock) return;
+  const Elt* T = b.tableau + p * (size_t)d.nrow * d.block_enc;
+  const Elt* chal = b.chal + p * (size_t)(1 + d.nchal);
+  const Elt* u_ldt = chal + 1;
+  const Elt* u_quad = chal + 1 + d.nwqrow + (d.nl + 1) + 3 * d.nq;
+  Elt* y = b.y + p * (size_t)(d.block + 2 * d.dblock);
+  const size_t ld = d.block_enc;
+  typename F::Acc acc;
+  if (j < d.block) {
+    F::acc_zero(acc);
+    for (uint32_t i = 0; i < d.nwqrow; ++i) F::mac(acc, T[(size_t)(i + d.iw) * ld + j], u_ldt[i]);
+    y[j] = F::add(T[j], F::reduce(acc));
+  }
+  {
+    const Elt* X = b.aext + p * (size_t)d.nwqrow * d.dblock;
+    F::acc_zero(acc);
+    for (uint32_t i = 0; i < d.nwqrow; ++i) F::mac(acc, T[(size_t)(i + d.iw) * ld + j], X[(size_t)i * d.dblock + j]);
+    y[d.block + j] = F::add(T[ld + j], F::reduce(acc));
+  }
+  {
+    F::acc_zero(acc);
+    const uint32_t iqx = d.iq, iqy = iqx + d.nqtriples, iqz = iqy + d.nqtriples;
+    for (uint32_t i = 0; i < d.nqtriples; ++i) {
+      Elt tmp = F::sub(T[(size_t)(iqz + i) * ld + j], F::mul(T[(size_t)(iqy + i) * ld + j], T[(size_t)(iqx + i) * ld + j]));
+      F::mac(acc, tmp, u_quad[i]);
+    }
+    y[d.block + d.dblock + j] = F::add(T[2 * ld + j], F::reduce(acc));
+  }
+}
+
+// ----------------------------------------------------------------------------
+// k_lig_finish: one CTA per proof.  Thread 0 writes the four response arrays
+// into the transcript and draws the opened columns (ligero_prover.h:127-145,
+// random.h:92-105); the CTA then marks the Merkle opening, run-length codes the
+// opened columns and serializes the whole proof (zk_proof.h:114-184).
+// scratch layout (uint32): perm[block_ext] | mark bytes[2*block_ext] | flag bytes[nreq*nrow]
+//                          | eoff[nreq*nrow] | path_idx[nreq*mc_pathlen]
+// ----------------------------------------------------------------------------
+template <class F>
+__device__ __forceinline__ void put_elt(uint8_t* dst, const typename F::Elt& e) {
+  uint32_t w[F::kWords];
+  F::to_wire(w, e);
+  if ((reinterpret_cast<uintptr_t>(dst) & 3) == 0) {
+    uint32_t* q = reinterpret_cast<uint32_t*>(dst);
+#pragma unroll
+    for (int k = 0; k < F::kWords; ++k) q[k] = w[k];
+  } else {
+#pragma unroll
+    for (int k = 0; k < F::kWords; ++k) {
+      dst[4 * k] = (uint8_t)w[k];
+      dst[4 * k + 1] = (uint8_t)(w[k] >> 8);
+      dst[4 * k + 2] = (uint8_t)(w[k] >> 16);
+      dst[4 * k + 3] = (uint8_t)(w[k] >> 24);
+    }
+  }
+}
+__device__ __forceinline__ void put_u32(uint8_t* dst, uint32_t g) {
+  dst[0] = (uint8_t)g; dst[1] = (uint8_t)(g >> 8); dst[2] = (uint8_t)(g >> 16); dst[3] = (uint8_t)(g >> 24);
+}
+__device__ __forceinline__ void put_digest(uint8_t* dst, const uint32_t* be_words) {
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    uint32_t x = be_words[k];
+    dst[4 * k] = (uint8_t)(x >> 24); dst[4 * k + 1] = (uint8_t)(x >> 16);
+    dst[4 * k + 2] = (uint8_t)(x >> 8); dst[4 * k + 3] = (uint8_t)x;
+  }
+}
+
+template <class F>
+__global__ void __launch_bounds__(256)
+k_lig_finish(ZkDims d, ZkBufs<typename F::Elt> b, const LayerDesc* __restrict__ layers) {
+  typedef typename F::Elt Elt;
+  const size_t p = blockIdx.x;
+  if (b.status[p] != 0) {
+    if (threadIdx.x == 0) b.out_len[p] = 0;
+    return;
+  }
+  const uint32_t tid = threadIdx.x, nth = blockDim.x;
+  const Elt* T = b.tableau + p * (size_t)d.nrow * d.block_enc;
+  const Elt* y = b.y + p * (size_t)(d.block + 2 * d.dblock);
+  const Elt* sc = b.sc + p * d.sc_elts;
+  const uint32_t* nodes = b.nodes + p * (size_t)(2 * d.block_ext * 8);
+  const uint8_t* nonces = b.rng + p * b.rng_stride + d.rng_nonce_off;
+  uint32_t* idx = b.idx + p * d.nreq;
+  uint8_t* out = b.out + p * b.out_stride;
+  uint32_t* sw = b.scratch + p * b.scratch_words;
+  const uint32_t n = d.block_ext, total = d.nreq * d.nrow;
+  uint32_t* perm = sw;
+  uint8_t* mark = reinterpret_cast<uint8_t*>(sw + n);
+  uint8_t* flag = mark + 2 * (size_t)((n + 3) & ~3u);
+  uint32_t* eoff = reinterpret_cast<uint32_t*>(flag + ((total + 3) & ~3u));
+  uint32_t* path_idx = eoff + total;
+  __shared__ uint32_t s_npath, s_req_end;
+
+  for (uint32_t i = tid; i < n; i += nth) perm[i] = i;
+  for (uint32_t i = tid; i < 2 * n; i += nth) mark[i] = 0;
+  __syncthreads();
+  if (tid == 0) {
+    Transcript* gts = reinterpret_cast<Transcript*>(b.ts + p * sizeof(Transcript));
+    Transcript ts = *gts;
+    const uint32_t lens[4] = {d.block, d.dblock, d.r, d.dblock - d.block};
+    const uint32_t offs[4] = {0, d.block, d.block + d.dblock, d.block + d.dblock + d.block};
+    for (int a = 0; a < 4; ++a) {
+      ts.begin_array(lens[a]);
+      for (uint32_t i = 0; i < lens[a]; ++i) ts_array_elt(&ts, y[offs[a] + i]);
+    }
+    // RandomEngine::choose (random.h:92-105)
+    for (uint32_t i = 0; i < d.nreq; ++i) {
+      uint32_t j = i + ts.nat(n - i);
+      uint32_t t = perm[i];
+      perm[i] = perm[j];
+      perm[j] = t;
+      idx[i] = perm[i];
+      mark[perm[i] + n] = 1;
+    }
+    *gts = ts;
+  }
+  __syncthreads();
+  // compressed_merkle_proof_tree (merkle_tree.h:75-98), level by level
+  if (n >= 2) {
+    int top = 31 - __clz(n - 1);
+    for (int lv = top; lv >= 0; --lv) {
+      uint32_t lo = 1u << lv, hi = min(2u << lv, n);
+      for (uint32_t i = lo + tid; i < hi; i += nth) mark[i] = mark[2 * i] | mark[2 * i + 1];
+      __syncthreads();
+    }
+  }
+  // opened columns: subfield flags (zk_proof.h:162-166)
+  for (uint32_t k = tid; k < total; k += nth) {
+    Elt e = T[(size_t)(k / d.nreq) * d.block_enc + d.dblock + idx[k % d.nreq]];
+    uint32_t u;
+    flag[k] = F::kChar2 ? (uint8_t)F::solve_sub16(e, &u) : (uint8_t)1;
+  }
+  __syncthreads();
+  const uint32_t off_sc = 32;
+  const uint32_t off_y = off_sc + d.sc_elts * F::kBytes;
+  const uint32_t off_nonce = off_y + (d.block + d.dblock + d.r + (d.dblock - d.block)) * F::kBytes;
+  const uint32_t off_req = off_nonce + d.nreq * 32;
+  if (tid == 0) {
+    // run-length layout: runs alternate full / subfield, starting with full
+    uint32_t o = off_req, ci = 0;
+    uint32_t subrun = 0;
+    while (ci < total) {
+      uint32_t runlen = 0;
+      while (ci + runlen < total && (uint32_t)flag[ci + runlen] == subrun) ++runlen;
+      put_u32(out + o, runlen);
+      o += 4;
+      uint32_t sz = subrun ? F::kSubBytes : F::kBytes;
+      for (uint32_t k = ci; k < ci + runlen; ++k) {
+        eoff[k] = o;
+        o += sz;
+      }
+      ci += runlen;
+      subrun ^= 1;
+    }
+    s_req_end = o;
+    // MerkleTree::generate_compressed_proof (merkle_tree.h:122-143)
+    uint32_t sz = 0;
+    for (uint32_t i = n; i-- > 1;) {
+      if (mark[i]) {
+        uint32_t child = 2 * i;
+        if (mark[child]) child = 2 * i + 1;
+        if (!mark[child]) path_idx[sz++] = child;
+      }
+    }
+    s_npath = sz;
+    put_u32(out + o, sz);
+    b.out_len[p] = (uint64_t)o + 4 + 32ull * sz;
+  }
+  __syncthreads();
+  // ---- serialize (zk_proof.h:114-184) ----
+  if (tid < 8) {
+    uint32_t x = nodes[8 + tid];  // root = node 1
+    out[4 * tid] = (uint8_t)(x >> 24); out[4 * tid + 1] = (uint8_t)(x >> 16);
+    out[4 * tid + 2] = (uint8_t)(x >> 8); out[4 * tid + 3] = (uint8_t)x;
+  }
+  for (uint32_t i = tid; i < d.sc_elts; i += nth) put_elt<F>(out + off_sc + (size_t)i * F::kBytes, sc[i]);
+  {
+    // y_ldt | y_dot | y_quad_0 (first r of quad) | y_quad_2 (quad[block..dblock))
+    const uint32_t n1 = d.block + d.dblock, n2 = n1 + d.r, n3 = n2 + (d.dblock - d.block);
+    for (uint32_t i = tid; i < n3; i += nth) {
+      Elt e = i < n1 ? y[i] : (i < n2 ? y[n1 + (i - n1)] : y[n1 + d.block + (i - n2)]);
+      put_elt<F>(out + off_y + (size_t)i * F::kBytes, e);
+    }
+  }
+  for (uint32_t i = tid; i < d.nreq * 8; i += nth) {
+    uint32_t q = i >> 3, k = i & 7;
+    const uint8_t* src = nonces + 32ull * idx[q] + 4 * k;
+    uint8_t* dst = out + off_nonce + 32 * q + 4 * k;
+    dst[0] = src[0]; dst[1] = src[1]; dst[2] = src[2]; dst[3] = src[3];
+  }
+  for (uint32_t k = tid; k < total; k += nth) {
+    Elt e = T[(size_t)(k / d.nreq) * d.block_enc + d.dblock + idx[k % d.nreq]];
+    if (flag[k] && F::kChar2) {
+      uint32_t u;
+      F::solve_sub16(e, &u);
+      out[eoff[k]] = (uint8_t)u;
+      out[eoff[k] + 1] = (uint8_t)(u >> 8);
+    } else {
+      put_elt<F>(out + eoff[k], e);
+    }
+  }
+  {
+    const uint32_t base = s_req_end + 4;
+    for (uint32_t i = tid; i < s_npath; i += nth) put_digest(out + base + 32ull * i, nodes + 8ull * path_idx[i]);
+  }
+}
+
+// sumcheck proof / witness / tableau read-back helpers use plain memcpy on the host side
+
+}  // namespace lf

@@ -17,6 +17,8 @@
 #include "field.cuh"
 #include "hash.cuh"
 #include "kernels_commit.cuh"
+#include "kernels_zk.cuh"
+#include "zk_types.cuh"
 
 namespace lf {
 
@@ -479,4 +481,4 @@ int lf_microbench(lf_ctx* ctx, int what, double* gops) {
 }
 
 }  // extern "C"
-#include "zk_stub.inc"
+#include "zk_host.inc"

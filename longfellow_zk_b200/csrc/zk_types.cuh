@@ -1,0 +1,97 @@
+// Shared host/device descriptors of the batched ZK prover pipeline.
+//
+// A circuit is uploaded once (lf_circuit_upload): the reference's delta-coded
+// Quad (lib/sumcheck/quad.h:56-226) is expanded and turned into STATIC PLANS,
+// because everything about the sparse structure of the sumcheck -- which quad
+// terms merge in Quad::bind_g (quad.h:152-185), which corners pair up in every
+// HQuad::bind_h round (hquad.h:89-123), which corners feed which QW entry
+// (prover_layers.h:230-243) -- depends only on the circuit's indices, never on
+// the witness.  The kernels therefore never sort, scan or compact: they gather
+// through precomputed CSR lists, which also makes every sum a deterministic
+// per-thread sequence (no atomics; required for prime fields).
+#pragma once
+#include <stdint.h>
+
+namespace lf {
+
+// flags stored in the top bits of a constant index
+constexpr uint32_t kViZero = 0x80000000u;  // constant == 0: assert-zero term
+constexpr uint32_t kViOne = 0x40000000u;   // constant == 1: skip the multiply
+constexpr uint32_t kViMask = 0x3fffffffu;
+
+struct LayerDesc {
+  uint32_t nw, logw, nterms;
+  uint32_t nout;     // number of output wires (= nw of the layer above, or nv)
+  uint32_t nhq0;     // HQuad corners right after bind_g
+  // offsets into the uint32 arena
+  uint32_t ev_off;   // [nout+1] CSR by gate: eval_circuit
+  uint32_t ev_h0, ev_h1, ev_vi;  // [nterms]
+  uint32_t bg_off;   // [nhq0+1] terms of each initial HQuad corner (canonical order)
+  uint32_t bg_g, bg_vi;          // [nterms]
+  uint32_t step0;    // first StepDesc of this layer (2*logw of them)
+  uint32_t w_off;    // element offset of this layer's input wires in the per-proof wire store
+  uint32_t out_off;  // element offset of this layer's output wires
+  uint32_t pad_off;  // element offset of this layer's pad inside the Ligero witness
+  uint32_t sc_off;   // element offset of this layer inside the sumcheck proof (= pad rng index)
+  uint32_t hb_off;   // offset of this layer's 2*logw hand challenges
+};
+
+struct StepDesc {
+  uint32_t n_in;     // corners before the round
+  uint32_t n_out;    // corners after bind_h
+  uint32_t n0;       // length of the hand's wire array before the round
+  uint32_t row_off;  // [n0+1] CSR by p0 = h[hand]
+  uint32_t row_c;    // [n_in] corner index
+  uint32_t row_p1;   // [n_in] h[other hand]
+  uint32_t merge;    // [n_out] (src << 2) | kind ; kind 0 pair, 1 lone even, 2 lone odd
+};
+
+struct ZkDims {
+  uint32_t nl, ninputs, npub, n_witness, nv, logv, nterms;
+  // LigeroParam (lib/ligero/ligero_param.h:116-147)
+  uint32_t nw, nq, block_enc, block, dblock, block_ext, r, w, nwrow, nqtriples, nwqrow, nrow, nreq,
+      mc_pathlen, iw, iq;
+  uint32_t sb;        // subfield boundary rebased to the private inputs (zk_prover.h:84-89)
+  uint32_t pad_size;  // sum of 4*logw+3
+  uint32_t sc_elts;   // sum of 4*logw+2: elements of the sumcheck proof = random pad elements
+  uint32_t nhb;       // sum of 2*logw
+  uint32_t max_nw, max_hq, max_eq;
+  uint32_t wl_elts;   // per-proof wire store size (elements)
+  uint32_t nchal;     // nwqrow + (nl+1) + 3*nq + nqtriples Ligero challenges
+  // caller-supplied randomness layout (bytes from the start of one proof's stream)
+  uint32_t rng_nonce_off;
+  uint32_t rng_total;
+  uint32_t max_proof_bytes;
+  uint32_t tinit_len;
+};
+
+// per-proof device buffers: base pointer + stride (in elements of the pointee)
+template <class Elt>
+struct ZkBufs {
+  const uint8_t* witness_in;  size_t witness_stride;   // ninputs * kBytes wire bytes
+  const uint8_t* rng;         size_t rng_stride;
+  Elt* wit;        // [nw] Ligero witness
+  Elt* tableau;    // [nrow * block_enc]
+  uint32_t* nodes; // [2 * block_ext * 8] Merkle heap, big-endian digest words
+  Elt* wl;         // [wl_elts] wires of every layer
+  Elt* wh;         // [4 * max_nw] hand arrays, ping-pong
+  Elt* hq;         // [2 * max_hq] HQuad values, ping-pong
+  Elt* eq;         // [2 * max_eq] EQ tables
+  Elt* sc;         // [sc_elts] sumcheck proof in wire order
+  Elt* bq;         // [nl] bound quads (ProofAux)
+  Elt* hb;         // [nhb] hand challenges
+  Elt* alphas;     // [nl] per-layer alpha
+  Elt* chal;       // [1 + nchal] alpha_in, u_ldt, alphal, alphaq, u_quad
+  Elt* avec;       // [nwqrow * w]
+  Elt* aext;       // [nwqrow * dblock]
+  Elt* y;          // [block + 2*dblock] y_ldt | y_dot | y_quad
+  uint32_t* idx;   // [nreq] opened columns
+  uint32_t* scratch;  // [scratch_words]
+  uint8_t* ts;     // [sizeof(Transcript)]
+  uint8_t* out;    size_t out_stride;
+  uint64_t* out_len;
+  int32_t* status;
+  size_t scratch_words;
+};
+
+}  // namespace lf

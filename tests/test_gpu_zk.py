@@ -1,0 +1,102 @@
+"""GPU parity of the whole prover: same witness, same RNG bytes, same transcript
+seed => the serialized proof must be byte-identical to the reference's
+(tests/golden/golden.json, produced by the unmodified reference) and to the
+oracle's, stage by stage."""
+import hashlib
+
+import numpy as np
+import pytest
+
+from fixtures import golden, load, rng_bytes
+
+pytestmark = pytest.mark.gpu
+
+GF = 4
+
+
+@pytest.fixture(scope="module")
+def sha(ctx):
+    import longfellow_zk_b200 as lf
+    circ, wit = load("sha1_gf128")
+    c = lf.Circuit(ctx, GF, circ)
+    return c, circ, wit
+
+
+def test_sha_circuit_info(sha):
+    c, circ, wit = sha
+    g = golden()["sha1_gf128"]
+    assert c.info["ninputs"] == g["info"]["ninputs"] == 3721
+    assert c.info["nterms"] == g["info"]["nterms"]
+    assert (c.info["block_enc"], c.info["block"], c.info["dblock"], c.info["nrow"]) == (4096, 455, 909, 20)
+    assert c.info["rng_bytes"] == g["proofs"][0]["rng_used"]
+    assert c.info["witness_bytes"] == len(wit)
+
+
+def test_sha_proof_stages_match_oracle(sha, oracle):
+    import longfellow_zk_b200 as lf
+    c, circ, wit = sha
+    rng = rng_bytes(1, c.info["rng_bytes"])
+    want = oracle.Circuit(GF, circ).prove(wit, rng, dump=True)
+    p = lf.ZkProver(c)
+    proofs, status = p.prove_batch(np.frombuffer(wit, np.uint8)[None, :], rng[None, :])
+    nw = c.info["nw"]
+    got_w = p.debug_fetch(0, 1)
+    assert (got_w == want["witness"][:nw * 16]).all(), "Ligero witness (inputs || pad)"
+    got_t = p.debug_fetch(0, 2).reshape(20, 4096, 16)
+    want_t = want["tableau"][:20 * 4096 * 16].reshape(20, 4096, 16)
+    for row in range(20):
+        assert (got_t[row, :909] == want_t[row, :909]).all(), f"tableau row {row} message part"
+        assert (got_t[row] == want_t[row]).all(), f"tableau row {row} extension"
+    assert p.debug_fetch(0, 3).tobytes() == want["root"], "Merkle root"
+    got_sc = p.debug_fetch(0, 4)
+    want_sc = want["sumcheck"][:got_sc.size]
+    if not (got_sc == want_sc).all():
+        bad = np.nonzero((got_sc != want_sc).reshape(-1, 16).any(axis=1))[0]
+        raise AssertionError(f"sumcheck proof differs first at element {bad[0]} of {got_sc.size // 16}")
+    assert status[0] == 0
+    assert len(proofs[0]) == len(want["proof"])
+    if proofs[0] != want["proof"]:
+        a, b = np.frombuffer(proofs[0], np.uint8), np.frombuffer(want["proof"], np.uint8)
+        raise AssertionError(f"proof bytes differ first at offset {np.nonzero(a != b)[0][0]} of {a.size}")
+
+
+def test_sha_proofs_match_reference_golden(sha):
+    """three seeded proofs in one batch against the reference's own output"""
+    import longfellow_zk_b200 as lf
+    c, circ, wit = sha
+    g = golden()["sha1_gf128"]
+    seeds = [pr["seed"] for pr in g["proofs"]]
+    rng = np.stack([rng_bytes(s, 1 << 19)[:c.info["rng_bytes"]] for s in seeds])
+    W = np.repeat(np.frombuffer(wit, np.uint8)[None, :], len(seeds), axis=0)
+    proofs, status = lf.ZkProver(c).prove_batch(W, rng)
+    for pr, got, st in zip(g["proofs"], proofs, status):
+        assert st == 0
+        assert len(got) == pr["proof_len"]
+        assert got[:64].hex() == pr["proof_head"]
+        assert hashlib.sha256(got).hexdigest() == pr["proof_sha256"]
+
+
+def test_bad_witness_is_rejected(sha):
+    import longfellow_zk_b200 as lf
+    c, circ, wit = sha
+    bad = bytearray(wit)
+    bad[16 * 20] ^= 1  # flip an input bit: the hash no longer matches
+    rng = rng_bytes(5, c.info["rng_bytes"])
+    W = np.stack([np.frombuffer(bytes(bad), np.uint8), np.frombuffer(wit, np.uint8)])
+    proofs, status = lf.ZkProver(c).prove_batch(W, np.stack([rng, rng]))
+    assert status[0] == -5 and proofs[0] == b""
+    assert status[1] == 0 and len(proofs[1]) > 100000
+
+
+def test_reference_verifier_accepts_gpu_proofs(sha, ref):
+    """the unmodified reference ZkVerifier accepts what the GPU produced"""
+    import longfellow_zk_b200 as lf
+    c, circ, wit = sha
+    B = 8
+    rng = np.stack([rng_bytes(100 + i, c.info["rng_bytes"]) for i in range(B)])
+    W = np.repeat(np.frombuffer(wit, np.uint8)[None, :], B, axis=0)
+    proofs, status = lf.ZkProver(c).prove_batch(W, rng)
+    rc = ref.Circuit(GF, circ)
+    for pr, st in zip(proofs, status):
+        assert st == 0
+        assert rc.verify(b"", pr) == 0
