@@ -1,0 +1,322 @@
+#!/usr/bin/env python
+"""bench.py -- prover throughput of the SHA-256 ZK proof (BASELINE.json configs[1],
+BM_ShaZK_fp2_128/1: 1-block flatsha256 circuit, Ligero over GF(2^128), rate 7,
+132 queries) on N B200s, next to the reference CPU prover on the box's host cores.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B] [--impl reference]
+
+A step = one batch of B independent proofs (fresh witness buffer, RNG bytes and
+transcript per proof) through the whole prover hot path: tableau layout, RS row
+encode, Merkle commit, on-device Fiat-Shamir transcript, eval_circuit, the layered
+sumcheck, Ligero prove and proof serialization.  `value` = proofs/s with inputs
+and outputs resident in HBM (CUDA events on the launching stream, max over
+ranks); `e2e` = the same through the C-ABI call with pinned HOST buffers, H2D and
+D2H inside the timed region.  Independent proofs shard across GPUs with no
+collective (weak scaling: B proofs per GPU).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+METRIC = "sha256_zk_prover_throughput"
+UNIT = "proofs/s"
+WORKLOAD = "BM_ShaZK_fp2_128/1: 1-block SHA-256 ZK proof, GF(2^128), rate 7, nreq 132"
+
+
+def load_fixture():
+    from fixtures import load
+    return load("sha1_gf128")
+
+
+def rng_stream(seed, n):
+    import numpy as np
+    return np.random.default_rng(seed).integers(0, 256, n, dtype=np.uint8)
+
+
+# ----------------------------------------------------------------------------
+# reference arm / cpu_baseline: the unmodified reference prover (oracle/_ref) on
+# the host cores, N independent single-threaded provers (the library has no
+# threads of its own, docs/content/en/docs/benchmarks.md:7).
+# ----------------------------------------------------------------------------
+def cpu_reference_throughput(nthreads, per_thread):
+    from oracle import refapi, portapi
+    circ, wit = load_fixture()
+    rng = rng_stream(1, 1 << 18)
+    if refapi.available():
+        c = refapi.Circuit(refapi.GF2_128_ID, circ)
+        secs, lat = c.bench(wit, rng, nthreads=nthreads, per_thread=per_thread)
+        kind = "reference"
+    else:  # the reference could not be built here: fall back to the oracle port
+        c = portapi.Circuit(portapi.GF2_128_ID, circ)
+        t0 = time.time()
+        for _ in range(per_thread):
+            c.prove(wit, rng)
+        secs, lat, nthreads = time.time() - t0, [], 1
+        kind = "port"
+    n = nthreads * per_thread
+    med = sorted(lat)[len(lat) // 2] if lat else secs / n * 1e3
+    return dict(value=n / secs, unit=UNIT, cores=nthreads, kind=kind,
+                sample=f"{nthreads} threads x {per_thread} proofs of the same workload ({secs:.2f} s wall)",
+                ms_per_proof_1thread=med)
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    nthreads = os.cpu_count() or 1
+    per_thread = 40
+    vals, secs_all = [], []
+    for i in range(args.warmup + args.steps):
+        t0 = time.time()
+        r = cpu_reference_throughput(nthreads, per_thread)
+        if i >= args.warmup:
+            vals.append(r["value"])
+            secs_all.append(time.time() - t0)
+    v = sum(vals) / len(vals)
+    r["value"] = v
+    line = dict(metric=METRIC, value=v, unit=UNIT, n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
+                ms_per_step=1e3 * sum(secs_all) / len(secs_all), higher_is_better=True, scaling="weak",
+                vs_baseline=None, dtype="gf2^128 (u32 limbs)", data="synthetic", impl="reference",
+                config=dict(workload=WORKLOAD, proofs_per_step=nthreads * per_thread, host_threads=nthreads),
+                cpu_baseline=r,
+                e2e=dict(value=v, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
+    print(json.dumps(line))
+
+
+# ----------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region"""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.p = [], None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(index), f"--query-gpu={self.Q}",
+                                       "--format=csv,noheader,nounits", "-lms", "100"],
+                                      stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.p = None
+
+    def _read(self):
+        for line in self.p.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.p:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=2)
+        except Exception:
+            self.p.kill()
+        sm = sorted(int(float(r[0])) for r in self.rows if r and r[0].replace(".", "").isdigit())
+        mx = [int(float(r[1])) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows if len(r) >= 7 for n, v in zip(names, r[3:7]) if v == "Active"})
+        return dict(sm_mhz=sm[len(sm) // 2] if sm else None, sm_max_mhz=max(mx) if mx else None,
+                    reasons=reasons, samples=len(sm))
+
+
+def run_ours(args):
+    import numpy as np
+    import torch
+    import longfellow_zk_b200 as lf
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the prover has no CPU fallback")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    circ, wit = load_fixture()
+    stream = torch.cuda.current_stream()
+    ctx = lf.Context(local, stream=stream.cuda_stream)
+    circuit = lf.Circuit(ctx, lf.FIELD_GF2_128, circ)
+    prover = lf.ZkProver(circuit)
+    info = circuit.info
+    B = args.batch
+    wb, rb, pb = info["witness_bytes"], info["rng_bytes"], info["max_proof_bytes"]
+    rstride = (rb + 15) & ~15
+
+    # synthetic inputs: the benchmark witness for every proof, per-proof RNG streams
+    gen = torch.Generator().manual_seed(1234 + rank)
+    h_wit = torch.from_numpy(np.frombuffer(wit, np.uint8).copy()).repeat(B, 1).pin_memory()
+    h_rng = torch.randint(0, 256, (B, rstride), dtype=torch.uint8, generator=gen).pin_memory()
+    h_out = torch.empty((B, pb), dtype=torch.uint8).pin_memory()
+    h_len = torch.zeros(B, dtype=torch.int64).pin_memory()
+    h_st = torch.zeros(B, dtype=torch.int32).pin_memory()
+    d_wit, d_rng = h_wit.cuda(), h_rng.cuda()
+    d_out = torch.empty((B, pb), dtype=torch.uint8, device="cuda")
+    d_len = torch.zeros(B, dtype=torch.int64, device="cuda")
+    d_st = torch.zeros(B, dtype=torch.int32, device="cuda")
+
+    def step_dev():
+        prover.prove_batch_ptr(B, d_wit.data_ptr(), d_rng.data_ptr(), rstride, d_out.data_ptr(), pb,
+                               d_len.data_ptr(), d_st.data_ptr(), device=True)
+
+    def step_host():
+        prover.prove_batch_ptr(B, h_wit.data_ptr(), h_rng.data_ptr(), rstride, h_out.data_ptr(), pb,
+                               h_len.data_ptr(), h_st.data_ptr(), device=False)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, use_events):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record(stream)
+        for _ in range(steps):
+            fn()
+        e1.record(stream)
+        torch.cuda.synchronize()
+        t1 = time.perf_counter()
+        ms = e0.elapsed_time(e1) if use_events else (t1 - t0) * 1e3
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        if dist is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        barrier()
+        return float(t.item())
+
+    # ---- warm-up + correctness of what is being timed
+    for _ in range(max(args.warmup, 3)):
+        step_dev()
+    torch.cuda.synchronize()
+    assert int(d_st.abs().sum().item()) == 0, "prover reported failures"
+    lens = d_len.cpu().numpy()
+    assert (lens > 100000).all()
+
+    # ---- device-resident throughput (value)
+    sampler = ClockSampler(local) if rank == 0 else None
+    l0 = ctx.launch_count
+    ms_total = timed(step_dev, args.steps, use_events=True)
+    launches = ctx.launch_count - l0
+    clocks = sampler.stop() if sampler else None
+    value = world * B * args.steps / (ms_total * 1e-3)
+
+    # ---- per-stage device times of one more batch (roofline of the dominant kernel)
+    prover.set_profiling(True)
+    stage_acc = {}
+    nprof = 3
+    for _ in range(nprof):
+        step_dev()
+        for k, v in prover.stage_ms().items():
+            stage_acc[k] = stage_acc.get(k, 0.0) + v / nprof
+    prover.set_profiling(False)
+
+    # ---- end to end through the host-pointer C-ABI call (pinned host buffers)
+    for _ in range(2):
+        step_host()
+    e2e_steps = max(2, min(args.steps, 5))
+    ms_e2e = timed(step_host, e2e_steps, use_events=False)
+    e2e_value = world * B * e2e_steps / (ms_e2e * 1e-3)
+    assert int(h_st.abs().sum().item()) == 0
+    # the proofs that came back through the host path equal the device-resident ones
+    torch.cuda.synchronize()
+    n0 = int(h_len[0].item())
+    assert n0 == int(lens[0]) and bytes(h_out[0, :n0].numpy()) == bytes(d_out[0, :n0].cpu().numpy())
+
+    # ---- single-proof latency (batch of one, device resident)
+    d_len1 = torch.zeros(1, dtype=torch.int64, device="cuda")
+    d_st1 = torch.zeros(1, dtype=torch.int32, device="cuda")
+
+    def step_one():
+        prover.prove_batch_ptr(1, d_wit.data_ptr(), d_rng.data_ptr(), rstride, d_out.data_ptr(), pb,
+                               d_len1.data_ptr(), d_st1.data_ptr(), device=True)
+    for _ in range(3):
+        step_one()
+    lat_ms = timed(step_one, 10, use_events=True) / 10
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (k_zk_sumcheck)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "MEASURED_PEAKS.json hbm_gbs (measured)" if "hbm_gbs" in peaks else "6650 GB/s (fallback)"
+    top = max(stage_acc, key=stage_acc.get)
+    sc_ms = stage_acc["sumcheck"]
+    alg_bytes = info["sumcheck_alg_bytes"] * B
+    achieved = alg_bytes / (sc_ms * 1e-3) / 1e9
+    gmul_peak = ctx.microbench(2)  # measured GF(2^128) multiply rate of this formulation (Gmul/s)
+    roofline = dict(bound="hbm", kernel="k_zk_sumcheck", achieved=achieved, peak=hbm_peak, unit="GB/s",
+                    frac=achieved / hbm_peak, traffic=None, peak_source=peak_src,
+                    kernel_ms_per_launch=sc_ms, share_of_step=sc_ms / sum(stage_acc.values()),
+                    algorithmic_bytes_per_proof=info["sumcheck_alg_bytes"],
+                    integer_pipe=dict(
+                        note="the kernel is integer-pipe bound (carry-less multiply out of IMAD.WIDE/LOP3); "
+                             "fraction of the measured GF(2^128) multiply rate of the same formulation",
+                        achieved_gmul_s=info["sumcheck_mults"] * B / (sc_ms * 1e-3) / 1e9,
+                        peak_gmul_s=gmul_peak,
+                        frac=info["sumcheck_mults"] * B / (sc_ms * 1e-3) / 1e9 / gmul_peak),
+                    stage_ms=stage_acc, top_stage=top)
+
+    # ---- the reference CPU prover on this box's host cores (bounded sample)
+    nthreads = os.cpu_count() or 1
+    cpu = cpu_reference_throughput(nthreads, 60)
+    cpu1 = cpu_reference_throughput(1, 30)
+    cpu["single_thread_proofs_per_s"] = cpu1["value"]
+    cpu["single_thread_ms_per_proof"] = cpu1["ms_per_proof_1thread"]
+
+    line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3),
+                ms_per_step=ms_total / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None,
+                dtype="gf2^128 (u32 limbs)", data="synthetic",
+                config=dict(workload=WORKLOAD, proofs_per_step_per_gpu=B, parallelism=f"independent proofs x{world}",
+                            l2="inputs+working set of one step (>%d MB) exceed the 126 MB L2" %
+                               (B * (wb + rb + pb) // (1 << 20)),
+                            ninputs=info["ninputs"], nterms=info["nterms"], tableau=[info["nrow"], info["block_enc"]],
+                            proof_bytes=int(lens[0])),
+                clocks=clocks,
+                e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=B * (wb + rstride),
+                         d2h_bytes_per_step=B * (pb + 12), ms_per_step=ms_e2e / e2e_steps),
+                gpu_launches=launches, roofline=roofline, cpu_baseline=cpu,
+                latency_ms_per_proof_batch1=lat_ms,
+                ms_per_proof=ms_total / args.steps / B)
+    print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--batch", type=int, default=1024, help="independent proofs per step per GPU")
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -102,6 +102,14 @@ typedef struct lf_circuit_info {
   size_t max_proof_bytes; /* upper bound of the serialized proof */
   size_t block_enc, block, dblock, block_ext, nrow, r, w, nwrow, nqtriples, nreq;
   size_t nw;              /* Ligero witnesses = private inputs + pad */
+  /* per-proof algorithmic work of the sumcheck kernel:
+   * bytes = sum over rounds of T*(8+kB) + T*kB + 4.5*n0*kB + T'*(8+kB);
+   * field multiplications = sum over rounds of T + 1.5*n0 + T' (+ bind_g) */
+  size_t sumcheck_alg_bytes, sumcheck_mults;
+  /* per-proof field multiplications of the whole prover (RS + eval + sumcheck + Ligero) */
+  size_t total_mults;
+  /* per-proof SHA-256 compressions (Merkle leaves + tree + transcript) */
+  size_t sha_compressions;
 } lf_circuit_info;
 int lf_circuit_get_info(const lf_circuit* c, lf_circuit_info* info);
 
@@ -138,6 +146,13 @@ enum lf_stage {
 /* copies stage data of proof `index` of the most recent batch (wire encoding) */
 int lf_zk_debug_fetch(lf_circuit* c, size_t index, int stage, uint8_t* out, size_t cap,
                       size_t* len);
+
+/* per-stage device times of the most recent batch, measured with CUDA events
+ * on the context stream when profiling is enabled (bench.py's roofline leg).
+ * stage order: 0 layout 1 rs_encode 2 merkle 3 transcript_init 4 eval_circuit
+ *              5 sumcheck 6 ligero_prove ; returns the number of stages */
+int lf_circuit_set_profiling(lf_circuit* c, int enable);
+int lf_circuit_get_stage_ms(lf_circuit* c, float* ms, size_t cap);
 
 /* number of kernel launches issued on behalf of this context so far */
 uint64_t lf_ctx_launch_count(const lf_ctx* ctx);

@@ -19,7 +19,7 @@ class CircuitInfo(C.Structure):
     _fields_ = [(n, C.c_size_t) for n in (
         "ninputs", "npub_in", "nl", "nterms", "kbytes", "witness_bytes", "rng_bytes",
         "max_proof_bytes", "block_enc", "block", "dblock", "block_ext", "nrow", "r", "w", "nwrow",
-        "nqtriples", "nreq", "nw")]
+        "nqtriples", "nreq", "nw", "sumcheck_alg_bytes", "sumcheck_mults", "total_mults", "sha_compressions")]
 
 
 EXPORTS = [
@@ -27,6 +27,7 @@ EXPORTS = [
     "lf_elt_mul", "lf_rs_interpolate", "lf_rs_interpolate_dev", "lf_merkle_commit",
     "lf_circuit_upload", "lf_circuit_free", "lf_circuit_get_info", "lf_zk_prove_batch",
     "lf_zk_prove_batch_dev", "lf_zk_debug_fetch", "lf_ctx_launch_count", "lf_microbench",
+    "lf_circuit_set_profiling", "lf_circuit_get_stage_ms",
 ]
 
 
@@ -64,6 +65,8 @@ def lib():
                                             C.c_void_p]
         L.lf_zk_debug_fetch.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.c_void_p, C.c_size_t,
                                         C.POINTER(C.c_size_t)]
+        L.lf_circuit_set_profiling.argtypes = [C.c_void_p, C.c_int]
+        L.lf_circuit_get_stage_ms.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.c_size_t]
         L.lf_microbench.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_double)]
         _lib = L
     return _lib

@@ -154,6 +154,26 @@ class ZkProver:
                                               len(tinit), _p(out), stride, _p(lens), _p(status)))
         return [out[i, :int(lens[i])].tobytes() for i in range(B)], status
 
+    STAGES = ["layout", "rs_encode", "merkle", "transcript_init", "eval_circuit", "sumcheck", "ligero_prove"]
+
+    def prove_batch_ptr(self, nproofs, wit_ptr, rng_ptr, rng_stride, out_ptr, out_stride, lens_ptr,
+                        status_ptr, tinit=b"test", device=False):
+        """Raw-pointer form (pinned host buffers, or device buffers with device=True;
+        the device form is asynchronous on the context stream)."""
+        fn = _native.lib().lf_zk_prove_batch_dev if device else _native.lib().lf_zk_prove_batch
+        check(fn(self.c._h, nproofs, C.c_void_p(wit_ptr), C.c_void_p(rng_ptr), rng_stride, tinit, len(tinit),
+                 C.c_void_p(out_ptr), out_stride, C.c_void_p(lens_ptr), C.c_void_p(status_ptr)))
+
+    def set_profiling(self, on=True):
+        check(_native.lib().lf_circuit_set_profiling(self.c._h, int(on)))
+
+    def stage_ms(self):
+        ms = (C.c_float * 8)()
+        n = _native.lib().lf_circuit_get_stage_ms(self.c._h, ms, 8)
+        if n < 0:
+            check(n)
+        return dict(zip(self.STAGES, [float(x) for x in ms[:n]]))
+
     def debug_fetch(self, index, stage, cap=1 << 26):
         buf = np.zeros(cap, np.uint8)
         n = C.c_size_t()

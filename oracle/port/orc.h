@@ -23,6 +23,7 @@
 enum {
   ORC_P256 = 1,
   ORC_GF2_128 = 4,
+  ORC_SECP256K1 = 10, /* Fp<4> over the secp256k1 prime, random/transcript_test.cc:131-283 */
   ORC_BN254 = 100,    /* Fp<4>, fft_test.cc:33-36 */
   ORC_FP128 = 101,    /* fp_p128.h: 2^128 - 2^108 + 1 */
   ORC_GOLDILOCKS = 102 /* Fp<1>: 2^64 - 2^32 + 1 */

@@ -193,6 +193,9 @@ size_t orc_transcript_script(int fid, const uint8_t* init, size_t init_len, cons
         f_to_bytes(F, out + o, rng_elt(&ts.base, F));
         o += F->kbytes;
       }
+    } else if (op == 'K') { /* Transcript::get: 32-byte snapshot */
+      sha256_final(&ts.sha, out + o);
+      o += 32;
     } else {
       return 0;
     }

@@ -274,8 +274,8 @@ static void fp_setup(field* F, int w64, const uint64_t m[4]) {
 /* ------------------------------------------------------------------ */
 /* field table                                                         */
 /* ------------------------------------------------------------------ */
-static field g_fields[5];
-static int g_init[5];
+static field g_fields[6];
+static int g_init[6];
 
 const field* orc_field(int id) {
   int slot;
@@ -285,6 +285,7 @@ const field* orc_field(int id) {
     case ORC_BN254: slot = 2; break;
     case ORC_FP128: slot = 3; break;
     case ORC_GOLDILOCKS: slot = 4; break;
+    case ORC_SECP256K1: slot = 5; break;
     default: return NULL;
   }
   field* F = &g_fields[slot];
@@ -314,6 +315,10 @@ const field* orc_field(int id) {
     F->omega2[1] = fp_to_mont(F, ey);
     F->omega_order = 1ull << 31;
     F->has_omega = 2;
+  } else if (id == ORC_SECP256K1) {
+    uint64_t m[4];
+    parse_dec("115792089237316195423570985008687907853269984665640564039457584007908834671663", m);
+    fp_setup(F, 4, m);
   } else if (id == ORC_BN254) {
     uint64_t m[4], o[4];
     parse_dec("21888242871839275222246405745257275088548364400416034343698204186575808495617", m);

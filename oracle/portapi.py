@@ -19,7 +19,8 @@ GF2_128_ID = 4
 FID_BN254 = 100
 FID_FP128 = 101
 FID_GOLDILOCKS = 102
-KBYTES = {P256_ID: 32, GF2_128_ID: 16, FID_BN254: 32, FID_FP128: 16, FID_GOLDILOCKS: 8}
+FID_SECP256K1 = 10
+KBYTES = {P256_ID: 32, GF2_128_ID: 16, 10: 32, FID_BN254: 32, FID_FP128: 16, FID_GOLDILOCKS: 8}
 
 _lib = None
 

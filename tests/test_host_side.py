@@ -1,0 +1,115 @@
+"""CPU-only checks of the product's host side: the C-ABI library loads and
+exports every symbol include/longfellow_b200.h declares, fails loudly without a
+GPU, and the header-only device primitives (compiled here as plain C++) agree
+with the oracle."""
+import ctypes as C
+import hashlib
+import os
+import re
+import struct
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _have_gpu():
+    try:
+        import torch
+        return torch.cuda.is_available()
+    except Exception:
+        return False
+
+
+def test_library_exports_every_declared_symbol():
+    from longfellow_zk_b200 import _native, build
+    build.build()
+    hdr = open(os.path.join(ROOT, "include", "longfellow_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = sorted(set(re.findall(r"\b(lf_[a-z0-9_]+)\s*\(", hdr)))
+    assert len(declared) >= 15
+    lib = C.CDLL(_native.LIB)
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in the header but not exported"
+    assert sorted(_native.EXPORTS) == declared
+    assert b"sm_100a" in _native.lib().lf_version()
+
+
+@pytest.mark.skipif(_have_gpu(), reason="checks the no-GPU failure mode")
+def test_no_cpu_fallback():
+    import longfellow_zk_b200 as lf
+    with pytest.raises(lf.LongfellowError) as e:
+        lf.Context(0)
+    assert e.value.code == -2 and "no CPU fallback" in str(e.value)
+
+
+@pytest.fixture(scope="module")
+def prim():
+    exe = "/tmp/lf_prim_check"
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-o", exe, os.path.join(ROOT, "tests/host/prim_check.cc")])
+    return lambda mode, data: subprocess.run([exe, mode], input=data, capture_output=True, check=True).stdout
+
+
+def test_device_gf128_mul_source_on_host(prim, oracle):
+    rs = np.random.default_rng(5)
+    a = rs.integers(0, 256, (4000, 16), dtype=np.uint8)
+    b = rs.integers(0, 256, (4000, 16), dtype=np.uint8)
+    a[0] = 0
+    a[1] = 255
+    b[1] = 255
+    assert prim("gfmul", np.concatenate([a, b], axis=1).tobytes()) == oracle.gf128_mul(a, b).tobytes()
+    assert prim("gfinv", a[2:40].tobytes()) == oracle.gf128_invert(a[2:40]).tobytes()
+
+
+def test_device_sha_aes_transcript_source_on_host(prim, oracle):
+    rs = np.random.default_rng(6)
+    for n in [0, 1, 3, 55, 56, 57, 63, 64, 65, 119, 120, 128, 1000]:
+        d = rs.integers(0, 256, n, dtype=np.uint8).tobytes()
+        assert prim("sha", d) == hashlib.sha256(d).digest(), n
+    key = rs.integers(0, 256, 32, dtype=np.uint8).tobytes()
+    blocks = rs.integers(0, 256, 160, dtype=np.uint8).tobytes()
+    assert prim("aes", key + blocks) == oracle.aes256_ecb(key, blocks)
+    u32 = lambda v: struct.pack("<I", v)
+    s = b"B" + u32(5) + b"hello" + b"R" + u32(40) + b"E" + bytes(range(16)) + b"G" + u32(3)
+    s += b"Z" + u32(1000) + b"N" + u32(3187) + b"N" + u32(256) + b"N" + u32(1)
+    s += b"A" + u32(2) + bytes(range(32)) + b"Z" + u32(155197) + b"R" + u32(17) + b"Z" + u32(3) + b"G" + u32(1)
+    assert prim("transcript", s) == oracle.transcript_script(b"test", s)
+
+
+def test_oracle_matches_unmodified_reference(oracle, ref):
+    """skipped on boxes where oracle/_ref was not built"""
+    rs = np.random.default_rng(7)
+    a = rs.integers(0, 256, (500, 16), dtype=np.uint8)
+    b = rs.integers(0, 256, (500, 16), dtype=np.uint8)
+    assert (ref.gf128_mul(a, b) == oracle.gf128_mul(a, b)).all()
+    assert (ref.lch14_what() == oracle.lch14_what()).all()
+    for x, y in zip(ref.gf128_constants(), oracle.gf128_constants()):
+        assert (x == y).all()
+    for l in (1, 4, 9):
+        B = rs.integers(0, 256, (1 << l, 16), dtype=np.uint8)
+        for op, ck in [("fft", 0), ("fft", 5 << l), ("ifft", 3 << l), ("bidir", 1), ("bidir", (1 << l) - 1)]:
+            assert (ref.lch14(op, l, ck, B) == oracle.lch14(op, l, ck, B)).all()
+    for n, m in [(455, 4096), (455, 909), (2, 3)]:
+        rows = rs.integers(0, 256, (2, m, 16), dtype=np.uint8)
+        assert (ref.lch14_interpolate(n, m, rows) == oracle.lch14_interpolate(n, m, rows)).all()
+    for nw, nq in [(4368, 13), (1495, 11), (87000, 17), (300000, 30000)]:
+        for fid in (4, 1):
+            assert ref.ligero_param(fid, nw, nq) == oracle.ligero_param(fid, nw, nq)
+    for fid in (oracle.FID_BN254, oracle.FID_FP128, oracle.FID_GOLDILOCKS, oracle.P256_ID):
+        kb = oracle.KBYTES[fid]
+        x = rs.integers(0, 256, (300, kb), dtype=np.uint8)
+        y = rs.integers(0, 256, (300, kb), dtype=np.uint8)
+        x[:, -1] &= 0x1f
+        y[:, -1] &= 0x1f
+        assert (ref.fp_mul(fid, x, y) == oracle.elt_op(fid, "mul", x, y)).all()
+        rows = rs.integers(0, 256, (2, 64, kb), dtype=np.uint8)
+        rows[:, :, -1] &= 0x1f
+        assert (ref.rs(fid, rows, 20, 64) == oracle.rs_interpolate(fid, 20, 64, rows)).all()
+    for fid in (oracle.FID_BN254, oracle.FID_FP128, oracle.FID_GOLDILOCKS):
+        kb = oracle.KBYTES[fid]
+        x = rs.integers(0, 256, (256, kb), dtype=np.uint8)
+        x[:, -1] &= 0x1f
+        for fwd in (False, True):
+            assert (ref.fft(fid, x, 256, fwd) == oracle.fft(fid, x, 256, fwd)).all()
