@@ -147,7 +147,10 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     circ, wit = load_fixture()
-    stream = torch.cuda.current_stream()
+    # the prover launches on an explicit (non-default) stream; the CUDA events
+    # below are recorded on that same stream
+    stream = torch.cuda.Stream()
+    assert stream.cuda_stream != 0
     ctx = lf.Context(local, stream=stream.cuda_stream)
     circuit = lf.Circuit(ctx, lf.FIELD_GF2_128, circ)
     prover = lf.ZkProver(circuit)

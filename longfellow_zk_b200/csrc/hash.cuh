@@ -154,28 +154,36 @@ struct Sha256 {
       --n;
     }
   }
-  // little-endian 32-bit words of a field element (wire bytes = LE)
-  LF_HD void update_le_words(const uint32_t* w, int nwords) {
-    if ((len & 3) == 0) {
-      for (int i = 0; i < nwords; ++i) {
-        uint32_t pos = (uint32_t)(len & 63);
-        buf[pos >> 2] = bswap32(w[i]);
-        len += 4;
-        if (pos == 60) {
-          sha256_compress(h, buf);
+  // one 32-bit word whose bytes enter the stream most-significant first; the
+  // stream position may be unaligned (tags are single bytes), so the word can
+  // straddle two buffer words or two blocks
+  LF_HD void put_word_be(uint32_t x) {
+    const uint32_t pos = (uint32_t)(len & 63), k = pos & 3, wi = pos >> 2;
+    len += 4;
+    if (k == 0) {
+      buf[wi] = x;
+      if (wi == 15) {
+        sha256_compress(h, buf);
 #pragma unroll
-          for (int k = 0; k < 16; ++k) buf[k] = 0;
-        }
+        for (int i = 0; i < 16; ++i) buf[i] = 0;
       }
     } else {
-      for (int i = 0; i < nwords; ++i) {
-        uint32_t x = w[i];
-        put_byte((uint8_t)x);
-        put_byte((uint8_t)(x >> 8));
-        put_byte((uint8_t)(x >> 16));
-        put_byte((uint8_t)(x >> 24));
+      const uint32_t sh = 8 * k;
+      buf[wi] |= x >> sh;
+      const uint32_t rest = x << (32 - sh);
+      if (wi == 15) {
+        sha256_compress(h, buf);
+#pragma unroll
+        for (int i = 1; i < 16; ++i) buf[i] = 0;
+        buf[0] = rest;
+      } else {
+        buf[wi + 1] |= rest;
       }
     }
+  }
+  // little-endian 32-bit words of a field element (wire bytes = LE)
+  LF_HD void update_le_words(const uint32_t* w, int nwords) {
+    for (int i = 0; i < nwords; ++i) put_word_be(bswap32(w[i]));
   }
   // digest of the bytes so far, without disturbing the running state
   // (Transcript::get, lib/random/transcript.h:99-105). out = 8 big-endian words
@@ -305,7 +313,8 @@ struct Transcript {
     sha.put_byte(b);
   }
   LF_HD void raw_len(uint64_t x) {
-    for (int i = 0; i < 8; ++i) sha.put_byte((uint8_t)(x >> (8 * i)));
+    sha.put_word_be(bswap32((uint32_t)x));
+    sha.put_word_be(bswap32((uint32_t)(x >> 32)));
   }
   // transcript.h:76-79
   LF_HD void init(const uint8_t* seed, uint32_t n) {
@@ -373,9 +382,14 @@ struct Transcript {
   // nwords LE words of challenge bytes
   LF_HD void words(uint32_t* out, int nwords) {
     for (int i = 0; i < nwords; ++i) {
-      uint32_t x = 0;
-      for (int k = 0; k < 4; ++k) x |= (uint32_t)next_byte() << (8 * k);
-      out[i] = x;
+      if (have_prf && (rdptr & 3) == 0 && rdptr < 16) {
+        out[i] = saved[rdptr >> 2];
+        rdptr += 4;
+      } else {
+        uint32_t x = 0;
+        for (int k = 0; k < 4; ++k) x |= (uint32_t)next_byte() << (8 * k);
+        out[i] = x;
+      }
     }
   }
   // RandomEngine::nat (lib/random/random.h:57-88)

@@ -228,13 +228,26 @@ k_zk_eval_layer(ZkDims d, ZkBufs<typename F::Elt> b, const uint32_t* __restrict_
 // k_zk_sumcheck: the whole layered sumcheck of one proof in one persistent CTA,
 // Fiat-Shamir transcript included (thread 0), so that the 2*sum(logw)
 // sequential rounds never leave the SM.
+//
+// All sparse sums are BALANCED SEGMENTED SUMS: the circuit's constant wire 0
+// appears in tens of thousands of quad terms, so one QW row (and one bind_g
+// corner) can own most of the work.  Every thread therefore takes an equal
+// contiguous slice of the CSR-ordered entries, sums runs of equal segment id,
+// stores complete segments directly and parks the partial of a segment that
+// started in an earlier slice in shared memory; the slice that owns the start
+// of the segment adds those partials after one barrier.  Sums are exact field
+// sums, so the regrouping cannot change the result.
 // ----------------------------------------------------------------------------
+constexpr int kScMaxThreads = 1024;
+
 template <class F>
 struct ScShared {
   Transcript ts;
   typename F::Elt G[2][40];   // bindings of the previous layer (Proof::kMaxBindings)
-  typename F::Elt red[2][8];  // per-warp partials of a0, a2
+  typename F::Elt red[2][kScMaxThreads / 32];  // per-warp partials of a0, a2
   typename F::Elt r, alpha, beta, sum, wc[2];
+  typename F::Elt hp[kScMaxThreads];  // head partials of the segmented sums
+  uint32_t hr[kScMaxThreads];         // their segment ids
   int fail;
 };
 
@@ -248,6 +261,59 @@ __device__ __forceinline__ typename F::Elt warp_sum(typename F::Elt s) {
     s = F::add(s, t);
   }
   return s;
+}
+
+// out[seg] = sum over the entries e of that segment of term(e); seg[] is
+// non-decreasing over e in [0, n).  Segments without entries are not touched.
+// Contains two __syncthreads(); all threads of the CTA must call it.
+template <class F, class Term>
+__device__ __forceinline__ void seg_sum(ScShared<F>* sh, uint32_t n, const uint32_t* __restrict__ seg,
+                                        typename F::Elt* __restrict__ out, Term term) {
+  typedef typename F::Elt Elt;
+  typedef typename F::Acc Acc;
+  const uint32_t tid = threadIdx.x, nth = blockDim.x;
+  const uint32_t per = (n + nth - 1) / nth;
+  const uint32_t e0 = min(n, tid * per), e1 = min(n, e0 + per);
+  const uint32_t kNone = 0xffffffffu;
+  sh->hr[tid] = kNone;
+  uint32_t own_last = kNone;  // segment whose start this slice owns and which is still open at e1
+  if (e0 < e1) {
+    uint32_t cur = seg[e0];
+    bool head = e0 > 0 && seg[e0 - 1] == cur;
+    Acc acc;
+    F::acc_zero(acc);
+    for (uint32_t e = e0; e < e1; ++e) {
+      uint32_t sg = seg[e];
+      if (sg != cur) {
+        Elt v = F::reduce(acc);
+        if (head) {
+          sh->hp[tid] = v;
+          sh->hr[tid] = cur;
+        } else {
+          out[cur] = v;
+        }
+        head = false;
+        cur = sg;
+        F::acc_zero(acc);
+      }
+      term(acc, e);
+    }
+    Elt v = F::reduce(acc);
+    if (head) {
+      sh->hp[tid] = v;
+      sh->hr[tid] = cur;
+    } else {
+      out[cur] = v;
+      if (e1 < n && seg[e1] == cur) own_last = cur;
+    }
+  }
+  __syncthreads();
+  if (own_last != kNone) {
+    Elt v = out[own_last];
+    for (uint32_t t = tid + 1; t < nth && sh->hr[t] == own_last; ++t) v = F::add(v, sh->hp[t]);
+    out[own_last] = v;
+  }
+  __syncthreads();
 }
 
 // serial part of one round, thread 0 only (prover_layers.h:244-251,320-329,
@@ -287,13 +353,58 @@ __device__ __noinline__ void sc_round_serial(ScShared<F>* sh, typename F::Elt a0
 }
 
 template <class F>
-__global__ void __launch_bounds__(256)
-k_zk_sumcheck(ZkDims d, ZkBufs<typename F::Elt> b, const uint32_t* __restrict__ arena,
-              const LayerDesc* __restrict__ layers, const StepDesc* __restrict__ steps,
-              const typename F::Elt* __restrict__ consts) {
+__device__ __noinline__ void sc_begin(ScShared<F>* sh, const Transcript* src) {
+  sh->ts = *src;
+  sh->ts.have_prf = 0;  // Transcript::clone() carries only the hash (transcript.h:86)
+  // begin_circuit: Q[40] then G[40] (transcript_sumcheck.h:49-52)
+  for (int i = 0; i < 40; ++i) (void)ts_elt(&sh->ts, (F*)nullptr);
+  for (int i = 0; i < 40; ++i) {
+    typename F::Elt g = ts_elt(&sh->ts, (F*)nullptr);
+    sh->G[0][i] = g;
+    sh->G[1][i] = g;
+  }
+  sh->wc[0] = F::zero();
+  sh->wc[1] = F::zero();
+  sh->fail = 0;
+}
+
+template <class F>
+__device__ __noinline__ void sc_begin_layer(ScShared<F>* sh, typename F::Elt* alpha_out) {
+  sh->alpha = ts_elt(&sh->ts, (F*)nullptr);
+  sh->beta = ts_elt(&sh->ts, (F*)nullptr);
+  *alpha_out = sh->alpha;
+  sh->sum = F::add(sh->wc[0], F::mul(sh->alpha, sh->wc[1]));
+}
+
+template <class F>
+__device__ __noinline__ void sc_end_layer(ScShared<F>* sh, typename F::Elt hquad, typename F::Elt w0,
+                                         typename F::Elt w1, const typename F::Elt* padwc,
+                                         typename F::Elt* proofwc, typename F::Elt* bq_out) {
+  typedef typename F::Elt Elt;
+  Elt expect = F::mul(hquad, F::mul(w0, w1));
+  if (!F::eq(expect, sh->sum)) sh->fail = 1;
+  sh->wc[0] = w0;
+  sh->wc[1] = w1;
+  *bq_out = hquad;
+  Elt t0 = F::sub(w0, padwc[0]), t1 = F::sub(w1, padwc[1]);
+  proofwc[0] = t0;
+  proofwc[1] = t1;
+  sh->ts.begin_array(2);
+  ts_array_elt(&sh->ts, t0);
+  ts_array_elt(&sh->ts, t1);
+}
+
+// The kernel body is shared by two launch configurations (throughput: many
+// small CTAs per SM so that one proof's serial transcript hides under the
+// others' parallel work; latency: one large CTA per proof).
+template <class F>
+__device__ __forceinline__ void sumcheck_body(const ZkDims& d, const ZkBufs<typename F::Elt>& b,
+                                              const uint32_t* __restrict__ arena,
+                                              const LayerDesc* __restrict__ layers,
+                                              const StepDesc* __restrict__ steps,
+                                              const typename F::Elt* __restrict__ consts, ScShared<F>& sh) {
   typedef typename F::Elt Elt;
   typedef typename F::Acc Acc;
-  __shared__ ScShared<F> sh;
   const size_t p = blockIdx.x;
   const uint32_t tid = threadIdx.x, nth = blockDim.x;
   if (b.status[p] != 0) return;  // witness already rejected by eval_circuit
@@ -301,36 +412,21 @@ k_zk_sumcheck(ZkDims d, ZkBufs<typename F::Elt> b, const uint32_t* __restrict__ 
   Elt* wl = b.wl + p * d.wl_elts;
   Elt* whbuf = b.wh + p * 4 * (size_t)d.max_nw;
   Elt* hqbuf = b.hq + p * 2 * (size_t)d.max_hq;
-  Elt* E0 = b.eq + p * 2 * (size_t)d.max_eq;
+  Elt* E0 = b.eq + p * 3 * (size_t)d.max_eq;
   Elt* E1 = E0 + d.max_eq;
+  Elt* QW = E1 + d.max_eq;
   Elt* sc = b.sc + p * d.sc_elts;
   const Elt* wit = b.wit + p * d.nw;
   Elt* hbs = b.hb + p * d.nhb;
 
-  if (tid == 0) {
-    sh.ts = *reinterpret_cast<const Transcript*>(b.ts + p * sizeof(Transcript));
-    sh.ts.have_prf = 0;  // Transcript::clone() carries only the hash (transcript.h:86)
-    // begin_circuit: Q[40] then G[40] (transcript_sumcheck.h:49-52)
-    for (int i = 0; i < 40; ++i) (void)ts_elt(&sh.ts, (F*)nullptr);
-    for (int i = 0; i < 40; ++i) {
-      Elt g = ts_elt(&sh.ts, (F*)nullptr);
-      sh.G[0][i] = g;
-      sh.G[1][i] = g;
-    }
-    sh.wc[0] = F::zero();
-    sh.wc[1] = F::zero();
-    sh.fail = 0;
-  }
+  if (tid == 0) sc_begin<F>(&sh, reinterpret_cast<const Transcript*>(b.ts + p * sizeof(Transcript)));
   __syncthreads();
 
   uint32_t logv = d.logv;
   for (uint32_t ly = 0; ly < d.nl; ++ly) {
     const LayerDesc L = layers[ly];
     if (tid == 0) {
-      sh.alpha = ts_elt(&sh.ts, (F*)nullptr);
-      sh.beta = ts_elt(&sh.ts, (F*)nullptr);
-      b.alphas[p * d.nl + ly] = sh.alpha;
-      sh.sum = F::add(sh.wc[0], F::mul(sh.alpha, sh.wc[1]));
+      sc_begin_layer<F>(&sh, &b.alphas[p * d.nl + ly]);
       E0[0] = F::one();
       E1[0] = sh.alpha;
     }
@@ -353,24 +449,17 @@ k_zk_sumcheck(ZkDims d, ZkBufs<typename F::Elt> b, const uint32_t* __restrict__ 
       }
       __syncthreads();
     }
-    // Quad::bind_g (quad.h:152-185): initial HQuad values
+    // Quad::bind_g (quad.h:152-185): initial HQuad values, one segment per corner
     {
-      const uint32_t* off = arena + L.bg_off;
       const uint32_t *tg = arena + L.bg_g, *tv = arena + L.bg_vi;
       const Elt beta = sh.beta;
-      for (uint32_t k = tid; k < L.nhq0; k += nth) {
-        Acc acc;
-        F::acc_zero(acc);
-        for (uint32_t t = off[k]; t < off[k + 1]; ++t) {
-          uint32_t g = tg[t], v = tv[t];
-          Elt dot = F::add(E0[g], E1[g]);
-          if (v & kViOne) F::acc_add_elt(acc, dot);
-          else F::mac(acc, (v & kViZero) ? beta : consts[v & kViMask], dot);
-        }
-        hqbuf[k] = F::reduce(acc);
-      }
+      seg_sum<F>(&sh, L.nterms, arena + L.bg_seg, hqbuf, [&](Acc& acc, uint32_t t) {
+        uint32_t g = tg[t], v = tv[t];
+        Elt dot = F::add(E0[g], E1[g]);
+        if (v & kViOne) F::acc_add_elt(acc, dot);
+        else F::mac(acc, (v & kViZero) ? beta : consts[v & kViMask], dot);
+      });
     }
-    __syncthreads();
 
     const Elt* wcur[2] = {wl + L.w_off, wl + L.w_off};
     uint32_t wpar[2] = {0, 0};
@@ -383,32 +472,27 @@ k_zk_sumcheck(ZkDims d, ZkBufs<typename F::Elt> b, const uint32_t* __restrict__ 
       const Elt* Wh = wcur[hand];
       const Elt* Wo = wcur[oh];
       const Elt* HQ = hqbuf + (size_t)hqpar * d.max_hq;
-      const uint32_t* roff = arena + S.row_off;
-      const uint32_t *rc = arena + S.row_c, *rp = arena + S.row_p1;
-      // QW[l] = sum_r Q[l,r] W[r] fused with the two dot products of
-      // ProverLayers::evaluations (prover_layers.h:230-243,357-402)
-      Acc a0, a2;
-      F::acc_zero(a0);
-      F::acc_zero(a2);
-      const uint32_t npair = (S.n0 + 1) / 2;
-      for (uint32_t i = tid; i < npair; i += nth) {
-        Acc q0;
-        F::acc_zero(q0);
-        for (uint32_t e = roff[2 * i]; e < roff[2 * i + 1]; ++e) F::mac(q0, HQ[rc[e]], Wo[rp[e]]);
-        Elt qw0 = F::reduce(q0), w0 = Wh[2 * i];
-        if (2 * i + 1 < S.n0) {
-          Acc q1;
-          F::acc_zero(q1);
-          for (uint32_t e = roff[2 * i + 1]; e < roff[2 * i + 2]; ++e) F::mac(q1, HQ[rc[e]], Wo[rp[e]]);
-          Elt qw1 = F::reduce(q1), w1 = Wh[2 * i + 1];
-          F::mac(a0, qw0, w0);
-          F::mac(a2, F::sub(qw1, qw0), F::sub(w1, w0));
-        } else {
-          F::mac(a0, qw0, w0);
-          F::mac(a2, qw0, w0);
-        }
-      }
+      // QW[l] = sum_r Q[l,r] W[r]  (prover_layers.h:230-243)
       {
+        const uint32_t* roff = arena + S.row_off;
+        for (uint32_t i = tid; i < S.n0; i += nth)
+          if (roff[i] == roff[i + 1]) QW[i] = F::zero();
+        const uint32_t *rc = arena + S.row_c, *rp = arena + S.row_p1;
+        seg_sum<F>(&sh, S.n_in, arena + S.row_r, QW,
+                   [&](Acc& acc, uint32_t e) { F::mac(acc, HQ[rc[e]], Wo[rp[e]]); });
+      }
+      // the two dot products of ProverLayers::evaluations (prover_layers.h:357-402)
+      const uint32_t npair = (S.n0 + 1) / 2;
+      {
+        Acc a0, a2;
+        F::acc_zero(a0);
+        F::acc_zero(a2);
+        for (uint32_t i = tid; i < npair; i += nth) {
+          Elt qw0 = QW[2 * i], w0 = Wh[2 * i];
+          F::mac(a0, qw0, w0);
+          if (2 * i + 1 < S.n0) F::mac(a2, F::sub(QW[2 * i + 1], qw0), F::sub(Wh[2 * i + 1], w0));
+          else F::mac(a2, qw0, w0);
+        }
         Elt s0 = warp_sum<F>(F::reduce(a0)), s2 = warp_sum<F>(F::reduce(a2));
         if ((tid & 31) == 0) {
           sh.red[0][tid >> 5] = s0;
@@ -450,21 +534,9 @@ k_zk_sumcheck(ZkDims d, ZkBufs<typename F::Elt> b, const uint32_t* __restrict__ 
       hqpar ^= 1;
     }
     // end of layer (prover_layers.h:263-270,331-344)
-    if (tid == 0) {
-      Elt hquad = hqbuf[(size_t)hqpar * d.max_hq];
-      Elt w0 = wcur[0][0], w1 = wcur[1][0];
-      Elt expect = F::mul(hquad, F::mul(w0, w1));
-      if (!F::eq(expect, sh.sum)) sh.fail = 1;
-      sh.wc[0] = w0;
-      sh.wc[1] = w1;
-      b.bq[p * d.nl + ly] = hquad;
-      Elt t0 = F::sub(w0, pad[4 * L.logw]), t1 = F::sub(w1, pad[4 * L.logw + 1]);
-      sc[L.sc_off + 4 * L.logw] = t0;
-      sc[L.sc_off + 4 * L.logw + 1] = t1;
-      sh.ts.begin_array(2);
-      ts_array_elt(&sh.ts, t0);
-      ts_array_elt(&sh.ts, t1);
-    }
+    if (tid == 0)
+      sc_end_layer<F>(&sh, hqbuf[(size_t)hqpar * d.max_hq], wcur[0][0], wcur[1][0], pad + 4 * L.logw,
+                      sc + L.sc_off + 4 * L.logw, &b.bq[p * d.nl + ly]);
     __syncthreads();
     logv = L.logw;
   }
@@ -472,6 +544,23 @@ k_zk_sumcheck(ZkDims d, ZkBufs<typename F::Elt> b, const uint32_t* __restrict__ 
     *reinterpret_cast<Transcript*>(b.ts + p * sizeof(Transcript)) = sh.ts;
     if (sh.fail) b.status[p] = -100;  // internal inconsistency: never expected
   }
+}
+
+template <class F>
+__global__ void __launch_bounds__(128, 4)
+k_zk_sumcheck_tp(ZkDims d, ZkBufs<typename F::Elt> b, const uint32_t* __restrict__ arena,
+                 const LayerDesc* __restrict__ layers, const StepDesc* __restrict__ steps,
+                 const typename F::Elt* __restrict__ consts) {
+  __shared__ ScShared<F> sh;
+  sumcheck_body<F>(d, b, arena, layers, steps, consts, sh);
+}
+template <class F>
+__global__ void __launch_bounds__(kScMaxThreads, 1)
+k_zk_sumcheck_lat(ZkDims d, ZkBufs<typename F::Elt> b, const uint32_t* __restrict__ arena,
+                  const LayerDesc* __restrict__ layers, const StepDesc* __restrict__ steps,
+                  const typename F::Elt* __restrict__ consts) {
+  __shared__ ScShared<F> sh;
+  sumcheck_body<F>(d, b, arena, layers, steps, consts, sh);
 }
 
 // ----------------------------------------------------------------------------
@@ -503,7 +592,7 @@ k_lig_input_eq(ZkDims d, ZkBufs<typename F::Elt> b, LayerDesc last) {
   typedef typename F::Elt Elt;
   const size_t p = blockIdx.x;
   if (b.status[p] != 0) return;
-  Elt* E0 = b.eq + p * 2 * (size_t)d.max_eq;
+  Elt* E0 = b.eq + p * 3 * (size_t)d.max_eq;
   Elt* E1 = E0 + d.max_eq;
   const Elt* hb = b.hb + p * d.nhb + last.hb_off;  // [2*round + hand]
   if (threadIdx.x == 0) {
@@ -573,7 +662,7 @@ k_lig_avec(ZkDims d, ZkBufs<typename F::Elt> b, const LayerDesc* __restrict__ la
   const Elt* bq = b.bq + p * d.nl;
   const Elt* alphas = b.alphas + p * d.nl;
   Elt* lagbuf = reinterpret_cast<Elt*>(b.scratch + p * b.scratch_words);  // [nhb][4]: lag0,lag1,lag2,P
-  const Elt* E0 = b.eq + p * 2 * (size_t)d.max_eq;
+  const Elt* E0 = b.eq + p * 3 * (size_t)d.max_eq;
   const Elt* E1 = E0 + d.max_eq;
 
   const uint32_t na = d.nwqrow * d.w;

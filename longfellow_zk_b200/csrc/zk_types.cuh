@@ -26,7 +26,7 @@ struct LayerDesc {
   // offsets into the uint32 arena
   uint32_t ev_off;   // [nout+1] CSR by gate: eval_circuit
   uint32_t ev_h0, ev_h1, ev_vi;  // [nterms]
-  uint32_t bg_off;   // [nhq0+1] terms of each initial HQuad corner (canonical order)
+  uint32_t bg_seg;   // [nterms] initial HQuad corner of each term (canonical order, non-decreasing)
   uint32_t bg_g, bg_vi;          // [nterms]
   uint32_t step0;    // first StepDesc of this layer (2*logw of them)
   uint32_t w_off;    // element offset of this layer's input wires in the per-proof wire store
@@ -41,6 +41,7 @@ struct StepDesc {
   uint32_t n_out;    // corners after bind_h
   uint32_t n0;       // length of the hand's wire array before the round
   uint32_t row_off;  // [n0+1] CSR by p0 = h[hand]
+  uint32_t row_r;    // [n_in] p0 of each CSR entry (non-decreasing)
   uint32_t row_c;    // [n_in] corner index
   uint32_t row_p1;   // [n_in] h[other hand]
   uint32_t merge;    // [n_out] (src << 2) | kind ; kind 0 pair, 1 lone even, 2 lone odd
@@ -76,7 +77,7 @@ struct ZkBufs {
   Elt* wl;         // [wl_elts] wires of every layer
   Elt* wh;         // [4 * max_nw] hand arrays, ping-pong
   Elt* hq;         // [2 * max_hq] HQuad values, ping-pong
-  Elt* eq;         // [2 * max_eq] EQ tables
+  Elt* eq;         // [3 * max_eq] EQ tables E0, E1 and the QW array
   Elt* sc;         // [sc_elts] sumcheck proof in wire order
   Elt* bq;         // [nl] bound quads (ProofAux)
   Elt* hb;         // [nhb] hand challenges
