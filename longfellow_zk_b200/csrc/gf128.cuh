@@ -74,7 +74,7 @@ __host__ __device__ __forceinline__ void clmul64(uint32_t a0, uint32_t a1, uint3
 }
 
 // Unreduced 128x128 -> 256-bit product, t[0..7] (two Karatsuba levels).
-__host__ __device__ __forceinline__ void gf_mul_wide(const gf128& a, const gf128& b, uint32_t t[8]) {
+__host__ __device__ __forceinline__ void gf_mul_wide_inl(const gf128& a, const gf128& b, uint32_t t[8]) {
   uint32_t lo[4], hi[4], mid[4];
   clmul64(a.w[0], a.w[1], b.w[0], b.w[1], lo);
   clmul64(a.w[2], a.w[3], b.w[2], b.w[3], hi);
@@ -90,6 +90,31 @@ __host__ __device__ __forceinline__ void gf_mul_wide(const gf128& a, const gf128
   t[6] = hi[2];
   t[7] = hi[3];
 }
+
+// On the device the ~450-instruction product is ONE out-of-line function: the
+// sumcheck kernel multiplies at a dozen sites, and inlining every one of them
+// made the kernel body > 100 KB, i.e. instruction-cache bound (ncu: 36 % of the
+// stall samples were "no instruction", profiles/r1_sumcheck_before.txt).
+// Arguments and the 8-word result travel in registers (no local memory).
+struct gf_wide {
+  uint32_t t[8];
+};
+#if defined(__CUDA_ARCH__) && !defined(LF_GF_INLINE_MUL)
+static __device__ __noinline__ gf_wide gf_mul_wide_fn(gf128 a, gf128 b) {
+  gf_wide w;
+  gf_mul_wide_inl(a, b, w.t);
+  return w;
+}
+__device__ __forceinline__ void gf_mul_wide(const gf128& a, const gf128& b, uint32_t t[8]) {
+  gf_wide w = gf_mul_wide_fn(a, b);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) t[i] = w.t[i];
+}
+#else
+__host__ __device__ __forceinline__ void gf_mul_wide(const gf128& a, const gf128& b, uint32_t t[8]) {
+  gf_mul_wide_inl(a, b, t);
+}
+#endif
 
 // Reduce a 256-bit polynomial modulo x^128 + x^7 + x^2 + x + 1
 // (same two folds as lib/gf2k/sysdep.h:45-66).
@@ -113,6 +138,11 @@ __host__ __device__ __forceinline__ gf128 gf_reduce(const uint32_t t[8]) {
 __host__ __device__ __forceinline__ gf128 gf_mul(const gf128& a, const gf128& b) {
   uint32_t t[8];
   gf_mul_wide(a, b, t);
+  return gf_reduce(t);
+}
+__host__ __device__ __forceinline__ gf128 gf_mul_inl(const gf128& a, const gf128& b) {
+  uint32_t t[8];
+  gf_mul_wide_inl(a, b, t);
   return gf_reduce(t);
 }
 

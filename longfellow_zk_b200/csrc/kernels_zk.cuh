@@ -437,15 +437,10 @@ __device__ __forceinline__ void sumcheck_body(const ZkDims& d, const ZkBufs<type
       const Elt g0 = sh.G[0][l], g1 = sh.G[1][l];
       for (uint32_t i = tid; i < 2 * S; i += nth) {
         uint32_t k = i & (S - 1);
-        if (i < S) {
-          Elt v = E0[k], hi = F::mul(v, g0);
-          E0[k] = F::sub(v, hi);
-          E0[k + S] = hi;
-        } else {
-          Elt v = E1[k], hi = F::mul(v, g1);
-          E1[k] = F::sub(v, hi);
-          E1[k + S] = hi;
-        }
+        Elt* E = (i < S) ? E0 : E1;
+        Elt v = E[k], hi = F::mul(v, (i < S) ? g0 : g1);
+        E[k] = F::sub(v, hi);
+        E[k + S] = hi;
       }
       __syncthreads();
     }
@@ -489,9 +484,11 @@ __device__ __forceinline__ void sumcheck_body(const ZkDims& d, const ZkBufs<type
         F::acc_zero(a2);
         for (uint32_t i = tid; i < npair; i += nth) {
           Elt qw0 = QW[2 * i], w0 = Wh[2 * i];
+          // odd tail (prover_layers.h:377-384): a2 += qw0*w0 = (0-qw0)*(0-w0)
+          const bool two = 2 * i + 1 < S.n0;
+          Elt qw1 = two ? QW[2 * i + 1] : F::zero(), w1 = two ? Wh[2 * i + 1] : F::zero();
           F::mac(a0, qw0, w0);
-          if (2 * i + 1 < S.n0) F::mac(a2, F::sub(QW[2 * i + 1], qw0), F::sub(Wh[2 * i + 1], w0));
-          else F::mac(a2, qw0, w0);
+          F::mac(a2, F::sub(qw1, qw0), F::sub(w1, w0));
         }
         Elt s0 = warp_sum<F>(F::reduce(a0)), s2 = warp_sum<F>(F::reduce(a2));
         if ((tid & 31) == 0) {
@@ -516,17 +513,21 @@ __device__ __forceinline__ void sumcheck_body(const ZkDims& d, const ZkBufs<type
       // Dense::bind (dense.h:70-89)
       Elt* Wn = whbuf + (size_t)(2 * hand + wpar[hand]) * d.max_nw;
       for (uint32_t i = tid; i < npair; i += nth) {
-        Elt f0 = Wh[2 * i];
-        Wn[i] = (2 * i + 1 < S.n0) ? affine<F>(r, f0, Wh[2 * i + 1]) : affine_nz_z<F>(r, f0);
+        // affine_interpolation_nz_z(r, f0) == affine_interpolation(r, f0, 0) (affine.h:25-52)
+        Elt f0 = Wh[2 * i], f1 = (2 * i + 1 < S.n0) ? Wh[2 * i + 1] : F::zero();
+        Wn[i] = affine<F>(r, f0, f1);
       }
       // HQuad::bind_h (hquad.h:89-123) through the merge plan
       Elt* HQn = hqbuf + (size_t)(hqpar ^ 1) * d.max_hq;
       const uint32_t* mg = arena + S.merge;
       for (uint32_t j = tid; j < S.n_out; j += nth) {
+        // pair: (v0, v1); lone even corner: (v0, 0); lone odd corner: (0, v0) -- the
+        // three affine_interpolation variants of hquad.h:99-115 are one formula
         uint32_t m = mg[j], src = m >> 2, kind = m & 3;
-        Elt v0 = HQ[src];
-        HQn[j] = kind == 0 ? affine<F>(r, v0, HQ[src + 1])
-                           : (kind == 1 ? affine_nz_z<F>(r, v0) : affine_z_nz<F>(r, v0));
+        Elt v = HQ[src];
+        Elt f0 = kind == 2 ? F::zero() : v;
+        Elt f1 = kind == 0 ? HQ[src + 1] : (kind == 2 ? v : F::zero());
+        HQn[j] = affine<F>(r, f0, f1);
       }
       __syncthreads();
       wcur[hand] = Wn;

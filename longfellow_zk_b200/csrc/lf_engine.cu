@@ -288,8 +288,8 @@ __global__ void k_bench_gfmul(gf128* out, int iters) {
   a.w[0] = threadIdx.x * 2654435761u + 1; a.w[1] = blockIdx.x + 3; a.w[2] = 0x9e3779b9u; a.w[3] = threadIdx.x;
   b.w[0] = 0x85ebca6bu; b.w[1] = threadIdx.x ^ 0xc2b2ae35u; b.w[2] = blockIdx.x; b.w[3] = 0x27d4eb2fu;
   for (int i = 0; i < iters; ++i) {
-    a = gf_mul(a, b);
-    b = gf_mul(b, a);
+    a = gf_mul_inl(a, b);
+    b = gf_mul_inl(b, a);
   }
   out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = gf_add(a, b);
 }
