@@ -246,8 +246,8 @@ struct ScShared {
   typename F::Elt G[2][40];   // bindings of the previous layer (Proof::kMaxBindings)
   typename F::Elt red[2][kScMaxThreads / 32];  // per-warp partials of a0, a2
   typename F::Elt r, alpha, beta, sum, wc[2];
-  typename F::Elt hp[kScMaxThreads];  // head partials of the segmented sums
-  uint32_t hr[kScMaxThreads];         // their segment ids
+  typename F::Elt* hp;  // [blockDim.x] head partials of the segmented sums
+  uint32_t* hr;         // [blockDim.x] their segment ids
   int fail;
 };
 
@@ -456,16 +456,16 @@ __device__ __forceinline__ void sumcheck_body(const ZkDims& d, const ZkBufs<type
       });
     }
 
-    const Elt* wcur[2] = {wl + L.w_off, wl + L.w_off};
-    uint32_t wpar[2] = {0, 0};
+    const Elt *wcur0 = wl + L.w_off, *wcur1 = wl + L.w_off;  // current array of each hand
+    uint32_t wpar0 = 0, wpar1 = 0;
     uint32_t hqpar = 0;
     const Elt* pad = wit + d.n_witness + L.pad_off;
 
     for (uint32_t t = 0; t < 2 * L.logw; ++t) {
       const StepDesc S = steps[L.step0 + t];
-      const uint32_t hand = t & 1, oh = hand ^ 1, round = t >> 1;
-      const Elt* Wh = wcur[hand];
-      const Elt* Wo = wcur[oh];
+      const uint32_t hand = t & 1, round = t >> 1;
+      const Elt* Wh = hand ? wcur1 : wcur0;
+      const Elt* Wo = hand ? wcur0 : wcur1;
       const Elt* HQ = hqbuf + (size_t)hqpar * d.max_hq;
       // QW[l] = sum_r Q[l,r] W[r]  (prover_layers.h:230-243)
       {
@@ -511,7 +511,7 @@ __device__ __forceinline__ void sumcheck_body(const ZkDims& d, const ZkBufs<type
       __syncthreads();
       const Elt r = sh.r;
       // Dense::bind (dense.h:70-89)
-      Elt* Wn = whbuf + (size_t)(2 * hand + wpar[hand]) * d.max_nw;
+      Elt* Wn = whbuf + (size_t)(2 * hand + (hand ? wpar1 : wpar0)) * d.max_nw;
       for (uint32_t i = tid; i < npair; i += nth) {
         // affine_interpolation_nz_z(r, f0) == affine_interpolation(r, f0, 0) (affine.h:25-52)
         Elt f0 = Wh[2 * i], f1 = (2 * i + 1 < S.n0) ? Wh[2 * i + 1] : F::zero();
@@ -530,13 +530,18 @@ __device__ __forceinline__ void sumcheck_body(const ZkDims& d, const ZkBufs<type
         HQn[j] = affine<F>(r, f0, f1);
       }
       __syncthreads();
-      wcur[hand] = Wn;
-      wpar[hand] ^= 1;
+      if (hand) {
+        wcur1 = Wn;
+        wpar1 ^= 1;
+      } else {
+        wcur0 = Wn;
+        wpar0 ^= 1;
+      }
       hqpar ^= 1;
     }
     // end of layer (prover_layers.h:263-270,331-344)
     if (tid == 0)
-      sc_end_layer<F>(&sh, hqbuf[(size_t)hqpar * d.max_hq], wcur[0][0], wcur[1][0], pad + 4 * L.logw,
+      sc_end_layer<F>(&sh, hqbuf[(size_t)hqpar * d.max_hq], wcur0[0], wcur1[0], pad + 4 * L.logw,
                       sc + L.sc_off + 4 * L.logw, &b.bq[p * d.nl + ly]);
     __syncthreads();
     logv = L.logw;
@@ -547,12 +552,35 @@ __device__ __forceinline__ void sumcheck_body(const ZkDims& d, const ZkBufs<type
   }
 }
 
+constexpr int kScTpThreads = 128;
 template <class F>
-__global__ void __launch_bounds__(128, 4)
+__global__ void __launch_bounds__(kScTpThreads, 8)
 k_zk_sumcheck_tp(ZkDims d, ZkBufs<typename F::Elt> b, const uint32_t* __restrict__ arena,
                  const LayerDesc* __restrict__ layers, const StepDesc* __restrict__ steps,
                  const typename F::Elt* __restrict__ consts) {
   __shared__ ScShared<F> sh;
+  __shared__ typename F::Elt hp[kScTpThreads];
+  __shared__ uint32_t hr[kScTpThreads];
+  if (threadIdx.x == 0) {
+    sh.hp = hp;
+    sh.hr = hr;
+  }
+  __syncthreads();
+  sumcheck_body<F>(d, b, arena, layers, steps, consts, sh);
+}
+template <class F>
+__global__ void __launch_bounds__(kScTpThreads, 4)
+k_zk_sumcheck_tp4(ZkDims d, ZkBufs<typename F::Elt> b, const uint32_t* __restrict__ arena,
+                  const LayerDesc* __restrict__ layers, const StepDesc* __restrict__ steps,
+                  const typename F::Elt* __restrict__ consts) {
+  __shared__ ScShared<F> sh;
+  __shared__ typename F::Elt hp[kScTpThreads];
+  __shared__ uint32_t hr[kScTpThreads];
+  if (threadIdx.x == 0) {
+    sh.hp = hp;
+    sh.hr = hr;
+  }
+  __syncthreads();
   sumcheck_body<F>(d, b, arena, layers, steps, consts, sh);
 }
 template <class F>
@@ -561,6 +589,13 @@ k_zk_sumcheck_lat(ZkDims d, ZkBufs<typename F::Elt> b, const uint32_t* __restric
                   const LayerDesc* __restrict__ layers, const StepDesc* __restrict__ steps,
                   const typename F::Elt* __restrict__ consts) {
   __shared__ ScShared<F> sh;
+  __shared__ typename F::Elt hp[kScMaxThreads];
+  __shared__ uint32_t hr[kScMaxThreads];
+  if (threadIdx.x == 0) {
+    sh.hp = hp;
+    sh.hr = hr;
+  }
+  __syncthreads();
   sumcheck_body<F>(d, b, arena, layers, steps, consts, sh);
 }
 
