@@ -89,6 +89,16 @@ class LCH14ReedSolomonFactory:
         return _Interpolator(self.ctx, FIELD_GF2_128, n, m)
 
 
+class ReedSolomonFactory:
+    """algebra/reed_solomon.h:132-147 (prime fields): make(n, m)->interpolate(y)."""
+
+    def __init__(self, ctx, field_id):
+        self.ctx, self.field_id = ctx, field_id
+
+    def make(self, n, m):
+        return _Interpolator(self.ctx, self.field_id, n, m)
+
+
 class MerkleCommitment:
     """merkle/merkle_commitment.h:46-64, specialised to Ligero's column hash
     (ligero/ligero_param.h:432-439): leaf j = SHA256(nonce_j || column dblock+j)."""

@@ -6,7 +6,9 @@
 #pragma once
 #include <stdint.h>
 
+#include "fp.cuh"
 #include "gf128.cuh"
+#include "hash.cuh"
 
 namespace lf {
 
@@ -75,6 +77,29 @@ struct FGf128 {
   }
 
 #ifdef __CUDACC__
+  // ---- byte streams (wire bytes, caller randomness, transcript) ----
+  // 16 little-endian bytes are an element (gf2_128.h:171-190); never fails
+  __device__ static __forceinline__ Elt from_bytes(const uint8_t* p, bool* ok) {
+    Elt e;
+    if ((reinterpret_cast<uintptr_t>(p) & 3) == 0) {
+      const uint32_t* q = reinterpret_cast<const uint32_t*>(p);
+      e.w[0] = q[0]; e.w[1] = q[1]; e.w[2] = q[2]; e.w[3] = q[3];
+    } else {
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        e.w[k] = (uint32_t)p[4 * k] | ((uint32_t)p[4 * k + 1] << 8) | ((uint32_t)p[4 * k + 2] << 16) |
+                 ((uint32_t)p[4 * k + 3] << 24);
+    }
+    return e;
+  }
+  // Field::sample on a fixed-size slot of the caller's random stream
+  __device__ static __forceinline__ Elt sample_bytes(const uint8_t* p, bool* ok) { return from_bytes(p, ok); }
+  // RandomEngine::elt on the transcript (random.h:37-41, gf2_128.h:182-190)
+  __device__ static __forceinline__ Elt ts_elt(Transcript* ts) {
+    Elt e;
+    ts->words(e.w, 4);
+    return e;
+  }
   __device__ static __forceinline__ Elt evalpt(int i) { return c_gf.evalpt[i]; }
   __device__ static __forceinline__ Elt newton(int k, int i) { return c_gf.newton[k][i]; }
   __device__ static __forceinline__ Elt lag_id(int k, int i) { return c_gf.lag_id[k][i]; }
@@ -108,6 +133,139 @@ struct FGf128 {
     }
     *u = acc;
     return (x0 | x1 | x2 | x3) == 0;
+  }
+#endif
+};
+
+// ---------------------------------------------------------------------------
+// Fp256Base = FpGeneric<4, true, Fp256Reduce> (lib/algebra/fp_p256.h:64-65,
+// lib/ec/p256.h:42): the NIST P-256 base field.  sample_subfield == sample,
+// in_subfield == true, kSubFieldBytes == kBytes (fp_generic.h:278,373-400).
+// ---------------------------------------------------------------------------
+#ifdef __CUDACC__
+static __constant__ FpConsts<8> c_p256;
+#endif
+
+struct FFp256 {
+  typedef fpw<8> Elt;
+  static constexpr int kWords = 8;
+  static constexpr int kBytes = 32;
+  static constexpr int kSubBytes = 32;
+  static constexpr bool kChar2 = false;
+  static constexpr int kFieldId = 1;  // proto/circuit_io.h P256_ID
+
+  struct Acc {
+    Elt v;
+  };
+
+#ifdef __CUDACC__
+  // one out-of-line Montgomery product (same reason as gf_mul_wide_fn)
+  static __device__ __noinline__ Elt mul_fn(Elt a, Elt b) { return fp_mul_p256(a, b, c_p256.m); }
+  __device__ static __forceinline__ Elt zero() {
+    Elt r;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) r.w[i] = 0;
+    return r;
+  }
+  __device__ static __forceinline__ Elt one() {
+    Elt r;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) r.w[i] = c_p256.one[i];
+    return r;
+  }
+  __device__ static __forceinline__ Elt add(const Elt& a, const Elt& b) { return fp_add<8>(a, b, c_p256.m); }
+  __device__ static __forceinline__ Elt sub(const Elt& a, const Elt& b) { return fp_sub<8>(a, b, c_p256.m); }
+  __device__ static __forceinline__ Elt neg(const Elt& a) { return fp_sub<8>(zero(), a, c_p256.m); }
+  __device__ static __forceinline__ Elt mul(const Elt& a, const Elt& b) { return mul_fn(a, b); }
+  __device__ static __forceinline__ bool is_zero(const Elt& a) {
+    uint32_t o = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) o |= a.w[i];
+    return o == 0;
+  }
+  __device__ static __forceinline__ bool eq(const Elt& a, const Elt& b) {
+    uint32_t o = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) o |= a.w[i] ^ b.w[i];
+    return o == 0;
+  }
+  // the reference's Accum is a wide integer (fp_generic.h:424-440); an eager
+  // modular accumulator yields the same field element
+  __device__ static __forceinline__ void acc_zero(Acc& a) { a.v = zero(); }
+  __device__ static __forceinline__ void mac(Acc& a, const Elt& x, const Elt& y) { a.v = add(a.v, mul(x, y)); }
+  __device__ static __forceinline__ void acc_add_elt(Acc& a, const Elt& x) { a.v = add(a.v, x); }
+  __device__ static __forceinline__ void acc_add(Acc& a, const Acc& b) { a.v = add(a.v, b.v); }
+  __device__ static __forceinline__ Elt reduce(const Acc& a) { return a.v; }
+
+  // from_montgomery / to_montgomery (fp_generic.h:264-281)
+  __device__ static __forceinline__ void to_wire(uint32_t out[8], const Elt& a) {
+    Elt o;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) o.w[i] = 0;
+    o.w[0] = 1;
+    Elt r = mul(a, o);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) out[i] = r.w[i];
+  }
+  __device__ static __forceinline__ Elt from_wire(const uint32_t in[8]) {
+    Elt a, q;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      a.w[i] = in[i];
+      q.w[i] = c_p256.rsq[i];
+    }
+    return mul(a, q);
+  }
+  // of_bytes_field (fp_generic.h:351-358): *ok = false if the value is >= p
+  __device__ static __forceinline__ Elt from_bytes(const uint8_t* p, bool* ok) {
+    uint32_t in[8];
+    if ((reinterpret_cast<uintptr_t>(p) & 3) == 0) {
+      const uint32_t* q = reinterpret_cast<const uint32_t*>(p);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) in[k] = q[k];
+    } else {
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+        in[k] = (uint32_t)p[4 * k] | ((uint32_t)p[4 * k + 1] << 8) | ((uint32_t)p[4 * k + 2] << 16) |
+                ((uint32_t)p[4 * k + 3] << 24);
+    }
+    if (fp_geq<8>(in, c_p256.m)) *ok = false;
+    return from_wire(in);
+  }
+  // Field::sample on one 32-byte slot of the caller's stream (fp_generic.h:360-371).
+  // exact_bits == 256, so there is no masking; a value >= p (probability 2^-32)
+  // would make the reference draw again -- reported through *ok.
+  __device__ static __forceinline__ Elt sample_bytes(const uint8_t* p, bool* ok) { return from_bytes(p, ok); }
+  __device__ static __forceinline__ Elt ts_elt(Transcript* ts) {
+    uint32_t in[8];
+    for (;;) {
+      ts->words(in, 8);
+      if (!fp_geq<8>(in, c_p256.m)) break;
+    }
+    return from_wire(in);
+  }
+  __device__ static __forceinline__ Elt evalpt(int i) {
+    Elt r;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) r.w[k] = c_p256.evalpt[i][k];
+    return r;
+  }
+  __device__ static __forceinline__ Elt newton(int k, int i) {
+    Elt r;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) r.w[q] = c_p256.newton[k][i][q];
+    return r;
+  }
+  __device__ static __forceinline__ Elt lag_id(int k, int i) {
+    Elt r;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) r.w[q] = c_p256.lag_id[k][i][q];
+    return r;
+  }
+  __device__ static __forceinline__ Elt of_sub16(uint32_t) { return zero(); }        // never used
+  __device__ static __forceinline__ bool solve_sub16(const Elt&, uint32_t* u) {       // never used
+    *u = 0;
+    return true;
   }
 #endif
 };

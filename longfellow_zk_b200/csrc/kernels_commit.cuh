@@ -117,6 +117,54 @@ k_rs_gf_rows(typename F::Elt* __restrict__ data, size_t row_stride, size_t batch
 }
 
 // ---------------------------------------------------------------------------
+// Prime-field RS extension (lib/algebra/reed_solomon.h:27-41,93-110):
+//   p(k) = lead[k-d] * sum_{i<n} x_i / (k - i),  x_i = (-1)^i C(d,i) p(i),  d = n-1
+// The reference evaluates the sum as an FFT convolution with the table 1/i
+// (lib/algebra/convolution.h:80-91,156-175); arithmetic is exact, so the direct
+// Toeplitz sum gives the same values.  One CTA per row keeps x[] in shared
+// memory; a warp reads 32 consecutive entries of the 1/i table per step.
+// ---------------------------------------------------------------------------
+template <class F>
+__global__ void __launch_bounds__(256)
+k_rs_fp_rows(typename F::Elt* __restrict__ data, size_t row_stride, size_t batch_stride, uint32_t n, uint32_t m,
+             const typename F::Elt* __restrict__ inv, const typename F::Elt* __restrict__ lead,
+             const typename F::Elt* __restrict__ binom) {
+  typedef typename F::Elt Elt;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  Elt* x = reinterpret_cast<Elt*>(smem_raw);
+  Elt* y = data + (size_t)blockIdx.y * batch_stride + (size_t)blockIdx.x * row_stride;
+  for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) x[i] = F::mul(binom[i], y[i]);
+  __syncthreads();
+  for (uint32_t k = n + threadIdx.x; k < m; k += blockDim.x) {
+    typename F::Acc acc;
+    F::acc_zero(acc);
+    const Elt* iv = inv + k;
+    for (uint32_t i = 0; i < n; ++i) F::mac(acc, x[i], iv[-(int)i]);
+    y[k] = F::mul(lead[k - (n - 1)], F::reduce(acc));
+  }
+}
+
+// wire <-> Montgomery conversion of flat element arrays (boundary of the C ABI)
+template <class F>
+__global__ void k_from_wire(const uint8_t* __restrict__ in, typename F::Elt* __restrict__ out, size_t n,
+                            int* __restrict__ bad) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  bool ok = true;
+  out[i] = F::from_bytes(in + i * F::kBytes, &ok);
+  if (!ok) *bad = 1;
+}
+template <class F>
+__global__ void k_to_wire(const typename F::Elt* __restrict__ in, uint32_t* __restrict__ out, size_t n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint32_t w[F::kWords];
+  F::to_wire(w, in[i]);
+#pragma unroll
+  for (int k = 0; k < F::kWords; ++k) out[i * F::kWords + k] = w[k];
+}
+
+// ---------------------------------------------------------------------------
 // Merkle leaves: one thread per (instance, column).  leaf_j =
 // SHA256(nonce_j || bytes(T[0][dblock+j]) || ... || bytes(T[nrow-1][dblock+j])).
 // A warp reads 32 consecutive elements of a row: 128-bit coalesced loads.

@@ -18,30 +18,19 @@
 
 namespace lf {
 
-// ----------------------------------------------------------------------------
-// field-specific sampling from a byte stream
-// ----------------------------------------------------------------------------
-// GF(2^128): 16 bytes are an element (gf2_128.h:182-190)
-__device__ __forceinline__ gf128 gf_from_bytes(const uint8_t* p) {
-  gf128 e;
-  if ((reinterpret_cast<uintptr_t>(p) & 3) == 0) {
-    const uint32_t* q = reinterpret_cast<const uint32_t*>(p);
-    e.w[0] = q[0]; e.w[1] = q[1]; e.w[2] = q[2]; e.w[3] = q[3];
-  } else {
-#pragma unroll
-    for (int k = 0; k < 4; ++k)
-      e.w[k] = (uint32_t)p[4 * k] | ((uint32_t)p[4 * k + 1] << 8) | ((uint32_t)p[4 * k + 2] << 16) |
-               ((uint32_t)p[4 * k + 3] << 24);
-  }
-  return e;
+// transcript writes of an element: tag + wire bytes (transcript.h:136-153)
+template <class F>
+__device__ __forceinline__ void ts_write_elt(Transcript* ts, const typename F::Elt& e) {
+  uint32_t w[F::kWords];
+  F::to_wire(w, e);
+  ts->write_elt_words(w, F::kWords);
 }
-__device__ __forceinline__ gf128 ts_elt(Transcript* ts, FGf128*) {
-  gf128 e;
-  ts->words(e.w, 4);
-  return e;
+template <class F>
+__device__ __forceinline__ void ts_array_elt(Transcript* ts, const typename F::Elt& e) {
+  uint32_t w[F::kWords];
+  F::to_wire(w, e);
+  ts->elt_words(w, F::kWords);
 }
-__device__ __forceinline__ void ts_write_elt(Transcript* ts, const gf128& e) { ts->write_elt_words(e.w, 4); }
-__device__ __forceinline__ void ts_array_elt(Transcript* ts, const gf128& e) { ts->elt_words(e.w, 4); }
 
 // ----------------------------------------------------------------------------
 // k_zk_witness: Ligero witness = private inputs || pad (zk_prover.h:78-96,152-188)
@@ -56,9 +45,11 @@ __global__ void k_zk_witness(ZkDims d, ZkBufs<typename F::Elt> b, const LayerDes
   if (i >= d.nw) return;
   Elt* wit = b.wit + p * d.nw;
   const uint8_t* rng = b.rng + p * b.rng_stride;
+  bool ok = true, rok = true;
   if (i < d.n_witness) {
     const uint8_t* w = b.witness_in + p * b.witness_stride + (size_t)(i + d.npub) * F::kBytes;
-    wit[i] = gf_from_bytes(w);
+    wit[i] = F::from_bytes(w, &ok);
+    if (!ok) b.status[p] = -3;  // non-canonical input element
     return;
   }
   uint32_t q = i - d.n_witness;  // index inside the pad block
@@ -71,12 +62,13 @@ __global__ void k_zk_witness(ZkDims d, ZkBufs<typename F::Elt> b, const LayerDes
   while (ly + 1 < d.nl && layers[ly + 1].pad_off <= q) ++ly;
   uint32_t j = q - layers[ly].pad_off, cnt = 4 * layers[ly].logw + 2;
   if (j < cnt) {
-    wit[i] = gf_from_bytes(rng + (size_t)(layers[ly].sc_off + j) * F::kBytes);
+    wit[i] = F::sample_bytes(rng + (size_t)(layers[ly].sc_off + j) * F::kBytes, &rok);
   } else {
-    Elt a = gf_from_bytes(rng + (size_t)(layers[ly].sc_off + cnt - 2) * F::kBytes);
-    Elt c = gf_from_bytes(rng + (size_t)(layers[ly].sc_off + cnt - 1) * F::kBytes);
+    Elt a = F::sample_bytes(rng + (size_t)(layers[ly].sc_off + cnt - 2) * F::kBytes, &rok);
+    Elt c = F::sample_bytes(rng + (size_t)(layers[ly].sc_off + cnt - 1) * F::kBytes, &rok);
     wit[i] = F::mul(a, c);
   }
+  if (!rok) b.status[p] = -6;  // a sample needs a re-draw (prime fields, probability 2^-32 each)
 }
 
 // ----------------------------------------------------------------------------
@@ -95,12 +87,13 @@ k_zk_layout(ZkDims d, ZkBufs<typename F::Elt> b, const uint32_t* __restrict__ ro
   const Elt* wit = b.wit + p * d.nw;
   const uint8_t* rng = b.rng + p * b.rng_stride + row_rng[row];
   __shared__ Elt red[8];
+  bool rok = true;
   if (row == 0) {  // ILDT: block random elements
-    for (uint32_t j = threadIdx.x; j < d.block; j += blockDim.x) T[j] = gf_from_bytes(rng + (size_t)j * F::kBytes);
+    for (uint32_t j = threadIdx.x; j < d.block; j += blockDim.x) T[j] = F::sample_bytes(rng + (size_t)j * F::kBytes, &rok);
   } else if (row == 1) {  // IDOT: dblock random, then T[r] -= sum of the W part
     Elt s = F::zero();
     for (uint32_t j = threadIdx.x; j < d.dblock; j += blockDim.x) {
-      Elt e = gf_from_bytes(rng + (size_t)j * F::kBytes);
+      Elt e = F::sample_bytes(rng + (size_t)j * F::kBytes, &rok);
       T[j] = e;
       if (j >= d.r && j < d.r + d.w) s = F::add(s, e);
     }
@@ -117,11 +110,11 @@ k_zk_layout(ZkDims d, ZkBufs<typename F::Elt> b, const uint32_t* __restrict__ ro
     if (threadIdx.x == 0) {
       Elt tot = red[0];
       for (uint32_t k = 1; k < blockDim.x / 32; ++k) tot = F::add(tot, red[k]);
-      T[d.r] = F::sub(gf_from_bytes(rng + (size_t)d.r * F::kBytes), tot);
+      T[d.r] = F::sub(F::sample_bytes(rng + (size_t)d.r * F::kBytes, &rok), tot);
     }
   } else if (row == 2) {  // IQUAD: dblock random with the W part cleared
     for (uint32_t j = threadIdx.x; j < d.dblock; j += blockDim.x) {
-      Elt e = gf_from_bytes(rng + (size_t)j * F::kBytes);
+      Elt e = F::sample_bytes(rng + (size_t)j * F::kBytes, &rok);
       T[j] = (j >= d.r && j < d.r + d.w) ? F::zero() : e;
     }
   } else if (row < d.iq) {  // witness rows
@@ -134,7 +127,7 @@ k_zk_layout(ZkDims d, ZkBufs<typename F::Elt> b, const uint32_t* __restrict__ ro
           const uint8_t* q = rng + 2 * (size_t)j;
           e = F::of_sub16((uint32_t)q[0] | ((uint32_t)q[1] << 8));
         } else {
-          e = gf_from_bytes(rng + (size_t)j * F::kBytes);
+          e = F::sample_bytes(rng + (size_t)j * F::kBytes, &rok);
         }
       } else {
         uint32_t k = i * d.w + (j - d.r);
@@ -148,7 +141,7 @@ k_zk_layout(ZkDims d, ZkBufs<typename F::Elt> b, const uint32_t* __restrict__ ro
     for (uint32_t j = threadIdx.x; j < d.block; j += blockDim.x) {
       Elt e;
       if (j < d.r) {
-        e = gf_from_bytes(rng + (size_t)j * F::kBytes);
+        e = F::sample_bytes(rng + (size_t)j * F::kBytes, &rok);
       } else {
         uint32_t k = i * d.w + (j - d.r);
         e = (k < d.nq) ? wit[lqc[3 * k + which]] : F::zero();
@@ -156,6 +149,7 @@ k_zk_layout(ZkDims d, ZkBufs<typename F::Elt> b, const uint32_t* __restrict__ ro
       T[j] = e;
     }
   }
+  if (!rok) b.status[p] = -6;
 }
 
 // ----------------------------------------------------------------------------
@@ -177,10 +171,19 @@ __global__ void k_zk_transcript_init(ZkDims d, ZkBufs<typename F::Elt> b, const 
   ts.write_bytes_words(rw, 8);
   ts.write_bytes(circuit_id, 32);
   for (uint32_t i = 0; i < d.npub; ++i) {
-    typename F::Elt e = gf_from_bytes(b.witness_in + p * b.witness_stride + (size_t)i * F::kBytes);
-    ts_write_elt(&ts, e);
+    // the wire bytes of the public inputs go into the transcript unchanged
+    const uint8_t* q = b.witness_in + p * b.witness_stride + (size_t)i * F::kBytes;
+    uint32_t w[F::kWords];
+    for (int k = 0; k < F::kWords; ++k)
+      w[k] = (uint32_t)q[4 * k] | ((uint32_t)q[4 * k + 1] << 8) | ((uint32_t)q[4 * k + 2] << 16) |
+             ((uint32_t)q[4 * k + 3] << 24);
+    ts.write_elt_words(w, F::kWords);
   }
-  ts_write_elt(&ts, F::zero());
+  {
+    uint32_t w[F::kWords];
+    for (int k = 0; k < F::kWords; ++k) w[k] = 0;
+    ts.write_elt_words(w, F::kWords);  // F.zero()
+  }
   ts.write0(d.nterms);
   *reinterpret_cast<Transcript*>(b.ts + p * sizeof(Transcript)) = ts;
 }
@@ -335,9 +338,9 @@ __device__ __noinline__ void sc_round_serial(ScShared<F>* sh, typename F::Elt a0
   Elt p0 = F::sub(ev[0], pad[0]), p2 = F::sub(ev[2], pad[1]);
   *proof0 = p0;
   *proof2 = p2;
-  ts_write_elt(&sh->ts, p0);
-  ts_write_elt(&sh->ts, p2);
-  Elt rnd = ts_elt(&sh->ts, (F*)nullptr);
+  ts_write_elt<F>(&sh->ts, p0);
+  ts_write_elt<F>(&sh->ts, p2);
+  Elt rnd = F::ts_elt(&sh->ts);
   *hb_out = rnd;
   // sum = evals.eval_lagrange(rnd)
   Elt t[3] = {ev[0], ev[1], ev[2]};
@@ -357,9 +360,9 @@ __device__ __noinline__ void sc_begin(ScShared<F>* sh, const Transcript* src) {
   sh->ts = *src;
   sh->ts.have_prf = 0;  // Transcript::clone() carries only the hash (transcript.h:86)
   // begin_circuit: Q[40] then G[40] (transcript_sumcheck.h:49-52)
-  for (int i = 0; i < 40; ++i) (void)ts_elt(&sh->ts, (F*)nullptr);
+  for (int i = 0; i < 40; ++i) (void)F::ts_elt(&sh->ts);
   for (int i = 0; i < 40; ++i) {
-    typename F::Elt g = ts_elt(&sh->ts, (F*)nullptr);
+    typename F::Elt g = F::ts_elt(&sh->ts);
     sh->G[0][i] = g;
     sh->G[1][i] = g;
   }
@@ -370,8 +373,8 @@ __device__ __noinline__ void sc_begin(ScShared<F>* sh, const Transcript* src) {
 
 template <class F>
 __device__ __noinline__ void sc_begin_layer(ScShared<F>* sh, typename F::Elt* alpha_out) {
-  sh->alpha = ts_elt(&sh->ts, (F*)nullptr);
-  sh->beta = ts_elt(&sh->ts, (F*)nullptr);
+  sh->alpha = F::ts_elt(&sh->ts);
+  sh->beta = F::ts_elt(&sh->ts);
   *alpha_out = sh->alpha;
   sh->sum = F::add(sh->wc[0], F::mul(sh->alpha, sh->wc[1]));
 }
@@ -390,8 +393,8 @@ __device__ __noinline__ void sc_end_layer(ScShared<F>* sh, typename F::Elt hquad
   proofwc[0] = t0;
   proofwc[1] = t1;
   sh->ts.begin_array(2);
-  ts_array_elt(&sh->ts, t0);
-  ts_array_elt(&sh->ts, t1);
+  ts_array_elt<F>(&sh->ts, t0);
+  ts_array_elt<F>(&sh->ts, t1);
 }
 
 // The kernel body is shared by two launch configurations (throughput: many
@@ -613,10 +616,10 @@ __global__ void k_lig_challenges(ZkDims d, ZkBufs<typename F::Elt> b, size_t npr
   Transcript* gts = reinterpret_cast<Transcript*>(b.ts + p * sizeof(Transcript));
   Transcript ts = *gts;
   typename F::Elt* chal = b.chal + p * (size_t)(1 + d.nchal);
-  chal[0] = ts_elt(&ts, (F*)nullptr);
+  chal[0] = F::ts_elt(&ts);
   uint32_t hashA[8] = {0xefbeaddeu, 0, 0, 0, 0, 0, 0, 0};  // bytes de ad be ef 00 ...
   ts.write_bytes_words(hashA, 8);
-  for (uint32_t i = 0; i < d.nchal; ++i) chal[1 + i] = ts_elt(&ts, (F*)nullptr);
+  for (uint32_t i = 0; i < d.nchal; ++i) chal[1 + i] = F::ts_elt(&ts);
   *gts = ts;
 }
 
@@ -918,7 +921,7 @@ k_lig_finish(ZkDims d, ZkBufs<typename F::Elt> b, const LayerDesc* __restrict__ 
     const uint32_t offs[4] = {0, d.block, d.block + d.dblock, d.block + d.dblock + d.block};
     for (int a = 0; a < 4; ++a) {
       ts.begin_array(lens[a]);
-      for (uint32_t i = 0; i < lens[a]; ++i) ts_array_elt(&ts, y[offs[a] + i]);
+      for (uint32_t i = 0; i < lens[a]; ++i) ts_array_elt<F>(&ts, y[offs[a] + i]);
     }
     // RandomEngine::choose (random.h:92-105)
     for (uint32_t i = 0; i < d.nreq; ++i) {
@@ -944,8 +947,10 @@ k_lig_finish(ZkDims d, ZkBufs<typename F::Elt> b, const LayerDesc* __restrict__ 
   // opened columns: subfield flags (zk_proof.h:162-166)
   for (uint32_t k = tid; k < total; k += nth) {
     Elt e = T[(size_t)(k / d.nreq) * d.block_enc + d.dblock + idx[k % d.nreq]];
-    uint32_t u;
-    flag[k] = F::kChar2 ? (uint8_t)F::solve_sub16(e, &u) : (uint8_t)1;
+    uint32_t u = 0;
+    bool in_sub = true;  // prime fields: in_subfield() is always true (fp_generic.h:278)
+    if (F::kChar2) in_sub = F::solve_sub16(e, &u);
+    flag[k] = (uint8_t)in_sub;
   }
   __syncthreads();
   const uint32_t off_sc = 32;

@@ -160,6 +160,59 @@ struct RsPlanHost {
   RsStep* d_steps = nullptr;
 };
 
+// host copy of the P-256 constant block and helpers on Montgomery limbs
+struct P256Host {
+  FpConsts<8> C;
+  P256Host() {
+    // lib/algebra/fp_p256.h:34-39
+    const uint32_t m[8] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0, 0, 0, 1, 0xFFFFFFFFu};
+    fp_build_consts<8>(m, &C);
+  }
+  fpw<8> mul(const fpw<8>& a, const fpw<8>& b) const { return fp_mul_generic<8>(a, b, C.m, C.mprime); }
+  fpw<8> add(const fpw<8>& a, const fpw<8>& b) const { return fp_add<8>(a, b, C.m); }
+  fpw<8> sub(const fpw<8>& a, const fpw<8>& b) const { return fp_sub<8>(a, b, C.m); }
+  fpw<8> one() const {
+    fpw<8> r;
+    for (int i = 0; i < 8; ++i) r.w[i] = C.one[i];
+    return r;
+  }
+  fpw<8> zero() const {
+    fpw<8> r;
+    for (int i = 0; i < 8; ++i) r.w[i] = 0;
+    return r;
+  }
+  fpw<8> inv(const fpw<8>& a) const {
+    uint32_t e[8], two[8] = {2, 0, 0, 0, 0, 0, 0, 0};
+    fp_subn<8>(e, C.m, two);
+    return fp_pow_host<8>(a, e, C);
+  }
+  bool from_wire(const uint8_t* p, fpw<8>* out) const {
+    fpw<8> a, q;
+    memcpy(a.w, p, 32);
+    if (fp_geq<8>(a.w, C.m)) return false;
+    for (int i = 0; i < 8; ++i) q.w[i] = C.rsq[i];
+    *out = mul(a, q);
+    return true;
+  }
+  void to_wire(uint8_t* p, const fpw<8>& a) const {
+    fpw<8> o = zero();
+    o.w[0] = 1;
+    fpw<8> r = mul(a, o);
+    memcpy(p, r.w, 32);
+  }
+};
+static const P256Host& p256_host() {
+  static const P256Host h;
+  return h;
+}
+
+// tables of ReedSolomon(n, m) (lib/algebra/reed_solomon.h:51-88) in Montgomery form
+struct RsFpTables {
+  fpw<8>* d_inv = nullptr;    // [m] 1/i, inv[0] = 0
+  fpw<8>* d_lead = nullptr;   // [m-n+1]
+  fpw<8>* d_binom = nullptr;  // [n]
+};
+
 }  // namespace lf
 
 using namespace lf;
@@ -171,6 +224,7 @@ struct lf_ctx {
   bool own_stream = false;
   gf128* d_tw = nullptr;
   std::map<std::pair<size_t, size_t>, RsPlanHost> rs_plans;
+  std::map<std::pair<size_t, size_t>, RsFpTables> rs_fp;
   uint64_t launches = 0;
   int sm_count = 0;
 };
@@ -231,13 +285,98 @@ static int launch_rs_gf(lf_ctx* ctx, gf128* d_rows, size_t row_stride, size_t nr
   return 0;
 }
 
-static int launch_merkle_gf(lf_ctx* ctx, const gf128* d_tab, size_t tab_batch_stride, uint32_t nrow,
-                            uint32_t block_enc, uint32_t dblock, const uint8_t* d_nonces,
-                            size_t nonce_batch_stride, uint32_t* d_nodes, size_t nodes_batch_stride,
-                            size_t nbatch) {
+static int ctx_rs_fp_tables(lf_ctx* ctx, size_t n, size_t m, RsFpTables** out) {
+  auto key = std::make_pair(n, m);
+  auto it = ctx->rs_fp.find(key);
+  if (it == ctx->rs_fp.end()) {
+    const P256Host& H = p256_host();
+    const size_t d = n - 1;
+    std::vector<fpw<8>> inv(m), sc(m), lead(m - n + 1), binom(n);
+    // utility.h:51-72 batch_inverse_arithmetic: inv[i] = 1/i
+    sc[0] = H.zero();
+    for (size_t i = 1; i < m; ++i) sc[i] = H.add(sc[i - 1], H.one());
+    {
+      std::vector<fpw<8>> pre(m);
+      fpw<8> p = H.one();
+      inv[0] = H.zero();
+      for (size_t i = 1; i < m; ++i) {
+        pre[i] = p;
+        p = H.mul(p, sc[i]);
+      }
+      p = H.inv(p);
+      for (size_t i = m; i-- > 1;) {
+        inv[i] = H.mul(pre[i], p);
+        p = H.mul(p, sc[i]);
+      }
+    }
+    // reed_solomon.h:62-79 leading constants (-1)^d (k-d) C(k,d)
+    lead[0] = H.one();
+    for (size_t i = 1; i + d < m; ++i) lead[i] = H.mul(lead[i - 1], H.mul(sc[d + i], inv[i]));
+    for (size_t k = d; k < m; ++k) {
+      lead[k - d] = H.mul(lead[k - d], sc[k - d]);
+      if (d % 2 == 1) lead[k - d] = H.sub(H.zero(), lead[k - d]);
+    }
+    // reed_solomon.h:81-87 (-1)^i C(d, i)
+    binom[0] = H.one();
+    for (size_t i = 1; i < n; ++i) binom[i] = H.mul(binom[i - 1], H.mul(sc[n - i], inv[i]));
+    for (size_t i = 1; i < n; i += 2) binom[i] = H.sub(H.zero(), binom[i]);
+    RsFpTables t;
+    LF_CUDA(cudaMalloc(&t.d_inv, m * 32));
+    LF_CUDA(cudaMalloc(&t.d_lead, lead.size() * 32));
+    LF_CUDA(cudaMalloc(&t.d_binom, n * 32));
+    LF_CUDA(cudaMemcpy(t.d_inv, inv.data(), m * 32, cudaMemcpyHostToDevice));
+    LF_CUDA(cudaMemcpy(t.d_lead, lead.data(), lead.size() * 32, cudaMemcpyHostToDevice));
+    LF_CUDA(cudaMemcpy(t.d_binom, binom.data(), n * 32, cudaMemcpyHostToDevice));
+    it = ctx->rs_fp.emplace(key, t).first;
+  }
+  *out = &it->second;
+  return 0;
+}
+
+static int launch_rs_p256(lf_ctx* ctx, fpw<8>* d_rows, size_t row_stride, size_t nrows, size_t batch_stride,
+                          size_t nbatch, size_t n, size_t m) {
+  if (n == 0 || m < n || m > (1u << 24)) return fail(LF_ERR_ARG, "rs: need 0 < n <= m <= 2^24");
+  if (nrows == 0 || nbatch == 0 || m == n) return 0;
+  if (n * 32 > 200 * 1024) return fail(LF_ERR_UNSUPPORTED, "rs: n > 6400 over Fp256 needs the FFT path (not built yet)");
+  RsFpTables* t;
+  int rc = ctx_rs_fp_tables(ctx, n, m, &t);
+  if (rc) return rc;
+  static bool attr_set = false;
+  if (!attr_set) {
+    LF_CUDA(cudaFuncSetAttribute(k_rs_fp_rows<FFp256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr_set = true;
+  }
+  dim3 grid((unsigned)nrows, (unsigned)nbatch);
+  k_rs_fp_rows<FFp256><<<grid, 256, n * 32, ctx->stream>>>(d_rows, row_stride, batch_stride, (uint32_t)n,
+                                                          (uint32_t)m, t->d_inv, t->d_lead, t->d_binom);
+  ctx->launches++;
+  LF_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// field-generic front ends used by the ZK pipeline
+template <class F>
+static int launch_rs(lf_ctx* ctx, typename F::Elt* d_rows, size_t row_stride, size_t nrows, size_t batch_stride,
+                     size_t nbatch, size_t n, size_t m);
+template <>
+int launch_rs<FGf128>(lf_ctx* ctx, gf128* d_rows, size_t row_stride, size_t nrows, size_t batch_stride,
+                      size_t nbatch, size_t n, size_t m) {
+  return launch_rs_gf(ctx, d_rows, row_stride, nrows, batch_stride, nbatch, n, m);
+}
+template <>
+int launch_rs<FFp256>(lf_ctx* ctx, fpw<8>* d_rows, size_t row_stride, size_t nrows, size_t batch_stride,
+                      size_t nbatch, size_t n, size_t m) {
+  return launch_rs_p256(ctx, d_rows, row_stride, nrows, batch_stride, nbatch, n, m);
+}
+
+template <class F>
+static int launch_merkle(lf_ctx* ctx, const typename F::Elt* d_tab, size_t tab_batch_stride, uint32_t nrow,
+                         uint32_t block_enc, uint32_t dblock, const uint8_t* d_nonces,
+                         size_t nonce_batch_stride, uint32_t* d_nodes, size_t nodes_batch_stride,
+                         size_t nbatch) {
   uint32_t block_ext = block_enc - dblock;
   dim3 grid((block_ext + 127) / 128, (unsigned)nbatch);
-  k_merkle_leaves<FGf128><<<grid, 128, 0, ctx->stream>>>(d_tab, tab_batch_stride, nrow, block_enc, dblock,
+  k_merkle_leaves<F><<<grid, 128, 0, ctx->stream>>>(d_tab, tab_batch_stride, nrow, block_enc, dblock,
                                                          block_ext, d_nonces, nonce_batch_stride, d_nodes,
                                                          nodes_batch_stride);
   ctx->launches++;
@@ -335,6 +474,7 @@ int lf_ctx_create(int device, void* stream, lf_ctx** out) {
   LF_CUDA(cudaMalloc(&c->d_tw, h.tw.size() * sizeof(gf128)));
   LF_CUDA(cudaMemcpy(c->d_tw, h.tw.data(), h.tw.size() * sizeof(gf128), cudaMemcpyHostToDevice));
   LF_CUDA(cudaMemcpyToSymbol(c_gf, &h.consts, sizeof(GfConsts)));
+  LF_CUDA(cudaMemcpyToSymbol(c_p256, &p256_host().C, sizeof(FpConsts<8>)));
   *out = c.release();
   return 0;
 }
@@ -344,6 +484,11 @@ void lf_ctx_destroy(lf_ctx* ctx) {
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   for (auto& kv : ctx->rs_plans) cudaFree(kv.second.d_steps);
+  for (auto& kv : ctx->rs_fp) {
+    cudaFree(kv.second.d_inv);
+    cudaFree(kv.second.d_lead);
+    cudaFree(kv.second.d_binom);
+  }
   cudaFree(ctx->d_tw);
   if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
@@ -357,73 +502,100 @@ int lf_ctx_synchronize(lf_ctx* ctx) {
 
 uint64_t lf_ctx_launch_count(const lf_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
-int lf_elt_mul(lf_ctx* ctx, int field_id, const void* a, const void* b, void* out, size_t n) {
-  if (!ctx || !a || !b || !out) return fail(LF_ERR_ARG, "lf_elt_mul: null argument");
-  if (field_id != LF_FIELD_GF2_128) return fail(LF_ERR_UNSUPPORTED, "lf_elt_mul: field not built yet");
-  if (n == 0) return 0;
-  LF_CUDA(cudaSetDevice(ctx->device));
-  gf128 *da, *db, *dc;
-  LF_CUDA(cudaMalloc(&da, n * 16));
-  LF_CUDA(cudaMalloc(&db, n * 16));
-  LF_CUDA(cudaMalloc(&dc, n * 16));
-  LF_CUDA(cudaMemcpyAsync(da, a, n * 16, cudaMemcpyHostToDevice, ctx->stream));
-  LF_CUDA(cudaMemcpyAsync(db, b, n * 16, cudaMemcpyHostToDevice, ctx->stream));
-  k_elt_mul<FGf128><<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(da, db, dc, n);
-  ctx->launches++;
-  LF_CUDA(cudaGetLastError());
-  LF_CUDA(cudaMemcpyAsync(out, dc, n * 16, cudaMemcpyDeviceToHost, ctx->stream));
+}  // extern "C"
+
+namespace {
+// host wire buffer -> device elements (Montgomery for prime fields)
+template <class F>
+int upload_elts(lf_ctx* ctx, const void* host, size_t n, typename F::Elt** d_out) {
+  typename F::Elt* d;
+  LF_CUDA(cudaMalloc(&d, std::max<size_t>(n, 1) * sizeof(typename F::Elt)));
+  if (F::kChar2) {
+    LF_CUDA(cudaMemcpyAsync(d, host, n * F::kBytes, cudaMemcpyHostToDevice, ctx->stream));
+  } else {
+    uint8_t* raw;
+    int* bad;
+    LF_CUDA(cudaMalloc(&raw, std::max<size_t>(n, 1) * F::kBytes));
+    LF_CUDA(cudaMalloc(&bad, sizeof(int)));
+    LF_CUDA(cudaMemsetAsync(bad, 0, sizeof(int), ctx->stream));
+    LF_CUDA(cudaMemcpyAsync(raw, host, n * F::kBytes, cudaMemcpyHostToDevice, ctx->stream));
+    k_from_wire<F><<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(raw, d, n, bad);
+    ctx->launches++;
+    int hbad = 0;
+    LF_CUDA(cudaMemcpyAsync(&hbad, bad, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    LF_CUDA(cudaStreamSynchronize(ctx->stream));
+    cudaFree(raw);
+    cudaFree(bad);
+    if (hbad) {
+      cudaFree(d);
+      return fail(LF_ERR_FORMAT, "element is not canonical (>= modulus)");
+    }
+  }
+  *d_out = d;
+  return 0;
+}
+template <class F>
+int download_elts(lf_ctx* ctx, const typename F::Elt* d, size_t n, void* host) {
+  if (F::kChar2) {
+    LF_CUDA(cudaMemcpyAsync(host, d, n * F::kBytes, cudaMemcpyDeviceToHost, ctx->stream));
+  } else {
+    uint32_t* raw;
+    LF_CUDA(cudaMalloc(&raw, std::max<size_t>(n, 1) * F::kBytes));
+    k_to_wire<F><<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(d, raw, n);
+    ctx->launches++;
+    LF_CUDA(cudaMemcpyAsync(host, raw, n * F::kBytes, cudaMemcpyDeviceToHost, ctx->stream));
+    LF_CUDA(cudaStreamSynchronize(ctx->stream));
+    cudaFree(raw);
+  }
   LF_CUDA(cudaStreamSynchronize(ctx->stream));
-  cudaFree(da);
-  cudaFree(db);
-  cudaFree(dc);
   return 0;
 }
 
-int lf_rs_interpolate_dev(lf_ctx* ctx, int field_id, size_t n, size_t m, void* d_rows, size_t row_stride,
-                          size_t nrows) {
-  if (!ctx || !d_rows) return fail(LF_ERR_ARG, "lf_rs_interpolate_dev: null argument");
-  if (field_id != LF_FIELD_GF2_128) return fail(LF_ERR_UNSUPPORTED, "rs: field not built yet");
-  if (row_stride < m) return fail(LF_ERR_ARG, "rs: row_stride < m");
-  LF_CUDA(cudaSetDevice(ctx->device));
-  return launch_rs_gf(ctx, (gf128*)d_rows, row_stride, nrows, 0, 1, n, m);
+template <class F>
+int elt_mul_t(lf_ctx* ctx, const void* a, const void* b, void* out, size_t n) {
+  typename F::Elt *da = nullptr, *db = nullptr, *dc = nullptr;
+  int rc = upload_elts<F>(ctx, a, n, &da);
+  if (!rc) rc = upload_elts<F>(ctx, b, n, &db);
+  if (!rc) {
+    cudaError_t e = cudaMalloc(&dc, n * sizeof(typename F::Elt));
+    if (e != cudaSuccess) rc = fail(LF_ERR_CUDA, cudaGetErrorString(e));
+  }
+  if (!rc) {
+    k_elt_mul<F><<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(da, db, dc, n);
+    ctx->launches++;
+    rc = download_elts<F>(ctx, dc, n, out);
+  }
+  cudaFree(da);
+  cudaFree(db);
+  cudaFree(dc);
+  return rc;
 }
 
-int lf_rs_interpolate(lf_ctx* ctx, int field_id, size_t n, size_t m, void* rows, size_t nrows) {
-  if (!ctx || !rows) return fail(LF_ERR_ARG, "lf_rs_interpolate: null argument");
-  if (field_id != LF_FIELD_GF2_128) return fail(LF_ERR_UNSUPPORTED, "rs: field not built yet");
-  if (nrows == 0) return 0;
-  LF_CUDA(cudaSetDevice(ctx->device));
-  size_t bytes = nrows * m * 16;
-  gf128* d;
-  LF_CUDA(cudaMalloc(&d, bytes));
-  LF_CUDA(cudaMemcpyAsync(d, rows, bytes, cudaMemcpyHostToDevice, ctx->stream));
-  int rc = launch_rs_gf(ctx, d, m, nrows, 0, 1, n, m);
-  if (rc == 0) {
-    LF_CUDA(cudaMemcpyAsync(rows, d, bytes, cudaMemcpyDeviceToHost, ctx->stream));
-    LF_CUDA(cudaStreamSynchronize(ctx->stream));
-  }
+template <class F>
+int rs_interpolate_t(lf_ctx* ctx, size_t n, size_t m, void* rows, size_t nrows) {
+  typename F::Elt* d = nullptr;
+  int rc = upload_elts<F>(ctx, rows, nrows * m, &d);
+  if (!rc) rc = launch_rs<F>(ctx, d, m, nrows, 0, 1, n, m);
+  if (!rc) rc = download_elts<F>(ctx, d, nrows * m, rows);
   cudaFree(d);
   return rc;
 }
 
-int lf_merkle_commit(lf_ctx* ctx, int field_id, size_t nrow, size_t block_enc, size_t dblock,
-                     const void* tableau, const uint8_t* nonces, uint8_t root_out[32], uint8_t* nodes_out) {
-  if (!ctx || !tableau || !nonces || !root_out) return fail(LF_ERR_ARG, "lf_merkle_commit: null argument");
-  if (field_id != LF_FIELD_GF2_128) return fail(LF_ERR_UNSUPPORTED, "merkle: field not built yet");
-  if (block_enc <= dblock || nrow == 0) return fail(LF_ERR_ARG, "merkle: need block_enc > dblock, nrow > 0");
-  LF_CUDA(cudaSetDevice(ctx->device));
+template <class F>
+int merkle_commit_t(lf_ctx* ctx, size_t nrow, size_t block_enc, size_t dblock, const void* tableau,
+                    const uint8_t* nonces, uint8_t root_out[32], uint8_t* nodes_out) {
   size_t block_ext = block_enc - dblock;
-  gf128* d_tab;
-  uint8_t* d_nonce;
-  uint32_t* d_nodes;
-  LF_CUDA(cudaMalloc(&d_tab, nrow * block_enc * 16));
+  typename F::Elt* d_tab = nullptr;
+  uint8_t* d_nonce = nullptr;
+  uint32_t* d_nodes = nullptr;
+  int rc = upload_elts<F>(ctx, tableau, nrow * block_enc, &d_tab);
+  if (rc) return rc;
   LF_CUDA(cudaMalloc(&d_nonce, block_ext * 32));
   LF_CUDA(cudaMalloc(&d_nodes, 2 * block_ext * 32));
   LF_CUDA(cudaMemsetAsync(d_nodes, 0, 2 * block_ext * 32, ctx->stream));
-  LF_CUDA(cudaMemcpyAsync(d_tab, tableau, nrow * block_enc * 16, cudaMemcpyHostToDevice, ctx->stream));
   LF_CUDA(cudaMemcpyAsync(d_nonce, nonces, block_ext * 32, cudaMemcpyHostToDevice, ctx->stream));
-  int rc = launch_merkle_gf(ctx, d_tab, 0, (uint32_t)nrow, (uint32_t)block_enc, (uint32_t)dblock, d_nonce,
-                            0, d_nodes, 0, 1);
+  rc = launch_merkle<F>(ctx, d_tab, 0, (uint32_t)nrow, (uint32_t)block_enc, (uint32_t)dblock, d_nonce, 0, d_nodes,
+                        0, 1);
   if (rc == 0) {
     std::vector<uint32_t> nodes(2 * block_ext * 8);
     LF_CUDA(cudaMemcpyAsync(nodes.data(), d_nodes, nodes.size() * 4, cudaMemcpyDeviceToHost, ctx->stream));
@@ -438,7 +610,7 @@ int lf_merkle_commit(lf_ctx* ctx, int field_id, size_t nrow, size_t block_enc, s
         dst[4 * k + 3] = (uint8_t)x;
       }
     };
-    put(root_out, block_ext == 1 ? 1 : 1);
+    put(root_out, 1);
     if (nodes_out)
       for (size_t i = 0; i < 2 * block_ext; ++i) put(nodes_out + 32 * i, i);
   }
@@ -446,6 +618,48 @@ int lf_merkle_commit(lf_ctx* ctx, int field_id, size_t nrow, size_t block_enc, s
   cudaFree(d_nonce);
   cudaFree(d_nodes);
   return rc;
+}
+}  // namespace
+
+extern "C" {
+
+#define LF_DISPATCH_FIELD(field_id, CALL)                                      \
+  switch (field_id) {                                                          \
+    case LF_FIELD_GF2_128: { typedef FGf128 F; return CALL; }                  \
+    case LF_FIELD_P256: { typedef FFp256 F; return CALL; }                     \
+    default: return fail(LF_ERR_UNSUPPORTED, "field not built yet");           \
+  }
+
+int lf_elt_mul(lf_ctx* ctx, int field_id, const void* a, const void* b, void* out, size_t n) {
+  if (!ctx || !a || !b || !out) return fail(LF_ERR_ARG, "lf_elt_mul: null argument");
+  if (n == 0) return 0;
+  LF_CUDA(cudaSetDevice(ctx->device));
+  LF_DISPATCH_FIELD(field_id, elt_mul_t<F>(ctx, a, b, out, n));
+}
+
+int lf_rs_interpolate_dev(lf_ctx* ctx, int field_id, size_t n, size_t m, void* d_rows, size_t row_stride,
+                          size_t nrows) {
+  if (!ctx || !d_rows) return fail(LF_ERR_ARG, "lf_rs_interpolate_dev: null argument");
+  if (row_stride < m) return fail(LF_ERR_ARG, "rs: row_stride < m");
+  LF_CUDA(cudaSetDevice(ctx->device));
+  // device rows are in the in-memory (Montgomery) representation
+  LF_DISPATCH_FIELD(field_id, launch_rs<F>(ctx, (typename F::Elt*)d_rows, row_stride, nrows, 0, 1, n, m));
+}
+
+int lf_rs_interpolate(lf_ctx* ctx, int field_id, size_t n, size_t m, void* rows, size_t nrows) {
+  if (!ctx || !rows) return fail(LF_ERR_ARG, "lf_rs_interpolate: null argument");
+  if (nrows == 0) return 0;
+  if (n == 0 || m < n) return fail(LF_ERR_ARG, "rs: need 0 < n <= m");
+  LF_CUDA(cudaSetDevice(ctx->device));
+  LF_DISPATCH_FIELD(field_id, rs_interpolate_t<F>(ctx, n, m, rows, nrows));
+}
+
+int lf_merkle_commit(lf_ctx* ctx, int field_id, size_t nrow, size_t block_enc, size_t dblock,
+                     const void* tableau, const uint8_t* nonces, uint8_t root_out[32], uint8_t* nodes_out) {
+  if (!ctx || !tableau || !nonces || !root_out) return fail(LF_ERR_ARG, "lf_merkle_commit: null argument");
+  if (block_enc <= dblock || nrow == 0) return fail(LF_ERR_ARG, "merkle: need block_enc > dblock, nrow > 0");
+  LF_CUDA(cudaSetDevice(ctx->device));
+  LF_DISPATCH_FIELD(field_id, merkle_commit_t<F>(ctx, nrow, block_enc, dblock, tableau, nonces, root_out, nodes_out));
 }
 
 int lf_microbench(lf_ctx* ctx, int what, double* gops) {

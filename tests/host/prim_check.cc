@@ -10,9 +10,12 @@
 #include <cstdio>
 #include <cstring>
 #include <vector>
+#include <type_traits>
 
 #include "../../longfellow_zk_b200/csrc/gf128.cuh"
 #include "../../longfellow_zk_b200/csrc/hash.cuh"
+#define LF_HDI inline
+#include "../../longfellow_zk_b200/csrc/fp.cuh"
 
 using namespace lf;
 
@@ -37,6 +40,40 @@ int main(int argc, char** argv) {
       gf128 c = gf_inv(a);
       fwrite(c.w, 1, 16, stdout);
     }
+  } else if (!strncmp(argv[1], "fp", 2)) {
+    // fpmul8 / fpmul8p256 / fpmul4 / fpmul2 : stdin = modulus (W words) || pairs of
+    // wire elements; stdout = wire products (through to/from Montgomery)
+    auto run = [&](auto tag, bool p256) {
+      constexpr int W = decltype(tag)::value;
+      FpConsts<W> C;
+      uint32_t mod[W];
+      memcpy(mod, in.data(), 4 * W);
+      fp_build_consts<W>(mod, &C);
+      fpw<W> rsq, one_int;
+      for (int i = 0; i < W; ++i) { rsq.w[i] = C.rsq[i]; one_int.w[i] = 0; }
+      one_int.w[0] = 1;
+      auto mul = [&](const fpw<W>& x, const fpw<W>& y) {
+        if constexpr (W == 8) { if (p256) return fp_mul_p256(x, y, C.m); }
+        return fp_mul_generic<W>(x, y, C.m, C.mprime);
+      };
+      for (size_t i = 4 * W; i + 8 * W <= in.size(); i += 8 * W) {
+        fpw<W> a, b;
+        memcpy(a.w, &in[i], 4 * W);
+        memcpy(b.w, &in[i + 4 * W], 4 * W);
+        fpw<W> am = mul(a, rsq), bm = mul(b, rsq);
+        fpw<W> c = mul(mul(am, bm), one_int);
+        fpw<W> s = fp_add<W>(am, bm, C.m), d = fp_sub<W>(am, bm, C.m);
+        fpw<W> sw = mul(s, one_int), dw = mul(d, one_int);
+        fwrite(c.w, 1, 4 * W, stdout);
+        fwrite(sw.w, 1, 4 * W, stdout);
+        fwrite(dw.w, 1, 4 * W, stdout);
+      }
+    };
+    if (!strcmp(argv[1], "fpmul8")) run(std::integral_constant<int, 8>{}, false);
+    else if (!strcmp(argv[1], "fpmul8p256")) run(std::integral_constant<int, 8>{}, true);
+    else if (!strcmp(argv[1], "fpmul4")) run(std::integral_constant<int, 4>{}, false);
+    else if (!strcmp(argv[1], "fpmul2")) run(std::integral_constant<int, 2>{}, false);
+    else return 2;
   } else if (!strcmp(argv[1], "sha")) {  // digest of stdin
     Sha256 s;
     s.init();
