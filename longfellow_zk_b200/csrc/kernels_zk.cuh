@@ -19,17 +19,19 @@
 namespace lf {
 
 // transcript writes of an element: tag + wire bytes (transcript.h:136-153)
+// (elements are taken by value and their words absorbed with a fully unrolled
+// loop, so the wire words stay in registers)
 template <class F>
-__device__ __forceinline__ void ts_write_elt(Transcript* ts, const typename F::Elt& e) {
+__device__ __forceinline__ void ts_array_elt(Transcript* ts, typename F::Elt e) {
   uint32_t w[F::kWords];
   F::to_wire(w, e);
-  ts->write_elt_words(w, F::kWords);
+#pragma unroll
+  for (int k = 0; k < F::kWords; ++k) ts->sha.put_word_be(bswap32(w[k]));
 }
 template <class F>
-__device__ __forceinline__ void ts_array_elt(Transcript* ts, const typename F::Elt& e) {
-  uint32_t w[F::kWords];
-  F::to_wire(w, e);
-  ts->elt_words(w, F::kWords);
+__device__ __forceinline__ void ts_write_elt(Transcript* ts, typename F::Elt e) {
+  ts->raw_byte(1);  // TAG_FIELD_ELEM
+  ts_array_elt<F>(ts, e);
 }
 
 // ----------------------------------------------------------------------------

@@ -64,6 +64,7 @@ struct ZkDims {
   uint32_t rng_total;
   uint32_t max_proof_bytes;
   uint32_t tinit_len;
+  uint32_t debug_stop;  // LF_DEBUG_STOP: early exit point inside k_lig_finish (bisecting)
 };
 
 // per-proof device buffers: base pointer + stride (in elements of the pointee)

@@ -1,0 +1,16 @@
+import sys, os
+import numpy as np
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+import longfellow_zk_b200 as lf
+from fixtures import load, rng_bytes
+which = sys.argv[1] if len(sys.argv) > 1 else "sha1_gf128"
+B = int(sys.argv[2]) if len(sys.argv) > 2 else 1
+fid = 4 if "gf128" in which else 1
+circ, wit = load(which)
+ctx = lf.Context(0)
+c = lf.Circuit(ctx, fid, circ)
+rng = np.stack([rng_bytes(1 + i, c.info["rng_bytes"]) for i in range(B)])
+W = np.repeat(np.frombuffer(wit, np.uint8)[None, :], B, axis=0)
+proofs, status = lf.ZkProver(c).prove_batch(W, rng)
+print("ok", which, B, [len(p) for p in proofs][:4], status[:4])
