@@ -144,6 +144,128 @@ k_rs_fp_rows(typename F::Elt* __restrict__ data, size_t row_stride, size_t batch
   }
 }
 
+// ---------------------------------------------------------------------------
+// The same extension through an exact real-input FFT convolution over
+// Fp2 = Fp[i]/(i^2+1), the counterpart of FFTExtConvolution + RFFT
+// (lib/algebra/convolution.h:128-191, lib/algebra/rfft.h:46-409): P-256 has no
+// 2-power roots of unity in Fp, but the norm-1 subgroup of Fp2 does (the root
+// of order 2^31 of lib/circuits/mdoc/mdoc_zk.cc:83-88).  With W a primitive
+// N-th root on the unit circle (conj(W) = 1/W), M = N/2 and V = W^2:
+//   z[j] = x[2j] + i x[2j+1];  Z = DFT_M(z) (decimation in frequency, output
+//   bit-reversed);  E2 = Z[k] + conj Z[M-k], O2 = -i (Z[k] - conj Z[M-k]),
+//   X2[k] = E2 + W^-k O2 (= 2 DFT_N(x)[k]);  P = X2 * Yh with Yh = DFT_N(1/i
+//   table)/(2N) precomputed;  Pe = P[k] + conj P[M-k], Po = (P[k] - conj P[M-k]) W^k,
+//   Q[k] = Pe + i Po;  q = inverse DFT_M(Q) (decimation in time, bit-reversed
+//   input)  ==>  conv[2j] = Re q[j], conv[2j+1] = Im q[j].
+// Every step is exact field arithmetic, so the result equals the direct sum
+// (k_rs_fp_rows) and the reference's output bit for bit.  One CTA per row; the
+// M complex points (64 B each) live in shared memory (128 KB for N = 4096).
+// ---------------------------------------------------------------------------
+template <class F>
+struct Cx {
+  typename F::Elt re, im;
+};
+template <class F>
+__device__ __forceinline__ Cx<F> cx_add(const Cx<F>& a, const Cx<F>& b) {
+  return Cx<F>{F::add(a.re, b.re), F::add(a.im, b.im)};
+}
+template <class F>
+__device__ __forceinline__ Cx<F> cx_sub(const Cx<F>& a, const Cx<F>& b) {
+  return Cx<F>{F::sub(a.re, b.re), F::sub(a.im, b.im)};
+}
+template <class F>
+__device__ __forceinline__ Cx<F> cx_conj(const Cx<F>& a) {
+  return Cx<F>{a.re, F::neg(a.im)};
+}
+template <class F>
+__device__ __forceinline__ Cx<F> cx_muli(const Cx<F>& a) {  // a * i
+  return Cx<F>{F::neg(a.im), a.re};
+}
+template <class F>
+__device__ __forceinline__ Cx<F> cx_mulmi(const Cx<F>& a) {  // a * (-i)
+  return Cx<F>{a.im, F::neg(a.re)};
+}
+// Fp2::mul with three base multiplications (lib/algebra/fp2.h:87-101)
+template <class F>
+__device__ __forceinline__ Cx<F> cx_mul(const Cx<F>& a, const Cx<F>& b) {
+  typename F::Elt t1 = F::mul(a.re, b.re), t2 = F::mul(a.im, b.im);
+  typename F::Elt t3 = F::mul(F::add(a.re, a.im), F::add(b.re, b.im));
+  return Cx<F>{F::sub(t1, t2), F::sub(F::sub(t3, t1), t2)};
+}
+
+template <class F>
+__global__ void __launch_bounds__(256)
+k_rs_fp_fft_rows(typename F::Elt* __restrict__ data, size_t row_stride, size_t batch_stride, uint32_t n,
+                 uint32_t m, uint32_t logM, const Cx<F>* __restrict__ Wk /* [M] W^k */,
+                 const Cx<F>* __restrict__ Yh /* [M+1] */, const typename F::Elt* __restrict__ lead,
+                 const typename F::Elt* __restrict__ binom) {
+  typedef typename F::Elt Elt;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  Cx<F>* a = reinterpret_cast<Cx<F>*>(smem_raw);
+  const uint32_t M = 1u << logM, tid = threadIdx.x, nth = blockDim.x;
+  Elt* y = data + (size_t)blockIdx.y * batch_stride + (size_t)blockIdx.x * row_stride;
+  auto brev = [logM](uint32_t k) { return logM ? (__brev(k) >> (32 - logM)) : 0u; };
+
+  for (uint32_t j = tid; j < M; j += nth) {
+    Cx<F> z;
+    z.re = (2 * j < n) ? F::mul(binom[2 * j], y[2 * j]) : F::zero();
+    z.im = (2 * j + 1 < n) ? F::mul(binom[2 * j + 1], y[2 * j + 1]) : F::zero();
+    a[j] = z;
+  }
+  __syncthreads();
+  // forward: decimation in frequency, twiddle V^-e = conj(W^(2e))
+  for (uint32_t lg = logM; lg >= 1; --lg) {
+    const uint32_t half = 1u << (lg - 1), step = M >> lg;
+    for (uint32_t t = tid; t < M / 2; t += nth) {
+      uint32_t j = t & (half - 1), i = (t >> (lg - 1)) << lg;
+      Cx<F> u = a[i + j], v = a[i + j + half];
+      a[i + j] = cx_add<F>(u, v);
+      Cx<F> dlt = cx_sub<F>(u, v);
+      a[i + j + half] = (j == 0) ? dlt : cx_mul<F>(dlt, cx_conj<F>(Wk[2 * j * step]));
+    }
+    __syncthreads();
+  }
+  // spectrum of the real sequence, multiply by Yh, re-pack for the inverse
+  for (uint32_t k = tid; k <= M / 2; k += nth) {
+    if (k == 0) {
+      Cx<F> z0 = a[0];
+      Elt e2 = F::add(z0.re, z0.re), o2 = F::add(z0.im, z0.im);
+      Cx<F> x0{F::add(e2, o2), F::zero()}, xm{F::sub(e2, o2), F::zero()};
+      Cx<F> p0 = cx_mul<F>(x0, Yh[0]), pm = cx_mul<F>(xm, Yh[M]);
+      a[0] = cx_add<F>(cx_add<F>(p0, pm), cx_muli<F>(cx_sub<F>(p0, pm)));
+    } else {
+      const uint32_t k2 = M - k, bk = brev(k), bk2 = brev(k2);
+      Cx<F> zk = a[bk], zk2c = cx_conj<F>(a[bk2]);
+      Cx<F> e2 = cx_add<F>(zk, zk2c), o2 = cx_mulmi<F>(cx_sub<F>(zk, zk2c));
+      const Cx<F> w = Wk[k];
+      Cx<F> xk = cx_add<F>(e2, cx_mul<F>(cx_conj<F>(w), o2));
+      Cx<F> xk2 = cx_sub<F>(cx_conj<F>(e2), cx_mul<F>(w, cx_conj<F>(o2)));
+      Cx<F> pk = cx_mul<F>(xk, Yh[k]), pk2c = cx_conj<F>(cx_mul<F>(xk2, Yh[k2]));
+      Cx<F> pe = cx_add<F>(pk, pk2c), po = cx_mul<F>(cx_sub<F>(pk, pk2c), w);
+      Cx<F> qk = cx_add<F>(pe, cx_muli<F>(po));
+      a[bk] = qk;
+      if (k2 != k) a[bk2] = cx_add<F>(cx_conj<F>(pe), cx_muli<F>(cx_conj<F>(po)));
+    }
+  }
+  __syncthreads();
+  // inverse: decimation in time on the bit-reversed array, twiddle V^e = W^(2e)
+  for (uint32_t lg = 1; lg <= logM; ++lg) {
+    const uint32_t half = 1u << (lg - 1), step = M >> lg;
+    for (uint32_t t = tid; t < M / 2; t += nth) {
+      uint32_t j = t & (half - 1), i = (t >> (lg - 1)) << lg;
+      Cx<F> u = a[i + j], v = a[i + j + half];
+      Cx<F> tv = (j == 0) ? v : cx_mul<F>(v, Wk[2 * j * step]);
+      a[i + j] = cx_add<F>(u, tv);
+      a[i + j + half] = cx_sub<F>(u, tv);
+    }
+    __syncthreads();
+  }
+  for (uint32_t k = n + tid; k < m; k += nth) {
+    const Cx<F>& q = a[k >> 1];
+    y[k] = F::mul(lead[k - (n - 1)], (k & 1) ? q.im : q.re);
+  }
+}
+
 // wire <-> Montgomery conversion of flat element arrays (boundary of the C ABI)
 template <class F>
 __global__ void k_from_wire(const uint8_t* __restrict__ in, typename F::Elt* __restrict__ out, size_t n,

@@ -211,7 +211,42 @@ struct RsFpTables {
   fpw<8>* d_inv = nullptr;    // [m] 1/i, inv[0] = 0
   fpw<8>* d_lead = nullptr;   // [m-n+1]
   fpw<8>* d_binom = nullptr;  // [n]
+  // FFT path (k_rs_fp_fft_rows): N = padding, M = N/2
+  uint32_t logM = 0;
+  Cx<FFp256>* d_wk = nullptr;  // [M] W^k
+  Cx<FFp256>* d_yh = nullptr;  // [M+1] DFT_N(1/i table) / (2N)
 };
+
+// host Fp2 over P-256 (Montgomery limbs)
+struct HCx {
+  fpw<8> re, im;
+};
+static HCx hcx_mul(const P256Host& H, const HCx& a, const HCx& b) {
+  return HCx{H.sub(H.mul(a.re, b.re), H.mul(a.im, b.im)), H.add(H.mul(a.re, b.im), H.mul(a.im, b.re))};
+}
+static void parse_dec256(const char* s, uint32_t out[8]) {
+  for (int i = 0; i < 8; ++i) out[i] = 0;
+  for (; *s; ++s) {
+    uint64_t c = (uint64_t)(*s - '0');
+    for (int i = 0; i < 8; ++i) {
+      c += (uint64_t)out[i] * 10;
+      out[i] = (uint32_t)c;
+      c >>= 32;
+    }
+  }
+}
+// primitive N-th root of unity on the unit circle of Fp2(P-256): the element of
+// order 2^31 of lib/circuits/mdoc/mdoc_zk.cc:83-88 / ecdsa/verify_test.cc:519-530, squared down
+static HCx p256_root(const P256Host& H, uint32_t logN) {
+  uint32_t x[8], y[8];
+  parse_dec256("112649224146410281873500457609690258373018840430489408729223714171582664680802", x);
+  parse_dec256("84087994358540907695740461427818660560182168997182378749313018254450460212908", y);
+  HCx w;
+  H.from_wire((const uint8_t*)x, &w.re);
+  H.from_wire((const uint8_t*)y, &w.im);
+  for (uint32_t o = 31; o > logN; --o) w = hcx_mul(H, w, w);
+  return w;
+}
 
 }  // namespace lf
 
@@ -321,6 +356,47 @@ static int ctx_rs_fp_tables(lf_ctx* ctx, size_t n, size_t m, RsFpTables** out) {
     for (size_t i = 1; i < n; ++i) binom[i] = H.mul(binom[i - 1], H.mul(sc[n - i], inv[i]));
     for (size_t i = 1; i < n; i += 2) binom[i] = H.sub(H.zero(), binom[i]);
     RsFpTables t;
+    {
+      // FFT tables: N = smallest power of two >= m (convolution.h:47-53 choose_padding)
+      uint32_t logN = 1;
+      while (((size_t)1 << logN) < m) ++logN;
+      const uint32_t N = 1u << logN, M = N / 2;
+      t.logM = logN - 1;
+      HCx W = p256_root(H, logN);
+      std::vector<HCx> wn(N);
+      wn[0] = HCx{H.one(), H.zero()};
+      for (uint32_t k = 1; k < N; ++k) wn[k] = hcx_mul(H, wn[k - 1], W);
+      // Yh = fftf_N(inv padded): radix-2 DIT with twiddles W^-e = conj(W^e)
+      std::vector<HCx> a(N);
+      auto brev = [logN](uint32_t k) {
+        uint32_t r = 0;
+        for (uint32_t i = 0; i < logN; ++i) r |= ((k >> i) & 1u) << (logN - 1 - i);
+        return r;
+      };
+      for (uint32_t j = 0; j < N; ++j) a[brev(j)] = HCx{j < m ? inv[j] : H.zero(), H.zero()};
+      for (uint32_t len = 2; len <= N; len <<= 1) {
+        uint32_t half = len / 2, step = N / len;
+        for (uint32_t i = 0; i < N; i += len)
+          for (uint32_t j = 0; j < half; ++j) {
+            HCx tw = wn[j * step];
+            tw.im = H.sub(H.zero(), tw.im);
+            HCx tv = hcx_mul(H, a[i + j + half], tw), u = a[i + j];
+            a[i + j] = HCx{H.add(u.re, tv.re), H.add(u.im, tv.im)};
+            a[i + j + half] = HCx{H.sub(u.re, tv.re), H.sub(u.im, tv.im)};
+          }
+      }
+      fpw<8> twoN = H.zero();
+      for (uint32_t i = 0; i < 2 * N; ++i) twoN = H.add(twoN, H.one());
+      fpw<8> s = H.inv(twoN);
+      std::vector<HCx> yh(M + 1), wk(M);
+      for (uint32_t k = 0; k <= M; ++k) yh[k] = HCx{H.mul(a[k].re, s), H.mul(a[k].im, s)};
+      for (uint32_t k = 0; k < M; ++k) wk[k] = wn[k];
+      static_assert(sizeof(HCx) == sizeof(Cx<FFp256>), "Cx layout");
+      LF_CUDA(cudaMalloc(&t.d_wk, wk.size() * sizeof(HCx)));
+      LF_CUDA(cudaMalloc(&t.d_yh, yh.size() * sizeof(HCx)));
+      LF_CUDA(cudaMemcpy(t.d_wk, wk.data(), wk.size() * sizeof(HCx), cudaMemcpyHostToDevice));
+      LF_CUDA(cudaMemcpy(t.d_yh, yh.data(), yh.size() * sizeof(HCx), cudaMemcpyHostToDevice));
+    }
     LF_CUDA(cudaMalloc(&t.d_inv, m * 32));
     LF_CUDA(cudaMalloc(&t.d_lead, lead.size() * 32));
     LF_CUDA(cudaMalloc(&t.d_binom, n * 32));
@@ -337,18 +413,28 @@ static int launch_rs_p256(lf_ctx* ctx, fpw<8>* d_rows, size_t row_stride, size_t
                           size_t nbatch, size_t n, size_t m) {
   if (n == 0 || m < n || m > (1u << 24)) return fail(LF_ERR_ARG, "rs: need 0 < n <= m <= 2^24");
   if (nrows == 0 || nbatch == 0 || m == n) return 0;
-  if (n * 32 > 200 * 1024) return fail(LF_ERR_UNSUPPORTED, "rs: n > 6400 over Fp256 needs the FFT path (not built yet)");
+  if (m > 6400) return fail(LF_ERR_UNSUPPORTED, "rs: m > 6400 over Fp256 needs a global-memory FFT (not built yet)");
   RsFpTables* t;
   int rc = ctx_rs_fp_tables(ctx, n, m, &t);
   if (rc) return rc;
   static bool attr_set = false;
   if (!attr_set) {
     LF_CUDA(cudaFuncSetAttribute(k_rs_fp_rows<FFp256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    LF_CUDA(cudaFuncSetAttribute(k_rs_fp_fft_rows<FFp256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     attr_set = true;
   }
   dim3 grid((unsigned)nrows, (unsigned)nbatch);
-  k_rs_fp_rows<FFp256><<<grid, 256, n * 32, ctx->stream>>>(d_rows, row_stride, batch_stride, (uint32_t)n,
-                                                          (uint32_t)m, t->d_inv, t->d_lead, t->d_binom);
+  static const bool force_direct = getenv("LF_RS_DIRECT") != nullptr;
+  const size_t fft_smem = ((size_t)64) << t->logM;
+  // the direct Toeplitz sum costs n*(m-n) multiplications, the FFT ~ 10 N log N
+  if (!force_direct && n * (m - n) > 4096 && fft_smem <= 200 * 1024) {
+    k_rs_fp_fft_rows<FFp256><<<grid, 256, fft_smem, ctx->stream>>>(d_rows, row_stride, batch_stride, (uint32_t)n,
+                                                                (uint32_t)m, t->logM, t->d_wk, t->d_yh, t->d_lead,
+                                                                t->d_binom);
+  } else {
+    k_rs_fp_rows<FFp256><<<grid, 256, n * 32, ctx->stream>>>(d_rows, row_stride, batch_stride, (uint32_t)n,
+                                                            (uint32_t)m, t->d_inv, t->d_lead, t->d_binom);
+  }
   ctx->launches++;
   LF_CUDA(cudaGetLastError());
   return 0;
@@ -488,6 +574,8 @@ void lf_ctx_destroy(lf_ctx* ctx) {
     cudaFree(kv.second.d_inv);
     cudaFree(kv.second.d_lead);
     cudaFree(kv.second.d_binom);
+    cudaFree(kv.second.d_wk);
+    cudaFree(kv.second.d_yh);
   }
   cudaFree(ctx->d_tw);
   if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
