@@ -31,9 +31,16 @@ UNIT = "proofs/s"
 WORKLOAD = "BM_ShaZK_fp2_128/1: 1-block SHA-256 ZK proof, GF(2^128), rate 7, nreq 132"
 
 
-def load_fixture():
+WORKLOADS = {
+    # name -> (fixture, field id, description)
+    "sha": ("sha1_gf128", 4, WORKLOAD),
+    "ecdsa": ("ecdsa1_p256", 1, "BM_ECDSAZKProver/1: ECDSA P-256 verification ZK proof, Fp256, rate 7, nreq 132"),
+}
+
+
+def load_fixture(name="sha"):
     from fixtures import load
-    return load("sha1_gf128")
+    return load(WORKLOADS[name][0])
 
 
 def rng_stream(seed, n):
@@ -46,16 +53,17 @@ def rng_stream(seed, n):
 # the host cores, N independent single-threaded provers (the library has no
 # threads of its own, docs/content/en/docs/benchmarks.md:7).
 # ----------------------------------------------------------------------------
-def cpu_reference_throughput(nthreads, per_thread):
+def cpu_reference_throughput(nthreads, per_thread, workload="sha"):
     from oracle import refapi, portapi
-    circ, wit = load_fixture()
-    rng = rng_stream(1, 1 << 18)
+    circ, wit = load_fixture(workload)
+    fid = WORKLOADS[workload][1]
+    rng = rng_stream(1, 1 << 19)
     if refapi.available():
-        c = refapi.Circuit(refapi.GF2_128_ID, circ)
+        c = refapi.Circuit(fid, circ)
         secs, lat = c.bench(wit, rng, nthreads=nthreads, per_thread=per_thread)
         kind = "reference"
     else:  # the reference could not be built here: fall back to the oracle port
-        c = portapi.Circuit(portapi.GF2_128_ID, circ)
+        c = portapi.Circuit(fid, circ)
         t0 = time.time()
         for _ in range(per_thread):
             c.prove(wit, rng)
@@ -128,6 +136,64 @@ class ClockSampler:
         reasons = sorted({n for r in self.rows if len(r) >= 7 for n, v in zip(names, r[3:7]) if v == "Active"})
         return dict(sm_mhz=sm[len(sm) // 2] if sm else None, sm_max_mhz=max(mx) if mx else None,
                     reasons=reasons, samples=len(sm))
+
+
+def measure_other(lf, ctx, stream, workload, B, steps=3):
+    """device-resident and end-to-end proofs/s of another circuit (single GPU, rank 0)"""
+    import numpy as np
+    import torch
+    fixture, fid, desc = WORKLOADS[workload]
+    circ, wit = load_fixture(workload)
+    circuit = lf.Circuit(ctx, fid, circ)
+    prover = lf.ZkProver(circuit)
+    info = circuit.info
+    wb, rb, pb = info["witness_bytes"], info["rng_bytes"], info["max_proof_bytes"]
+    rstride = (rb + 15) & ~15
+    gen = torch.Generator().manual_seed(77)
+    h_wit = torch.from_numpy(np.frombuffer(wit, np.uint8).copy()).repeat(B, 1).pin_memory()
+    # every 32-byte sample must be < p: clear the top bit pattern that could exceed it
+    h_rng = torch.randint(0, 256, (B, rstride), dtype=torch.uint8, generator=gen)
+    h_rng[:, 31::32] &= 0x7F
+    h_rng = h_rng.pin_memory()
+    h_out = torch.empty((B, pb), dtype=torch.uint8).pin_memory()
+    h_len = torch.zeros(B, dtype=torch.int64).pin_memory()
+    h_st = torch.zeros(B, dtype=torch.int32).pin_memory()
+    d_wit, d_rng = h_wit.cuda(), h_rng.cuda()
+    d_out = torch.empty((B, pb), dtype=torch.uint8, device="cuda")
+    d_len = torch.zeros(B, dtype=torch.int64, device="cuda")
+    d_st = torch.zeros(B, dtype=torch.int32, device="cuda")
+
+    def dev():
+        prover.prove_batch_ptr(B, d_wit.data_ptr(), d_rng.data_ptr(), rstride, d_out.data_ptr(), pb,
+                               d_len.data_ptr(), d_st.data_ptr(), device=True)
+
+    def host():
+        prover.prove_batch_ptr(B, h_wit.data_ptr(), h_rng.data_ptr(), rstride, h_out.data_ptr(), pb,
+                               h_len.data_ptr(), h_st.data_ptr(), device=False)
+    for _ in range(3):
+        dev()
+    torch.cuda.synchronize()
+    assert int(d_st.abs().sum().item()) == 0
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(steps):
+        dev()
+    e1.record(stream)
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    prover.set_profiling(True)
+    dev()
+    stages = prover.stage_ms()
+    prover.set_profiling(False)
+    host()
+    t0 = time.perf_counter()
+    for _ in range(2):
+        host()
+    t1 = time.perf_counter()
+    assert int(h_st.abs().sum().item()) == 0
+    return dict(workload=desc, proofs_per_step=B, value=B * steps / (ms * 1e-3), unit=UNIT,
+                e2e=dict(value=2 * B / (t1 - t0), unit=UNIT), stage_ms=stages,
+                proof_bytes=int(d_len[0].item()), total_mults_per_proof=info["total_mults"])
 
 
 def run_ours(args):
@@ -288,6 +354,17 @@ def run_ours(args):
     cpu["single_thread_proofs_per_s"] = cpu1["value"]
     cpu["single_thread_ms_per_proof"] = cpu1["ms_per_proof_1thread"]
 
+    # ---- second workload (BASELINE.json configs[2]): ECDSA P-256 over Fp256, short run
+    other = {}
+    try:
+        other["ecdsa_p256"] = measure_other(lf, ctx, stream, "ecdsa", min(B, 1024))
+        ecpu = cpu_reference_throughput(nthreads, 6, "ecdsa")
+        ecpu1 = cpu_reference_throughput(1, 4, "ecdsa")
+        ecpu["single_thread_ms_per_proof"] = ecpu1["ms_per_proof_1thread"]
+        other["ecdsa_p256"]["cpu_baseline"] = ecpu
+    except Exception as ex:  # the headline line must not depend on the extra workload
+        other["ecdsa_p256"] = dict(error=str(ex))
+
     line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3),
                 ms_per_step=ms_total / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None,
                 dtype="gf2^128 (u32 limbs)", data="synthetic",
@@ -301,7 +378,7 @@ def run_ours(args):
                          d2h_bytes_per_step=B * (pb + 12), ms_per_step=ms_e2e / e2e_steps),
                 gpu_launches=launches, roofline=roofline, cpu_baseline=cpu,
                 latency_ms_per_proof_batch1=lat_ms,
-                ms_per_proof=ms_total / args.steps / B)
+                ms_per_proof=ms_total / args.steps / B, other_workloads=other)
     print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()
