@@ -63,6 +63,18 @@ const char* lf_version(void);
 /* replaces Field::mulf (fp_generic.h:187-198, gf2_128.h:233-235); host buffers. */
 int lf_elt_mul(lf_ctx* ctx, int field_id, const void* a, const void* b, void* out, size_t n);
 
+/* ---- (a4) FFT ----------------------------------------------------------- */
+/* replaces FFT<Field>::fftb (forward == 0: T[j] = sum_k F[k] w^{jk}) and fftf
+ * (forward != 0: w^-1), lib/algebra/fft.h:185-201, in place on n = 2^k host
+ * elements, unnormalised (fftf o fftb = n * id).  The root of unity is the
+ * field's standard one: BN254 (order 2^28, fft_test.cc:38-44), Fp128 and
+ * Goldilocks (order 2^32, reed_solomon_test.cc:358-360).  For LF_FIELD_P256 the
+ * transform is over Fp2 = Fp[i]/(i^2+1) (fft_test.cc:168-172): elts are n pairs
+ * (re, im) and the root is the order-2^31 element of mdoc_zk.cc:83-88. */
+int lf_fft(lf_ctx* ctx, int field_id, void* elts, size_t n, int forward);
+/* device-resident timing of fftb at size n (CUDA events on the context stream) */
+int lf_fft_time(lf_ctx* ctx, int field_id, size_t n, int reps, double* ms_per_fft);
+
 /* ---- (a7,a9) Reed-Solomon row extension -------------------------------- */
 /* replaces InterpolatorFactory::make(n, m)->interpolate(y) batched over rows
  * (lib/gf2k/lch14_reed_solomon.h:49-123, lib/algebra/reed_solomon.h:93-147):

@@ -27,7 +27,7 @@ EXPORTS = [
     "lf_elt_mul", "lf_rs_interpolate", "lf_rs_interpolate_dev", "lf_merkle_commit",
     "lf_circuit_upload", "lf_circuit_free", "lf_circuit_get_info", "lf_zk_prove_batch",
     "lf_zk_prove_batch_dev", "lf_zk_debug_fetch", "lf_ctx_launch_count", "lf_microbench",
-    "lf_circuit_set_profiling", "lf_circuit_get_stage_ms",
+    "lf_circuit_set_profiling", "lf_circuit_get_stage_ms", "lf_fft", "lf_fft_time",
 ]
 
 
@@ -67,6 +67,8 @@ def lib():
                                         C.POINTER(C.c_size_t)]
         L.lf_circuit_set_profiling.argtypes = [C.c_void_p, C.c_int]
         L.lf_circuit_get_stage_ms.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.c_size_t]
+        L.lf_fft.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.c_int]
+        L.lf_fft_time.argtypes = [C.c_void_p, C.c_int, C.c_size_t, C.c_int, C.POINTER(C.c_double)]
         L.lf_microbench.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_double)]
         _lib = L
     return _lib

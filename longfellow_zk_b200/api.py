@@ -15,7 +15,10 @@ from ._native import LongfellowError, check  # noqa: F401
 
 FIELD_P256 = 1
 FIELD_GF2_128 = 4
-KBYTES = {FIELD_P256: 32, FIELD_GF2_128: 16}
+FIELD_BN254 = 100
+FIELD_FP128 = 101
+FIELD_GOLDILOCKS = 102
+KBYTES = {FIELD_P256: 32, FIELD_GF2_128: 16, FIELD_BN254: 32, FIELD_FP128: 16, FIELD_GOLDILOCKS: 8}
 
 
 def _u8(a):
@@ -58,6 +61,18 @@ class Context:
         check(_native.lib().lf_elt_mul(self._h, field_id, _p(a), _p(b), _p(out),
                                        a.size // KBYTES[field_id]))
         return out
+
+    def fft(self, field_id, elts, n, forward=False):
+        """FFT<Field>::fftb / fftf (algebra/fft.h:185-201) on n elements (wire encoding);
+        for FIELD_P256 the elements are n (re, im) pairs of Fp2."""
+        elts = _u8(elts).copy()
+        check(_native.lib().lf_fft(self._h, field_id, _p(elts), n, int(forward)))
+        return elts
+
+    def fft_time_ms(self, field_id, n, reps=10):
+        ms = C.c_double()
+        check(_native.lib().lf_fft_time(self._h, field_id, n, reps, C.byref(ms)))
+        return ms.value
 
     def microbench(self, what):
         g = C.c_double()

@@ -137,56 +137,96 @@ struct FGf128 {
 #endif
 };
 
-// ---------------------------------------------------------------------------
-// Fp256Base = FpGeneric<4, true, Fp256Reduce> (lib/algebra/fp_p256.h:64-65,
-// lib/ec/p256.h:42): the NIST P-256 base field.  sample_subfield == sample,
-// in_subfield == true, kSubFieldBytes == kBytes (fp_generic.h:278,373-400).
-// ---------------------------------------------------------------------------
 #ifdef __CUDACC__
-static __constant__ FpConsts<8> c_p256;
+static __constant__ FpConsts<8> c_p256;   // lib/algebra/fp_p256.h
+static __constant__ FpConsts<8> c_bn254;  // Fp<4>, lib/algebra/fft_test.cc:33-36
+static __constant__ FpConsts<4> c_fp128;  // lib/algebra/fp_p128.h
+static __constant__ FpConsts<2> c_gold;   // Fp<1> 2^64-2^32+1
 #endif
 
-struct FFp256 {
-  typedef fpw<8> Elt;
-  static constexpr int kWords = 8;
-  static constexpr int kBytes = 32;
-  static constexpr int kSubBytes = 32;
-  static constexpr bool kChar2 = false;
+struct P256Traits {
+  static constexpr int W = 8;
   static constexpr int kFieldId = 1;  // proto/circuit_io.h P256_ID
+  static constexpr bool kP256 = true;
+#ifdef __CUDACC__
+  __device__ static __forceinline__ const FpConsts<8>& C() { return c_p256; }
+#endif
+};
+struct Bn254Traits {
+  static constexpr int W = 8;
+  static constexpr int kFieldId = 100;
+  static constexpr bool kP256 = false;
+#ifdef __CUDACC__
+  __device__ static __forceinline__ const FpConsts<8>& C() { return c_bn254; }
+#endif
+};
+struct Fp128Traits {
+  static constexpr int W = 4;
+  static constexpr int kFieldId = 101;
+  static constexpr bool kP256 = false;
+#ifdef __CUDACC__
+  __device__ static __forceinline__ const FpConsts<4>& C() { return c_fp128; }
+#endif
+};
+struct GoldTraits {
+  static constexpr int W = 2;
+  static constexpr int kFieldId = 102;
+  static constexpr bool kP256 = false;
+#ifdef __CUDACC__
+  __device__ static __forceinline__ const FpConsts<2>& C() { return c_gold; }
+#endif
+};
+
+template <class T>
+struct FFp {
+  static constexpr int W = T::W;
+  typedef fpw<W> Elt;
+  static constexpr int kWords = W;
+  static constexpr int kBytes = 4 * W;
+  static constexpr int kSubBytes = 4 * W;
+  static constexpr bool kChar2 = false;
+  static constexpr int kFieldId = T::kFieldId;
 
   struct Acc {
     Elt v;
   };
 
 #ifdef __CUDACC__
-  // one out-of-line Montgomery product (same reason as gf_mul_wide_fn)
-  static __device__ __noinline__ Elt mul_fn(Elt a, Elt b) { return fp_mul_p256(a, b, c_p256.m); }
+  // one out-of-line Montgomery product per field (same reason as gf_mul_wide_fn)
+  static __device__ __noinline__ Elt mul_fn(Elt a, Elt b) {
+    if constexpr (T::kP256) {
+      return fp_mul_p256(a, b, T::C().m);
+    } else {
+      return fp_mul_generic<W>(a, b, T::C().m, T::C().mprime);
+    }
+  }
   __device__ static __forceinline__ Elt zero() {
     Elt r;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) r.w[i] = 0;
+    for (int i = 0; i < W; ++i) r.w[i] = 0;
     return r;
   }
-  __device__ static __forceinline__ Elt one() {
+  __device__ static __forceinline__ Elt cst(const uint32_t* src) {
     Elt r;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) r.w[i] = c_p256.one[i];
+    for (int i = 0; i < W; ++i) r.w[i] = src[i];
     return r;
   }
-  __device__ static __forceinline__ Elt add(const Elt& a, const Elt& b) { return fp_add<8>(a, b, c_p256.m); }
-  __device__ static __forceinline__ Elt sub(const Elt& a, const Elt& b) { return fp_sub<8>(a, b, c_p256.m); }
-  __device__ static __forceinline__ Elt neg(const Elt& a) { return fp_sub<8>(zero(), a, c_p256.m); }
+  __device__ static __forceinline__ Elt one() { return cst(T::C().one); }
+  __device__ static __forceinline__ Elt add(const Elt& a, const Elt& b) { return fp_add<W>(a, b, T::C().m); }
+  __device__ static __forceinline__ Elt sub(const Elt& a, const Elt& b) { return fp_sub<W>(a, b, T::C().m); }
+  __device__ static __forceinline__ Elt neg(const Elt& a) { return fp_sub<W>(zero(), a, T::C().m); }
   __device__ static __forceinline__ Elt mul(const Elt& a, const Elt& b) { return mul_fn(a, b); }
   __device__ static __forceinline__ bool is_zero(const Elt& a) {
     uint32_t o = 0;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) o |= a.w[i];
+    for (int i = 0; i < W; ++i) o |= a.w[i];
     return o == 0;
   }
   __device__ static __forceinline__ bool eq(const Elt& a, const Elt& b) {
     uint32_t o = 0;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) o |= a.w[i] ^ b.w[i];
+    for (int i = 0; i < W; ++i) o |= a.w[i] ^ b.w[i];
     return o == 0;
   }
   // the reference's Accum is a wide integer (fp_generic.h:424-440); an eager
@@ -198,70 +238,69 @@ struct FFp256 {
   __device__ static __forceinline__ Elt reduce(const Acc& a) { return a.v; }
 
   // from_montgomery / to_montgomery (fp_generic.h:264-281)
-  __device__ static __forceinline__ void to_wire(uint32_t out[8], const Elt& a) {
-    Elt o;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) o.w[i] = 0;
+  __device__ static __forceinline__ void to_wire(uint32_t out[W], const Elt& a) {
+    Elt o = zero();
     o.w[0] = 1;
     Elt r = mul(a, o);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) out[i] = r.w[i];
+    for (int i = 0; i < W; ++i) out[i] = r.w[i];
   }
-  __device__ static __forceinline__ Elt from_wire(const uint32_t in[8]) {
-    Elt a, q;
+  __device__ static __forceinline__ Elt from_wire(const uint32_t in[W]) {
+    Elt a;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      a.w[i] = in[i];
-      q.w[i] = c_p256.rsq[i];
-    }
-    return mul(a, q);
+    for (int i = 0; i < W; ++i) a.w[i] = in[i];
+    return mul(a, cst(T::C().rsq));
   }
   // of_bytes_field (fp_generic.h:351-358): *ok = false if the value is >= p
   __device__ static __forceinline__ Elt from_bytes(const uint8_t* p, bool* ok) {
-    uint32_t in[8];
+    uint32_t in[W];
     if ((reinterpret_cast<uintptr_t>(p) & 3) == 0) {
       const uint32_t* q = reinterpret_cast<const uint32_t*>(p);
 #pragma unroll
-      for (int k = 0; k < 8; ++k) in[k] = q[k];
+      for (int k = 0; k < W; ++k) in[k] = q[k];
     } else {
 #pragma unroll
-      for (int k = 0; k < 8; ++k)
+      for (int k = 0; k < W; ++k)
         in[k] = (uint32_t)p[4 * k] | ((uint32_t)p[4 * k + 1] << 8) | ((uint32_t)p[4 * k + 2] << 16) |
                 ((uint32_t)p[4 * k + 3] << 24);
     }
-    if (fp_geq<8>(in, c_p256.m)) *ok = false;
+    if (fp_geq<W>(in, T::C().m)) *ok = false;
     return from_wire(in);
   }
-  // Field::sample on one 32-byte slot of the caller's stream (fp_generic.h:360-371).
-  // exact_bits == 256, so there is no masking; a value >= p (probability 2^-32)
-  // would make the reference draw again -- reported through *ok.
-  __device__ static __forceinline__ Elt sample_bytes(const uint8_t* p, bool* ok) { return from_bytes(p, ok); }
+  // Field::sample on one slot of the caller's stream (fp_generic.h:360-371): the
+  // candidate is masked to exact_bits; a value >= p would make the reference
+  // draw again -- reported through *ok.
+  __device__ static __forceinline__ void mask_bits(uint32_t in[W]) {
+    const uint32_t eb = T::C().exact_bits;
+#pragma unroll
+    for (int k = 0; k < W; ++k) {
+      uint32_t lo = 32u * k;
+      if (eb <= lo) in[k] = 0;
+      else if (eb < lo + 32) in[k] &= (1u << (eb - lo)) - 1u;
+    }
+  }
+  __device__ static __forceinline__ Elt sample_bytes(const uint8_t* p, bool* ok) {
+    uint32_t in[W];
+#pragma unroll
+    for (int k = 0; k < W; ++k)
+      in[k] = (uint32_t)p[4 * k] | ((uint32_t)p[4 * k + 1] << 8) | ((uint32_t)p[4 * k + 2] << 16) |
+              ((uint32_t)p[4 * k + 3] << 24);
+    mask_bits(in);
+    if (fp_geq<W>(in, T::C().m)) *ok = false;
+    return from_wire(in);
+  }
   __device__ static __forceinline__ Elt ts_elt(Transcript* ts) {
-    uint32_t in[8];
+    uint32_t in[W];
     for (;;) {
-      ts->words(in, 8);
-      if (!fp_geq<8>(in, c_p256.m)) break;
+      ts->words(in, W);
+      mask_bits(in);
+      if (!fp_geq<W>(in, T::C().m)) break;
     }
     return from_wire(in);
   }
-  __device__ static __forceinline__ Elt evalpt(int i) {
-    Elt r;
-#pragma unroll
-    for (int k = 0; k < 8; ++k) r.w[k] = c_p256.evalpt[i][k];
-    return r;
-  }
-  __device__ static __forceinline__ Elt newton(int k, int i) {
-    Elt r;
-#pragma unroll
-    for (int q = 0; q < 8; ++q) r.w[q] = c_p256.newton[k][i][q];
-    return r;
-  }
-  __device__ static __forceinline__ Elt lag_id(int k, int i) {
-    Elt r;
-#pragma unroll
-    for (int q = 0; q < 8; ++q) r.w[q] = c_p256.lag_id[k][i][q];
-    return r;
-  }
+  __device__ static __forceinline__ Elt evalpt(int i) { return cst(T::C().evalpt[i]); }
+  __device__ static __forceinline__ Elt newton(int k, int i) { return cst(T::C().newton[k][i]); }
+  __device__ static __forceinline__ Elt lag_id(int k, int i) { return cst(T::C().lag_id[k][i]); }
   __device__ static __forceinline__ Elt of_sub16(uint32_t) { return zero(); }        // never used
   __device__ static __forceinline__ bool solve_sub16(const Elt&, uint32_t* u) {       // never used
     *u = 0;
@@ -269,6 +308,13 @@ struct FFp256 {
   }
 #endif
 };
+
+// Fp256Base = FpGeneric<4, true, Fp256Reduce> (lib/algebra/fp_p256.h:64-65, lib/ec/p256.h:42);
+// sample_subfield == sample, in_subfield == true, kSubFieldBytes == kBytes (fp_generic.h:278,373-400)
+typedef FFp<P256Traits> FFp256;
+typedef FFp<Bn254Traits> FFpBn254;
+typedef FFp<Fp128Traits> FFp128;
+typedef FFp<GoldTraits> FFpGold;
 
 // arrays/affine.h:25-52
 template <class F>

@@ -18,6 +18,7 @@
 #include "field.cuh"
 #include "hash.cuh"
 #include "kernels_commit.cuh"
+#include "kernels_fft.cuh"
 #include "kernels_zk.cuh"
 #include "zk_types.cuh"
 
@@ -160,6 +161,91 @@ struct RsPlanHost {
   RsStep* d_steps = nullptr;
 };
 
+static void parse_dec_words(const char* s, uint32_t* out, int W) {
+  for (int i = 0; i < W; ++i) out[i] = 0;
+  for (; *s; ++s) {
+    uint64_t c = (uint64_t)(*s - '0');
+    for (int i = 0; i < W; ++i) {
+      c += (uint64_t)out[i] * 10;
+      out[i] = (uint32_t)c;
+      c >>= 32;
+    }
+  }
+}
+
+// host arithmetic of a Montgomery field with W 32-bit limbs (same limb code as the device)
+template <int W>
+struct FpHostT {
+  FpConsts<W> C;
+  fpw<W> omega;            // root of unity of order 2^omega_log (Montgomery form), if any
+  uint32_t omega_log = 0;
+  explicit FpHostT(const char* modulus_dec, const char* omega_dec = nullptr, uint32_t olog = 0) {
+    uint32_t m[W];
+    parse_dec_words(modulus_dec, m, W);
+    fp_build_consts<W>(m, &C);
+    if (omega_dec) {
+      uint32_t o[W];
+      parse_dec_words(omega_dec, o, W);
+      from_wire((const uint8_t*)o, &omega);
+      omega_log = olog;
+    }
+  }
+  fpw<W> mul(const fpw<W>& a, const fpw<W>& b) const { return fp_mul_generic<W>(a, b, C.m, C.mprime); }
+  fpw<W> add(const fpw<W>& a, const fpw<W>& b) const { return fp_add<W>(a, b, C.m); }
+  fpw<W> sub(const fpw<W>& a, const fpw<W>& b) const { return fp_sub<W>(a, b, C.m); }
+  fpw<W> one() const {
+    fpw<W> r;
+    for (int i = 0; i < W; ++i) r.w[i] = C.one[i];
+    return r;
+  }
+  fpw<W> zero() const {
+    fpw<W> r;
+    for (int i = 0; i < W; ++i) r.w[i] = 0;
+    return r;
+  }
+  fpw<W> inv(const fpw<W>& a) const {
+    uint32_t e[W], two[W];
+    for (int i = 0; i < W; ++i) two[i] = 0;
+    two[0] = 2;
+    fp_subn<W>(e, C.m, two);
+    return fp_pow_host<W>(a, e, C);
+  }
+  bool from_wire(const uint8_t* p, fpw<W>* out) const {
+    fpw<W> a, q;
+    memcpy(a.w, p, 4 * W);
+    if (fp_geq<W>(a.w, C.m)) return false;
+    for (int i = 0; i < W; ++i) q.w[i] = C.rsq[i];
+    *out = mul(a, q);
+    return true;
+  }
+  void to_wire(uint8_t* p, const fpw<W>& a) const {
+    fpw<W> o = zero();
+    o.w[0] = 1;
+    fpw<W> r = mul(a, o);
+    memcpy(p, r.w, 4 * W);
+  }
+  // primitive 2^logn-th root
+  fpw<W> root(uint32_t logn) const {
+    fpw<W> w = omega;
+    for (uint32_t o = omega_log; o > logn; --o) w = mul(w, w);
+    return w;
+  }
+};
+// the benchmark fields of lib/algebra/fft_test.cc:33-44 and reed_solomon_test.cc:337-401
+static const FpHostT<8>& bn254_host() {
+  static const FpHostT<8> h("21888242871839275222246405745257275088548364400416034343698204186575808495617",
+                            "19103219067921713944291392827692070036145651957329286315305642004821462161904", 28);
+  return h;
+}
+static const FpHostT<4>& fp128_host() {
+  static const FpHostT<4> h("340282042402384805036647824275747635201", "164956748514267535023998284330560247862", 32);
+  return h;
+}
+static const FpHostT<2>& gold_host() {
+  static const FpHostT<2> h("18446744069414584321", "1753635133440165772", 32);
+  return h;
+}
+
 // host copy of the P-256 constant block and helpers on Montgomery limbs
 struct P256Host {
   FpConsts<8> C;
@@ -260,6 +346,8 @@ struct lf_ctx {
   gf128* d_tw = nullptr;
   std::map<std::pair<size_t, size_t>, RsPlanHost> rs_plans;
   std::map<std::pair<size_t, size_t>, RsFpTables> rs_fp;
+  std::map<std::pair<int, uint32_t>, void*> fft_tw;             // (field, logn) -> w^k, k < n/2
+  std::map<std::pair<int, std::pair<size_t, size_t>>, void*> rs_conv;  // (field,(n,m)) -> RsConvTables*
   uint64_t launches = 0;
   int sm_count = 0;
 };
@@ -320,41 +408,52 @@ static int launch_rs_gf(lf_ctx* ctx, gf128* d_rows, size_t row_stride, size_t nr
   return 0;
 }
 
+// inv[i] = 1/i, lead, binom of ReedSolomon(n, m) (lib/algebra/reed_solomon.h:51-88,
+// lib/algebra/utility.h:51-72) in Montgomery form, for any host field H
+template <class H, class E>
+static void rs_tables_host(const H& Hf, size_t n, size_t m, std::vector<E>& inv, std::vector<E>& lead,
+                           std::vector<E>& binom) {
+  const size_t d = n - 1;
+  std::vector<E> sc(m);
+  inv.resize(m);
+  lead.resize(m - n + 1);
+  binom.resize(n);
+  sc[0] = Hf.zero();
+  for (size_t i = 1; i < m; ++i) sc[i] = Hf.add(sc[i - 1], Hf.one());
+  {
+    std::vector<E> pre(m);
+    E p = Hf.one();
+    inv[0] = Hf.zero();
+    for (size_t i = 1; i < m; ++i) {
+      pre[i] = p;
+      p = Hf.mul(p, sc[i]);
+    }
+    p = Hf.inv(p);
+    for (size_t i = m; i-- > 1;) {
+      inv[i] = Hf.mul(pre[i], p);
+      p = Hf.mul(p, sc[i]);
+    }
+  }
+  // reed_solomon.h:62-79 leading constants (-1)^d (k-d) C(k,d)
+  lead[0] = Hf.one();
+  for (size_t i = 1; i + d < m; ++i) lead[i] = Hf.mul(lead[i - 1], Hf.mul(sc[d + i], inv[i]));
+  for (size_t k = d; k < m; ++k) {
+    lead[k - d] = Hf.mul(lead[k - d], sc[k - d]);
+    if (d % 2 == 1) lead[k - d] = Hf.sub(Hf.zero(), lead[k - d]);
+  }
+  // reed_solomon.h:81-87 (-1)^i C(d, i)
+  binom[0] = Hf.one();
+  for (size_t i = 1; i < n; ++i) binom[i] = Hf.mul(binom[i - 1], Hf.mul(sc[n - i], inv[i]));
+  for (size_t i = 1; i < n; i += 2) binom[i] = Hf.sub(Hf.zero(), binom[i]);
+}
+
 static int ctx_rs_fp_tables(lf_ctx* ctx, size_t n, size_t m, RsFpTables** out) {
   auto key = std::make_pair(n, m);
   auto it = ctx->rs_fp.find(key);
   if (it == ctx->rs_fp.end()) {
     const P256Host& H = p256_host();
-    const size_t d = n - 1;
-    std::vector<fpw<8>> inv(m), sc(m), lead(m - n + 1), binom(n);
-    // utility.h:51-72 batch_inverse_arithmetic: inv[i] = 1/i
-    sc[0] = H.zero();
-    for (size_t i = 1; i < m; ++i) sc[i] = H.add(sc[i - 1], H.one());
-    {
-      std::vector<fpw<8>> pre(m);
-      fpw<8> p = H.one();
-      inv[0] = H.zero();
-      for (size_t i = 1; i < m; ++i) {
-        pre[i] = p;
-        p = H.mul(p, sc[i]);
-      }
-      p = H.inv(p);
-      for (size_t i = m; i-- > 1;) {
-        inv[i] = H.mul(pre[i], p);
-        p = H.mul(p, sc[i]);
-      }
-    }
-    // reed_solomon.h:62-79 leading constants (-1)^d (k-d) C(k,d)
-    lead[0] = H.one();
-    for (size_t i = 1; i + d < m; ++i) lead[i] = H.mul(lead[i - 1], H.mul(sc[d + i], inv[i]));
-    for (size_t k = d; k < m; ++k) {
-      lead[k - d] = H.mul(lead[k - d], sc[k - d]);
-      if (d % 2 == 1) lead[k - d] = H.sub(H.zero(), lead[k - d]);
-    }
-    // reed_solomon.h:81-87 (-1)^i C(d, i)
-    binom[0] = H.one();
-    for (size_t i = 1; i < n; ++i) binom[i] = H.mul(binom[i - 1], H.mul(sc[n - i], inv[i]));
-    for (size_t i = 1; i < n; i += 2) binom[i] = H.sub(H.zero(), binom[i]);
+    std::vector<fpw<8>> inv, lead, binom;
+    rs_tables_host(H, n, m, inv, lead, binom);
     RsFpTables t;
     {
       // FFT tables: N = smallest power of two >= m (convolution.h:47-53 choose_padding)
@@ -440,6 +539,161 @@ static int launch_rs_p256(lf_ctx* ctx, fpw<8>* d_rows, size_t row_stride, size_t
   return 0;
 }
 
+// ---------------------------------------------------------------- stand-alone FFT
+template <class A>
+static int fft_run(lf_ctx* ctx, typename A::Elt* d, size_t batch_stride, size_t nbatch, uint32_t logn,
+                   const typename A::Elt* d_tw, bool inverse_root, bool dif, bool bitrev) {
+  typedef typename A::Elt Elt;
+  if (logn == 0 || nbatch == 0) return 0;
+  static bool attr_set = false;
+  if (!attr_set) {
+    LF_CUDA(cudaFuncSetAttribute(k_fft_stages<A>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    attr_set = true;
+  }
+  uint32_t tile_log = 0;
+  while ((sizeof(Elt) << (tile_log + 1)) <= 64 * 1024) ++tile_log;
+  struct Grp {
+    uint32_t s0, nst, logL;
+  };
+  std::vector<Grp> groups;
+  uint32_t s = std::min(tile_log, logn);
+  groups.push_back(Grp{0, s, 0});
+  while (s < logn) {
+    uint32_t logL = std::min<uint32_t>(s, 5);
+    uint32_t nst = std::min(logn - s, tile_log - logL);
+    groups.push_back(Grp{s, nst, logL});
+    s += nst;
+  }
+  const unsigned nb = (unsigned)nbatch;
+  auto do_bitrev = [&]() {
+    k_fft_bitrev<A><<<dim3(((1u << logn) + 255) / 256, nb), 256, 0, ctx->stream>>>(d, logn, batch_stride);
+    ctx->launches++;
+  };
+  if (!dif && bitrev) do_bitrev();
+  for (size_t gi = 0; gi < groups.size(); ++gi) {
+    const Grp& g = dif ? groups[groups.size() - 1 - gi] : groups[gi];
+    const uint32_t tile = 1u << (g.nst + g.logL);
+    k_fft_stages<A><<<dim3((1u << logn) / tile, nb), 256, (size_t)tile * sizeof(Elt), ctx->stream>>>(
+        d, batch_stride, logn, g.s0, g.nst, g.logL, d_tw, inverse_root ? 1 : 0, dif ? 1 : 0);
+    ctx->launches++;
+  }
+  if (dif && bitrev) do_bitrev();
+  LF_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// w^k, k < n/2 for the scalar fields
+template <class H, int W>
+static int fft_twiddles(lf_ctx* ctx, int field_id, const H& Hf, uint32_t logn, fpw<W>** out) {
+  auto key = std::make_pair(field_id, logn);
+  auto it = ctx->fft_tw.find(key);
+  if (it == ctx->fft_tw.end()) {
+    if (logn > Hf.omega_log) return fail(LF_ERR_ARG, "fft: n exceeds the order of the field's root of unity");
+    const size_t half = logn ? ((size_t)1 << (logn - 1)) : 1;
+    std::vector<fpw<W>> tw(half);
+    fpw<W> w = Hf.root(logn);
+    tw[0] = Hf.one();
+    for (size_t k = 1; k < half; ++k) tw[k] = Hf.mul(tw[k - 1], w);
+    void* dptr;
+    LF_CUDA(cudaMalloc(&dptr, half * sizeof(fpw<W>)));
+    LF_CUDA(cudaMemcpy(dptr, tw.data(), half * sizeof(fpw<W>), cudaMemcpyHostToDevice));
+    it = ctx->fft_tw.emplace(key, dptr).first;
+  }
+  *out = (fpw<W>*)it->second;
+  return 0;
+}
+// W^k, k < n/2 in Fp2 of P-256 (key: field id 1)
+static int fft_twiddles_p256(lf_ctx* ctx, uint32_t logn, Cx<FFp256>** out) {
+  auto key = std::make_pair((int)LF_FIELD_P256, logn);
+  auto it = ctx->fft_tw.find(key);
+  if (it == ctx->fft_tw.end()) {
+    if (logn > 31) return fail(LF_ERR_ARG, "fft: n exceeds 2^31");
+    const P256Host& H = p256_host();
+    const size_t half = logn ? ((size_t)1 << (logn - 1)) : 1;
+    std::vector<HCx> tw(half);
+    HCx w = p256_root(H, logn);
+    tw[0] = HCx{H.one(), H.zero()};
+    for (size_t k = 1; k < half; ++k) tw[k] = hcx_mul(H, tw[k - 1], w);
+    void* dptr;
+    LF_CUDA(cudaMalloc(&dptr, half * sizeof(HCx)));
+    LF_CUDA(cudaMemcpy(dptr, tw.data(), half * sizeof(HCx), cudaMemcpyHostToDevice));
+    it = ctx->fft_tw.emplace(key, dptr).first;
+  }
+  *out = (Cx<FFp256>*)it->second;
+  return 0;
+}
+
+// ReedSolomon over a field with 2-power roots = FFTConvolution
+// (lib/algebra/convolution.h:55-106): fftf(x) * fftf(1/i table) / N -> fftb
+struct RsConvTables {
+  uint32_t logN = 0;
+  void *d_yh = nullptr, *d_lead = nullptr, *d_binom = nullptr;
+};
+template <class F, class H>
+static int rs_conv_run(lf_ctx* ctx, const H& Hf, typename F::Elt* d_rows, size_t row_stride, size_t nrows, size_t n,
+                       size_t m) {
+  typedef typename F::Elt Elt;
+  typedef AlgF<F> A;
+  if (n == 0 || m < n) return fail(LF_ERR_ARG, "rs: need 0 < n <= m");
+  if (nrows == 0 || m == n) return 0;
+  uint32_t logN = 0;
+  while (((size_t)1 << logN) < m) ++logN;
+  const size_t N = (size_t)1 << logN;
+  Elt* d_tw;
+  int rc = fft_twiddles<H, F::W>(ctx, F::kFieldId, Hf, logN, &d_tw);
+  if (rc) return rc;
+  auto key = std::make_pair((int)F::kFieldId, std::make_pair(n, m));
+  auto it = ctx->rs_conv.find(key);
+  if (it == ctx->rs_conv.end()) {
+    std::vector<Elt> inv, lead, binom;
+    rs_tables_host(Hf, n, m, inv, lead, binom);
+    // fold the 1/N of the inverse transform into the leading constants
+    Elt nn = Hf.zero();
+    {
+      // N as a field element by doubling
+      nn = Hf.one();
+      for (uint32_t i = 0; i < logN; ++i) nn = Hf.add(nn, nn);
+    }
+    Elt ninv = Hf.inv(nn);
+    for (auto& v : lead) v = Hf.mul(v, ninv);
+    auto* t = new RsConvTables;
+    t->logN = logN;
+    std::vector<Elt> ypad(N, Hf.zero());
+    std::copy(inv.begin(), inv.end(), ypad.begin());
+    LF_CUDA(cudaMalloc(&t->d_yh, N * sizeof(Elt)));
+    LF_CUDA(cudaMalloc(&t->d_lead, lead.size() * sizeof(Elt)));
+    LF_CUDA(cudaMalloc(&t->d_binom, n * sizeof(Elt)));
+    LF_CUDA(cudaMemcpy(t->d_yh, ypad.data(), N * sizeof(Elt), cudaMemcpyHostToDevice));
+    LF_CUDA(cudaMemcpy(t->d_lead, lead.data(), lead.size() * sizeof(Elt), cudaMemcpyHostToDevice));
+    LF_CUDA(cudaMemcpy(t->d_binom, binom.data(), n * sizeof(Elt), cudaMemcpyHostToDevice));
+    // spectrum of the 1/i table, kept in the bit-reversed order the DIF transform leaves
+    if ((rc = fft_run<A>(ctx, (Elt*)t->d_yh, 0, 1, logN, d_tw, /*inverse_root=*/true, /*dif=*/true, false))) return rc;
+    LF_CUDA(cudaStreamSynchronize(ctx->stream));
+    it = ctx->rs_conv.emplace(key, (void*)t).first;
+  }
+  auto* t = (RsConvTables*)it->second;
+  Elt* x;
+  LF_CUDA(cudaMalloc(&x, nrows * N * sizeof(Elt)));
+  k_rs_pad<F><<<dim3((unsigned)((N + 255) / 256), (unsigned)nrows), 256, 0, ctx->stream>>>(
+      d_rows, row_stride, x, (uint32_t)n, (uint32_t)N, (const Elt*)t->d_binom);
+  ctx->launches++;
+  if ((rc = fft_run<A>(ctx, x, N, nrows, logN, d_tw, true, true, false)) == 0) {
+    k_fft_pointwise<A><<<dim3((unsigned)((N + 255) / 256), (unsigned)nrows), 256, 0, ctx->stream>>>(
+        x, (const Elt*)t->d_yh, N);
+    ctx->launches++;
+    rc = fft_run<A>(ctx, x, N, nrows, logN, d_tw, false, false, false);
+  }
+  if (rc == 0) {
+    k_rs_finish<F><<<dim3((unsigned)((m - n + 255) / 256), (unsigned)nrows), 256, 0, ctx->stream>>>(
+        d_rows, row_stride, x, (uint32_t)n, (uint32_t)m, (uint32_t)N, (const Elt*)t->d_lead);
+    ctx->launches++;
+    cudaError_t ce = cudaStreamSynchronize(ctx->stream);
+    if (ce != cudaSuccess) rc = fail(LF_ERR_CUDA, cudaGetErrorString(ce));
+  }
+  cudaFree(x);
+  return rc;
+}
+
 // field-generic front ends used by the ZK pipeline
 template <class F>
 static int launch_rs(lf_ctx* ctx, typename F::Elt* d_rows, size_t row_stride, size_t nrows, size_t batch_stride,
@@ -453,6 +707,25 @@ template <>
 int launch_rs<FFp256>(lf_ctx* ctx, fpw<8>* d_rows, size_t row_stride, size_t nrows, size_t batch_stride,
                       size_t nbatch, size_t n, size_t m) {
   return launch_rs_p256(ctx, d_rows, row_stride, nrows, batch_stride, nbatch, n, m);
+}
+
+template <>
+int launch_rs<FFpBn254>(lf_ctx* ctx, fpw<8>* d_rows, size_t row_stride, size_t nrows, size_t batch_stride,
+                        size_t nbatch, size_t n, size_t m) {
+  if (nbatch != 1) return fail(LF_ERR_UNSUPPORTED, "rs: batches over this field are not built");
+  return rs_conv_run<FFpBn254>(ctx, bn254_host(), d_rows, row_stride, nrows, n, m);
+}
+template <>
+int launch_rs<FFp128>(lf_ctx* ctx, fpw<4>* d_rows, size_t row_stride, size_t nrows, size_t batch_stride,
+                      size_t nbatch, size_t n, size_t m) {
+  if (nbatch != 1) return fail(LF_ERR_UNSUPPORTED, "rs: batches over this field are not built");
+  return rs_conv_run<FFp128>(ctx, fp128_host(), d_rows, row_stride, nrows, n, m);
+}
+template <>
+int launch_rs<FFpGold>(lf_ctx* ctx, fpw<2>* d_rows, size_t row_stride, size_t nrows, size_t batch_stride,
+                       size_t nbatch, size_t n, size_t m) {
+  if (nbatch != 1) return fail(LF_ERR_UNSUPPORTED, "rs: batches over this field are not built");
+  return rs_conv_run<FFpGold>(ctx, gold_host(), d_rows, row_stride, nrows, n, m);
 }
 
 template <class F>
@@ -561,6 +834,9 @@ int lf_ctx_create(int device, void* stream, lf_ctx** out) {
   LF_CUDA(cudaMemcpy(c->d_tw, h.tw.data(), h.tw.size() * sizeof(gf128), cudaMemcpyHostToDevice));
   LF_CUDA(cudaMemcpyToSymbol(c_gf, &h.consts, sizeof(GfConsts)));
   LF_CUDA(cudaMemcpyToSymbol(c_p256, &p256_host().C, sizeof(FpConsts<8>)));
+  LF_CUDA(cudaMemcpyToSymbol(c_bn254, &bn254_host().C, sizeof(FpConsts<8>)));
+  LF_CUDA(cudaMemcpyToSymbol(c_fp128, &fp128_host().C, sizeof(FpConsts<4>)));
+  LF_CUDA(cudaMemcpyToSymbol(c_gold, &gold_host().C, sizeof(FpConsts<2>)));
   *out = c.release();
   return 0;
 }
@@ -570,6 +846,14 @@ void lf_ctx_destroy(lf_ctx* ctx) {
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   for (auto& kv : ctx->rs_plans) cudaFree(kv.second.d_steps);
+  for (auto& kv : ctx->fft_tw) cudaFree(kv.second);
+  for (auto& kv : ctx->rs_conv) {
+    auto* t = (RsConvTables*)kv.second;
+    cudaFree(t->d_yh);
+    cudaFree(t->d_lead);
+    cudaFree(t->d_binom);
+    delete t;
+  }
   for (auto& kv : ctx->rs_fp) {
     cudaFree(kv.second.d_inv);
     cudaFree(kv.second.d_lead);
@@ -715,6 +999,15 @@ extern "C" {
   switch (field_id) {                                                          \
     case LF_FIELD_GF2_128: { typedef FGf128 F; return CALL; }                  \
     case LF_FIELD_P256: { typedef FFp256 F; return CALL; }                     \
+    case LF_FIELD_BN254: { typedef FFpBn254 F; return CALL; }                  \
+    case LF_FIELD_FP128: { typedef FFp128 F; return CALL; }                    \
+    case LF_FIELD_GOLDILOCKS: { typedef FFpGold F; return CALL; }              \
+    default: return fail(LF_ERR_UNSUPPORTED, "field not built yet");           \
+  }
+#define LF_DISPATCH_ZK_FIELD(field_id, CALL)                                   \
+  switch (field_id) {                                                          \
+    case LF_FIELD_GF2_128: { typedef FGf128 F; return CALL; }                  \
+    case LF_FIELD_P256: { typedef FFp256 F; return CALL; }                     \
     default: return fail(LF_ERR_UNSUPPORTED, "field not built yet");           \
   }
 
@@ -747,7 +1040,105 @@ int lf_merkle_commit(lf_ctx* ctx, int field_id, size_t nrow, size_t block_enc, s
   if (!ctx || !tableau || !nonces || !root_out) return fail(LF_ERR_ARG, "lf_merkle_commit: null argument");
   if (block_enc <= dblock || nrow == 0) return fail(LF_ERR_ARG, "merkle: need block_enc > dblock, nrow > 0");
   LF_CUDA(cudaSetDevice(ctx->device));
-  LF_DISPATCH_FIELD(field_id, merkle_commit_t<F>(ctx, nrow, block_enc, dblock, tableau, nonces, root_out, nodes_out));
+  LF_DISPATCH_ZK_FIELD(field_id, merkle_commit_t<F>(ctx, nrow, block_enc, dblock, tableau, nonces, root_out, nodes_out));
+}
+
+}  // extern "C"
+
+namespace {
+template <class F, class H>
+int fft_scalar_t(lf_ctx* ctx, const H& Hf, void* elts, size_t n, uint32_t logn, int forward, int reps, double* ms) {
+  typedef typename F::Elt Elt;
+  Elt* d = nullptr;
+  Elt* d_tw;
+  int rc = fft_twiddles<H, F::W>(ctx, F::kFieldId, Hf, logn, &d_tw);
+  if (rc) return rc;
+  if (elts) {
+    rc = upload_elts<F>(ctx, elts, n, &d);
+  } else {
+    LF_CUDA(cudaMalloc(&d, n * sizeof(Elt)));
+    LF_CUDA(cudaMemsetAsync(d, 0x5a, n * sizeof(Elt), ctx->stream));  // timing only: any limbs do
+  }
+  if (rc) return rc;
+  cudaEvent_t e0, e1;
+  LF_CUDA(cudaEventCreate(&e0));
+  LF_CUDA(cudaEventCreate(&e1));
+  LF_CUDA(cudaEventRecord(e0, ctx->stream));
+  for (int r = 0; r < reps && !rc; ++r) rc = fft_run<AlgF<F>>(ctx, d, 0, 1, logn, d_tw, forward != 0, false, true);
+  LF_CUDA(cudaEventRecord(e1, ctx->stream));
+  LF_CUDA(cudaEventSynchronize(e1));
+  if (ms) {
+    float t;
+    LF_CUDA(cudaEventElapsedTime(&t, e0, e1));
+    *ms = t / reps;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  if (!rc && elts) rc = download_elts<F>(ctx, d, n, elts);
+  cudaFree(d);
+  return rc;
+}
+int fft_p256_t(lf_ctx* ctx, void* elts, size_t n, uint32_t logn, int forward, int reps, double* ms) {
+  typedef FFp256 F;
+  fpw<8>* d = nullptr;
+  Cx<F>* d_tw;
+  int rc = fft_twiddles_p256(ctx, logn, &d_tw);
+  if (rc) return rc;
+  if (elts) {
+    rc = upload_elts<F>(ctx, elts, 2 * n, &d);  // (re, im) pairs
+  } else {
+    LF_CUDA(cudaMalloc(&d, 2 * n * sizeof(fpw<8>)));
+    LF_CUDA(cudaMemsetAsync(d, 0x5a, 2 * n * sizeof(fpw<8>), ctx->stream));
+  }
+  if (rc) return rc;
+  cudaEvent_t e0, e1;
+  LF_CUDA(cudaEventCreate(&e0));
+  LF_CUDA(cudaEventCreate(&e1));
+  LF_CUDA(cudaEventRecord(e0, ctx->stream));
+  for (int r = 0; r < reps && !rc; ++r)
+    rc = fft_run<AlgCx<F>>(ctx, (Cx<F>*)d, 0, 1, logn, d_tw, forward != 0, false, true);
+  LF_CUDA(cudaEventRecord(e1, ctx->stream));
+  LF_CUDA(cudaEventSynchronize(e1));
+  if (ms) {
+    float t;
+    LF_CUDA(cudaEventElapsedTime(&t, e0, e1));
+    *ms = t / reps;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  if (!rc && elts) rc = download_elts<F>(ctx, d, 2 * n, elts);
+  cudaFree(d);
+  return rc;
+}
+int fft_dispatch(lf_ctx* ctx, int field_id, void* elts, size_t n, int forward, int reps, double* ms) {
+  if (n == 0 || (n & (n - 1))) return fail(LF_ERR_ARG, "fft: n must be a power of two");
+  uint32_t logn = 0;
+  while (((size_t)1 << logn) < n) ++logn;
+  if (logn > 26) return fail(LF_ERR_ARG, "fft: n too large");
+  switch (field_id) {
+    case LF_FIELD_BN254: return fft_scalar_t<FFpBn254>(ctx, bn254_host(), elts, n, logn, forward, reps, ms);
+    case LF_FIELD_FP128: return fft_scalar_t<FFp128>(ctx, fp128_host(), elts, n, logn, forward, reps, ms);
+    case LF_FIELD_GOLDILOCKS: return fft_scalar_t<FFpGold>(ctx, gold_host(), elts, n, logn, forward, reps, ms);
+    case LF_FIELD_P256: return fft_p256_t(ctx, elts, n, logn, forward, reps, ms);
+    default: return fail(LF_ERR_UNSUPPORTED, "fft: field has no FFT here (GF(2^128) uses the LCH14 transform inside RS)");
+  }
+}
+}  // namespace
+
+extern "C" {
+
+int lf_fft(lf_ctx* ctx, int field_id, void* elts, size_t n, int forward) {
+  if (!ctx || !elts) return fail(LF_ERR_ARG, "lf_fft: null argument");
+  LF_CUDA(cudaSetDevice(ctx->device));
+  return fft_dispatch(ctx, field_id, elts, n, forward, 1, nullptr);
+}
+
+int lf_fft_time(lf_ctx* ctx, int field_id, size_t n, int reps, double* ms_per_fft) {
+  if (!ctx || !ms_per_fft || reps <= 0) return fail(LF_ERR_ARG, "lf_fft_time: bad argument");
+  LF_CUDA(cudaSetDevice(ctx->device));
+  int rc = fft_dispatch(ctx, field_id, nullptr, n, 0, 1, nullptr);  // warm-up (tables, attributes)
+  if (rc) return rc;
+  return fft_dispatch(ctx, field_id, nullptr, n, 0, reps, ms_per_fft);
 }
 
 int lf_microbench(lf_ctx* ctx, int what, double* gops) {

@@ -1,0 +1,84 @@
+"""GPU parity of the stand-alone prime-field transforms (BASELINE config 1):
+FFT<Field>::fftb / fftf and ReedSolomon::interpolate over the reference's
+benchmark fields, against the oracle."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+MOD = {
+    100: 21888242871839275222246405745257275088548364400416034343698204186575808495617,
+    101: 2**128 - 2**108 + 1,
+    102: 2**64 - 2**32 + 1,
+    1: 0xffffffff00000001000000000000000000000000ffffffffffffffffffffffff,
+}
+KB = {100: 32, 101: 16, 102: 8, 1: 32}
+
+
+def rand_elts(rs, fid, n):
+    p, kb = MOD[fid], KB[fid]
+    v = [int.from_bytes(rs.bytes(kb + 8), "little") % p for _ in range(n)]
+    return np.frombuffer(b"".join(x.to_bytes(kb, "little") for x in v), np.uint8).reshape(n, kb).copy()
+
+
+@pytest.mark.parametrize("fid", [100, 101, 102, 1])
+def test_field_mul_matches_oracle(ctx, oracle, fid):
+    rs = np.random.default_rng(fid)
+    a, b = rand_elts(rs, fid, 3000), rand_elts(rs, fid, 3000)
+    a[0] = 0
+    a[1] = np.frombuffer((MOD[fid] - 1).to_bytes(KB[fid], "little"), np.uint8)
+    b[1] = a[1]
+    assert (ctx.elt_mul(fid, a, b) == oracle.elt_op(fid, "mul", a, b)).all()
+
+
+@pytest.mark.parametrize("fid", [100, 101, 102])
+@pytest.mark.parametrize("n", [1, 2, 8, 1024, 4096, 65536])
+def test_fft_matches_oracle(ctx, oracle, fid, n):
+    rs = np.random.default_rng(fid * 7 + n)
+    a = rand_elts(rs, fid, n)
+    for fwd in (False, True):
+        assert (ctx.fft(fid, a, n, fwd) == oracle.fft(fid, a, n, fwd)).all(), (fid, n, fwd)
+
+
+@pytest.mark.parametrize("n", [2, 64, 2048, 65536])
+def test_fft_fp2_p256_matches_oracle(ctx, oracle, n):
+    rs = np.random.default_rng(n)
+    a = rand_elts(rs, 1, 2 * n)
+    for fwd in (False, True):
+        assert (ctx.fft(1, a, n, fwd) == oracle.fft(1, a, n, fwd)).all(), (n, fwd)
+
+
+@pytest.mark.parametrize("fid", [100, 101, 102])
+def test_fft_roundtrip_and_linearity_at_scale(ctx, fid):
+    """fftf(fftb(x)) = n x and linearity at n = 2^18 (no oracle needed)"""
+    n = 1 << 18
+    rs = np.random.default_rng(fid)
+    p, kb = MOD[fid], KB[fid]
+    x = rand_elts(rs, fid, n)
+    y = ctx.fft(fid, ctx.fft(fid, x, n, False), n, True)
+    # n * x mod p on a sample of positions
+    for i in list(range(0, n, n // 16)) + [n - 1]:
+        xi = int.from_bytes(x[i].tobytes(), "little")
+        assert int.from_bytes(y[i].tobytes(), "little") == (xi * n) % p
+
+
+@pytest.mark.parametrize("fid", [100, 101, 102])
+@pytest.mark.parametrize("n,m", [(455, 4096), (5, 16), (1, 3), (300, 301), (4096, 16384)])
+def test_rs_matches_oracle(ctx, oracle, fid, n, m):
+    import longfellow_zk_b200 as lf
+    rs = np.random.default_rng(fid + n + m)
+    rows = rand_elts(rs, fid, 2 * m).reshape(2, m, KB[fid])
+    got = lf.ReedSolomonFactory(ctx, fid).make(n, m).interpolate(rows)
+    assert (got == oracle.rs_interpolate(fid, n, m, rows)).all()
+
+
+def test_fft_timing_reports(ctx):
+    import json
+    import os
+    res = {}
+    for name, fid in [("bn254_fp4", 100), ("fp128", 101), ("goldilocks", 102), ("fp2_p256", 1)]:
+        res[f"fft_{name}_65536_ms"] = ctx.fft_time_ms(fid, 65536, reps=20)
+    print("FFT_TIMING", json.dumps(res))
+    os.makedirs("gpurun_out", exist_ok=True)
+    json.dump(res, open("gpurun_out/fft_timing.json", "w"))
+    assert all(v > 0 for v in res.values())
