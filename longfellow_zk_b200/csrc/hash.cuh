@@ -118,6 +118,29 @@ struct Sha256 {
   uint32_t buf[16];  // big-endian words being filled
   uint64_t len;      // bytes absorbed
 
+  // One compression of the buffered block.  h and buf are copied to locals so
+  // that the fully unrolled rounds run out of registers even when *this lives
+  // in shared or local memory (the transcript thread's state).
+  LF_HD void compress_block() {
+    uint32_t hh[8], ww[16];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) hh[i] = h[i];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) ww[i] = buf[i];
+    sha256_compress(hh, ww);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) h[i] = hh[i];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) buf[i] = 0;
+  }
+  LF_HD void compress_zero_block() {
+    uint32_t hh[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) hh[i] = h[i];
+    sha256_compress_zero(hh);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) h[i] = hh[i];
+  }
   LF_HD void init() {
     sha256_iv(h);
     len = 0;
@@ -129,11 +152,7 @@ struct Sha256 {
     uint32_t wi = pos >> 2, sh = 24 - 8 * (pos & 3);
     buf[wi] |= (uint32_t)b << sh;
     ++len;
-    if (pos == 63) {
-      sha256_compress(h, buf);
-#pragma unroll
-      for (int i = 0; i < 16; ++i) buf[i] = 0;
-    }
+    if (pos == 63) compress_block();
   }
   LF_HD void update(const uint8_t* p, uint32_t n) {
     for (uint32_t i = 0; i < n; ++i) put_byte(p[i]);
@@ -144,10 +163,17 @@ struct Sha256 {
       put_byte(0);
       --n;
     }
-    while (n >= 64) {
-      sha256_compress_zero(h);
-      len += 64;
-      n -= 64;
+    if (n >= 64) {
+      uint32_t hh[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) hh[i] = h[i];
+      while (n >= 64) {
+        sha256_compress_zero(hh);
+        len += 64;
+        n -= 64;
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) h[i] = hh[i];
     }
     while (n > 0) {
       put_byte(0);
@@ -162,19 +188,13 @@ struct Sha256 {
     len += 4;
     if (k == 0) {
       buf[wi] = x;
-      if (wi == 15) {
-        sha256_compress(h, buf);
-#pragma unroll
-        for (int i = 0; i < 16; ++i) buf[i] = 0;
-      }
+      if (wi == 15) compress_block();
     } else {
       const uint32_t sh = 8 * k;
       buf[wi] |= x >> sh;
       const uint32_t rest = x << (32 - sh);
       if (wi == 15) {
-        sha256_compress(h, buf);
-#pragma unroll
-        for (int i = 1; i < 16; ++i) buf[i] = 0;
+        compress_block();
         buf[0] = rest;
       } else {
         buf[wi + 1] |= rest;
@@ -231,18 +251,28 @@ struct Sha256 {
 static __constant__ uint8_t kAesSbox_dev[256] = {LF_AES_SBOX};
 #endif
 static const uint8_t kAesSbox_host[256] = {LF_AES_SBOX};
-LF_HD __forceinline__ uint32_t aes_sbox(uint32_t i) {
+// The S-box is read through a pointer: kernels stage the 256 bytes in shared
+// memory (aes_stage_sbox), where a dependent byte lookup costs ~30 cycles
+// instead of a divergent constant-bank access; host code uses the static table.
+LF_HD __forceinline__ const uint8_t* aes_default_sbox() {
 #ifdef __CUDA_ARCH__
-  return kAesSbox_dev[i];
+  return kAesSbox_dev;
 #else
-  return kAesSbox_host[i];
+  return kAesSbox_host;
 #endif
 }
+#ifdef __CUDACC__
+// call from all threads of a CTA; sb = __shared__ uint8_t[256]
+__device__ __forceinline__ void aes_stage_sbox(uint8_t* sb) {
+  for (uint32_t i = threadIdx.x; i < 256; i += blockDim.x) sb[i] = kAesSbox_dev[i];
+  __syncthreads();
+}
+#endif
 
 // AES works on columns held as little-endian words: byte r of word c = state[r][c].
-LF_HD __forceinline__ uint32_t aes_subword(uint32_t x) {
-  return aes_sbox(x & 0xff) | (aes_sbox((x >> 8) & 0xff) << 8) |
-         (aes_sbox((x >> 16) & 0xff) << 16) | (aes_sbox(x >> 24) << 24);
+LF_HD __forceinline__ uint32_t aes_subword(const uint8_t* sb, uint32_t x) {
+  return (uint32_t)sb[x & 0xff] | ((uint32_t)sb[(x >> 8) & 0xff] << 8) |
+         ((uint32_t)sb[(x >> 16) & 0xff] << 16) | ((uint32_t)sb[x >> 24] << 24);
 }
 LF_HD __forceinline__ uint32_t aes_xtime4(uint32_t x) {  // xtime on 4 packed bytes
   return ((x & 0x7f7f7f7fu) << 1) ^ (((x >> 7) & 0x01010101u) * 0x1bu);
@@ -251,33 +281,33 @@ LF_HD __forceinline__ uint32_t aes_xtime4(uint32_t x) {  // xtime on 4 packed by
 struct Aes256 {
   uint32_t rk[60];
   // key: 8 words, byte i of the key = byte (i&3) of word i>>2
-  LF_HD void init(const uint32_t key[8]) {
+  LF_HD void init(const uint32_t key[8], const uint8_t* sb) {
 #pragma unroll
     for (int i = 0; i < 8; ++i) rk[i] = key[i];
     uint32_t rcon = 1;
     for (int i = 8; i < 60; ++i) {
       uint32_t t = rk[i - 1];
       if ((i & 7) == 0) {
-        t = aes_subword((t >> 8) | (t << 24)) ^ rcon;  // RotWord on LE-packed bytes
+        t = aes_subword(sb, (t >> 8) | (t << 24)) ^ rcon;  // RotWord on LE-packed bytes
         rcon = (rcon << 1) ^ ((rcon >> 7) * 0x11bu);
       } else if ((i & 7) == 4) {
-        t = aes_subword(t);
+        t = aes_subword(sb, t);
       }
       rk[i] = rk[i - 8] ^ t;
     }
   }
-  LF_HD void encrypt(const uint32_t in[4], uint32_t out[4]) const {
+  LF_HD void encrypt(const uint32_t in[4], uint32_t out[4], const uint8_t* sb) const {
     uint32_t s0 = in[0] ^ rk[0], s1 = in[1] ^ rk[1], s2 = in[2] ^ rk[2], s3 = in[3] ^ rk[3];
     for (int r = 1; r <= 14; ++r) {
       // SubBytes + ShiftRows: new column c takes row k from column (c+k)&3
-      uint32_t t0 = aes_sbox(s0 & 0xff) | (aes_sbox((s1 >> 8) & 0xff) << 8) |
-                    (aes_sbox((s2 >> 16) & 0xff) << 16) | (aes_sbox(s3 >> 24) << 24);
-      uint32_t t1 = aes_sbox(s1 & 0xff) | (aes_sbox((s2 >> 8) & 0xff) << 8) |
-                    (aes_sbox((s3 >> 16) & 0xff) << 16) | (aes_sbox(s0 >> 24) << 24);
-      uint32_t t2 = aes_sbox(s2 & 0xff) | (aes_sbox((s3 >> 8) & 0xff) << 8) |
-                    (aes_sbox((s0 >> 16) & 0xff) << 16) | (aes_sbox(s1 >> 24) << 24);
-      uint32_t t3 = aes_sbox(s3 & 0xff) | (aes_sbox((s0 >> 8) & 0xff) << 8) |
-                    (aes_sbox((s1 >> 16) & 0xff) << 16) | (aes_sbox(s2 >> 24) << 24);
+      uint32_t t0 = (uint32_t)sb[s0 & 0xff] | ((uint32_t)sb[(s1 >> 8) & 0xff] << 8) |
+                    ((uint32_t)sb[(s2 >> 16) & 0xff] << 16) | ((uint32_t)sb[s3 >> 24] << 24);
+      uint32_t t1 = (uint32_t)sb[s1 & 0xff] | ((uint32_t)sb[(s2 >> 8) & 0xff] << 8) |
+                    ((uint32_t)sb[(s3 >> 16) & 0xff] << 16) | ((uint32_t)sb[s0 >> 24] << 24);
+      uint32_t t2 = (uint32_t)sb[s2 & 0xff] | ((uint32_t)sb[(s3 >> 8) & 0xff] << 8) |
+                    ((uint32_t)sb[(s0 >> 16) & 0xff] << 16) | ((uint32_t)sb[s1 >> 24] << 24);
+      uint32_t t3 = (uint32_t)sb[s3 & 0xff] | ((uint32_t)sb[(s0 >> 8) & 0xff] << 8) |
+                    ((uint32_t)sb[(s1 >> 16) & 0xff] << 16) | ((uint32_t)sb[s2 >> 24] << 24);
       if (r < 14) {
         // MixColumns on packed columns: out = 2*t ^ 3*rot8(t) ^ rot16(t) ^ rot24(t)
 #define LF_MIX(t)                                                      \
@@ -307,6 +337,7 @@ struct Transcript {
   uint32_t rdptr;     // byte read pointer into saved[]
   uint32_t have_prf;
   uint32_t saved[4];  // LE-packed bytes of the current PRF block
+  const uint8_t* sbox;  // AES S-box to use (re-pointed by every kernel after loading the state)
 
   LF_HD void raw_byte(uint8_t b) {
     have_prf = 0;
@@ -322,6 +353,7 @@ struct Transcript {
     have_prf = 0;
     nblock = 0;
     rdptr = 16;
+    sbox = aes_default_sbox();
     write_bytes(seed, n);
   }
   // transcript.h:116-121
@@ -361,7 +393,7 @@ struct Transcript {
       sha.snapshot(d);
 #pragma unroll
       for (int i = 0; i < 8; ++i) key[i] = bswap32(d[i]);  // digest bytes, LE-packed
-      prf.init(key);
+      prf.init(key, sbox);
       have_prf = 1;
       nblock = 0;
       rdptr = 16;
@@ -369,7 +401,7 @@ struct Transcript {
     if (rdptr == 16) {
       uint32_t in[4] = {(uint32_t)nblock, (uint32_t)(nblock >> 32), 0, 0};
       ++nblock;
-      prf.encrypt(in, saved);
+      prf.encrypt(in, saved, sbox);
       rdptr = 0;
     }
     uint8_t b = (uint8_t)(saved[rdptr >> 2] >> (8 * (rdptr & 3)));

@@ -161,10 +161,13 @@ k_zk_layout(ZkDims d, ZkBufs<typename F::Elt> b, const uint32_t* __restrict__ ro
 template <class F>
 __global__ void k_zk_transcript_init(ZkDims d, ZkBufs<typename F::Elt> b, const uint8_t* __restrict__ tinit,
                                      const uint8_t* __restrict__ circuit_id, size_t nproofs) {
+  __shared__ uint8_t s_sbox[256];
+  aes_stage_sbox(s_sbox);
   size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= nproofs) return;
   Transcript ts;
   ts.init(tinit, d.tinit_len);
+  ts.sbox = s_sbox;
   // ligero_transcript.h:31-34 write_commitment: root digest is node 1
   const uint32_t* root = b.nodes + p * (size_t)(2 * d.block_ext * 8) + 8;
   uint32_t rw[8];
@@ -253,6 +256,7 @@ struct ScShared {
   typename F::Elt r, alpha, beta, sum, wc[2];
   typename F::Elt* hp;  // [blockDim.x] head partials of the segmented sums
   uint32_t* hr;         // [blockDim.x] their segment ids
+  uint8_t sbox[256];    // AES S-box staged in shared memory
   int fail;
 };
 
@@ -360,6 +364,7 @@ __device__ __noinline__ void sc_round_serial(ScShared<F>* sh, typename F::Elt a0
 template <class F>
 __device__ __noinline__ void sc_begin(ScShared<F>* sh, const Transcript* src) {
   sh->ts = *src;
+  sh->ts.sbox = sh->sbox;
   sh->ts.have_prf = 0;  // Transcript::clone() carries only the hash (transcript.h:86)
   // begin_circuit: Q[40] then G[40] (transcript_sumcheck.h:49-52)
   for (int i = 0; i < 40; ++i) (void)F::ts_elt(&sh->ts);
@@ -424,6 +429,7 @@ __device__ __forceinline__ void sumcheck_body(const ZkDims& d, const ZkBufs<type
   const Elt* wit = b.wit + p * d.nw;
   Elt* hbs = b.hb + p * d.nhb;
 
+  aes_stage_sbox(sh.sbox);
   if (tid == 0) sc_begin<F>(&sh, reinterpret_cast<const Transcript*>(b.ts + p * sizeof(Transcript)));
   __syncthreads();
 
@@ -613,10 +619,13 @@ k_zk_sumcheck_lat(ZkDims d, ZkBufs<typename F::Elt> b, const uint32_t* __restric
 // ----------------------------------------------------------------------------
 template <class F>
 __global__ void k_lig_challenges(ZkDims d, ZkBufs<typename F::Elt> b, size_t nproofs) {
+  __shared__ uint8_t s_sbox[256];
+  aes_stage_sbox(s_sbox);
   size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= nproofs || b.status[p] != 0) return;
   Transcript* gts = reinterpret_cast<Transcript*>(b.ts + p * sizeof(Transcript));
   Transcript ts = *gts;
+  ts.sbox = s_sbox;
   typename F::Elt* chal = b.chal + p * (size_t)(1 + d.nchal);
   chal[0] = F::ts_elt(&ts);
   uint32_t hashA[8] = {0xefbeaddeu, 0, 0, 0, 0, 0, 0, 0};  // bytes de ad be ef 00 ...
@@ -912,6 +921,8 @@ k_lig_finish(ZkDims d, ZkBufs<typename F::Elt> b, const LayerDesc* __restrict__ 
   uint32_t* eoff = reinterpret_cast<uint32_t*>(flag + ((total + 3) & ~3u));
   uint32_t* path_idx = eoff + total;
   __shared__ uint32_t s_npath, s_req_end;
+  __shared__ uint8_t s_sbox[256];
+  for (uint32_t i = threadIdx.x; i < 256; i += blockDim.x) s_sbox[i] = kAesSbox_dev[i];
 
   for (uint32_t i = tid; i < n; i += nth) perm[i] = i;
   for (uint32_t i = tid; i < 2 * n; i += nth) mark[i] = 0;
@@ -919,6 +930,7 @@ k_lig_finish(ZkDims d, ZkBufs<typename F::Elt> b, const LayerDesc* __restrict__ 
   if (tid == 0) {
     Transcript* gts = reinterpret_cast<Transcript*>(b.ts + p * sizeof(Transcript));
     Transcript ts = *gts;
+    ts.sbox = s_sbox;
     const uint32_t lens[4] = {d.block, d.dblock, d.r, d.dblock - d.block};
     const uint32_t offs[4] = {0, d.block, d.block + d.dblock, d.block + d.dblock + d.block};
     for (int a = 0; a < 4; ++a) {

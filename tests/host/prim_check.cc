@@ -88,11 +88,11 @@ int main(int argc, char** argv) {
     Aes256 a;
     uint32_t key[8];
     memcpy(key, in.data(), 32);
-    a.init(key);
+    a.init(key, aes_default_sbox());
     for (size_t i = 32; i + 16 <= in.size(); i += 16) {
       uint32_t x[4], y[4];
       memcpy(x, &in[i], 16);
-      a.encrypt(x, y);
+      a.encrypt(x, y, aes_default_sbox());
       fwrite(y, 1, 16, stdout);
     }
   } else if (!strcmp(argv[1], "transcript")) {
