@@ -258,6 +258,7 @@ struct ScShared {
   uint32_t* hr;         // [blockDim.x] their segment ids
   uint8_t sbox[256];    // AES S-box staged in shared memory
   int fail;
+  long long prof[8];    // LF_PROF: cycles of thread 0 per phase
 };
 
 template <class F>
@@ -317,9 +318,31 @@ __device__ __forceinline__ void seg_sum(ScShared<F>* sh, uint32_t n, const uint3
     }
   }
   __syncthreads();
+  // Suffix sums of the head partials inside each warp (runs of equal segment id
+  // are contiguous in thread order), so that the owner of a long segment adds
+  // one value per warp instead of one per thread.
+  {
+    Elt v = sh->hp[tid];
+    const uint32_t sg = sh->hr[tid], lane = tid & 31;
+    if (sg == kNone) v = F::zero();
+#pragma unroll
+    for (int dlt = 1; dlt < 32; dlt <<= 1) {
+      Elt v2;
+#pragma unroll
+      for (int k = 0; k < F::kWords; ++k) v2.w[k] = __shfl_down_sync(0xffffffffu, v.w[k], dlt);
+      uint32_t sg2 = __shfl_down_sync(0xffffffffu, sg, dlt);
+      if (lane + dlt < 32 && sg != kNone && sg2 == sg) v = F::add(v, v2);
+    }
+    sh->hp[tid] = v;  // each thread rewrites only its own slot
+  }
+  __syncthreads();
   if (own_last != kNone) {
     Elt v = out[own_last];
-    for (uint32_t t = tid + 1; t < nth && sh->hr[t] == own_last; ++t) v = F::add(v, sh->hp[t]);
+    uint32_t t = tid + 1;
+    while (t < nth && sh->hr[t] == own_last) {
+      v = F::add(v, sh->hp[t]);  // sum of this warp's part of the run starting at t
+      t = (t | 31u) + 1;         // first thread of the next warp
+    }
     out[own_last] = v;
   }
   __syncthreads();
@@ -430,6 +453,10 @@ __device__ __forceinline__ void sumcheck_body(const ZkDims& d, const ZkBufs<type
   Elt* hbs = b.hb + p * d.nhb;
 
   aes_stage_sbox(sh.sbox);
+  if (tid == 0) {
+    for (int i = 0; i < 8; ++i) sh.prof[i] = 0;
+    sh.prof[3] = clock64();
+  }
   if (tid == 0) sc_begin<F>(&sh, reinterpret_cast<const Transcript*>(b.ts + p * sizeof(Transcript)));
   __syncthreads();
 
@@ -508,6 +535,7 @@ __device__ __forceinline__ void sumcheck_body(const ZkDims& d, const ZkBufs<type
         }
       }
       __syncthreads();
+      long long tp0 = clock64();
       if (tid == 0) {
         Elt s0 = sh.red[0][0], s2 = sh.red[1][0];
         for (uint32_t k = 1; k < nth / 32; ++k) {
@@ -518,6 +546,8 @@ __device__ __forceinline__ void sumcheck_body(const ZkDims& d, const ZkBufs<type
         sc_round_serial<F>(&sh, s0, s2, pad + 4 * round + 2 * hand, sc + L.sc_off + 4 * round + hand,
                            sc + L.sc_off + 4 * round + 2 + hand, hbs + L.hb_off + t);
         sh.G[hand][round] = sh.r;
+        sh.prof[0] += clock64() - tp0;
+        sh.prof[1] += 1;
       }
       __syncthreads();
       const Elt r = sh.r;
@@ -560,6 +590,9 @@ __device__ __forceinline__ void sumcheck_body(const ZkDims& d, const ZkBufs<type
   if (tid == 0) {
     *reinterpret_cast<Transcript*>(b.ts + p * sizeof(Transcript)) = sh.ts;
     if (sh.fail) b.status[p] = -100;  // internal inconsistency: never expected
+    sh.prof[2] = clock64() - sh.prof[3];
+    long long* dbg = reinterpret_cast<long long*>(hqbuf);  // free after the last layer
+    for (int i = 0; i < 4; ++i) dbg[i] = sh.prof[i];
   }
 }
 

@@ -12,5 +12,10 @@ ctx = lf.Context(0)
 c = lf.Circuit(ctx, fid, circ)
 rng = np.stack([rng_bytes(1 + i, c.info["rng_bytes"]) for i in range(B)])
 W = np.repeat(np.frombuffer(wit, np.uint8)[None, :], B, axis=0)
-proofs, status = lf.ZkProver(c).prove_batch(W, rng)
+pr0 = lf.ZkProver(c)
+proofs, status = pr0.prove_batch(W, rng)
+dbg = pr0.debug_fetch(0, 99).view(np.int64)
+print('serial cycles', dbg[0], 'rounds', dbg[1], 'cycles/round', dbg[0] / max(dbg[1], 1), 'kernel cycles', dbg[2])
 print("ok", which, B, [len(p) for p in proofs][:4], status[:4])
+pr = lf.ZkProver(c)
+
