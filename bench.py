@@ -209,6 +209,7 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dist = None
     if world > 1:
+        os.environ.pop("NCCL_DEBUG", None)  # keep stdout to the one JSON line
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
