@@ -101,6 +101,8 @@ struct FGf128 {
     return e;
   }
   __device__ static __forceinline__ Elt evalpt(int i) { return c_gf.evalpt[i]; }
+  // a * poly_evaluation_point(2)  (= a * g)
+  __device__ static __forceinline__ Elt mul_x2(const Elt& a) { return gf_mul(a, c_gf.evalpt[2]); }
   __device__ static __forceinline__ Elt newton(int k, int i) { return c_gf.newton[k][i]; }
   __device__ static __forceinline__ Elt lag_id(int k, int i) { return c_gf.lag_id[k][i]; }
   // GF2_128::of_scalar for a 16-bit subfield index (gf2_128.h:151-160)
@@ -299,6 +301,8 @@ struct FFp {
     return from_wire(in);
   }
   __device__ static __forceinline__ Elt evalpt(int i) { return cst(T::C().evalpt[i]); }
+  // a * poly_evaluation_point(2)  (= a + a: the point is the integer 2, fp_generic.h:117-124)
+  __device__ static __forceinline__ Elt mul_x2(const Elt& a) { return add(a, a); }
   __device__ static __forceinline__ Elt newton(int k, int i) { return cst(T::C().newton[k][i]); }
   __device__ static __forceinline__ Elt lag_id(int k, int i) { return cst(T::C().lag_id[k][i]); }
   __device__ static __forceinline__ Elt of_sub16(uint32_t) { return zero(); }        // never used

@@ -276,9 +276,12 @@ __device__ __forceinline__ typename F::Elt warp_sum(typename F::Elt s) {
 // out[seg] = sum over the entries e of that segment of term(e); seg[] is
 // non-decreasing over e in [0, n).  Segments without entries are not touched.
 // Contains two __syncthreads(); all threads of the CTA must call it.
-template <class F, class Term>
+// fetch(e) loads the operands of entry e; accum(acc, ops) adds the entry's term.
+// (Issuing the loads one entry ahead was tried and measured slower: the kernel
+// is bound by the multiply pipes and barriers, not by load latency.)
+template <class F, class Fetch, class Accum>
 __device__ __forceinline__ void seg_sum(ScShared<F>* sh, uint32_t n, const uint32_t* __restrict__ seg,
-                                        typename F::Elt* __restrict__ out, Term term) {
+                                        typename F::Elt* __restrict__ out, Fetch fetch, Accum accum) {
   typedef typename F::Elt Elt;
   typedef typename F::Acc Acc;
   const uint32_t tid = threadIdx.x, nth = blockDim.x;
@@ -293,7 +296,8 @@ __device__ __forceinline__ void seg_sum(ScShared<F>* sh, uint32_t n, const uint3
     Acc acc;
     F::acc_zero(acc);
     for (uint32_t e = e0; e < e1; ++e) {
-      uint32_t sg = seg[e];
+      const uint32_t sg = seg[e];
+      const auto cur_ops = fetch(e);
       if (sg != cur) {
         Elt v = F::reduce(acc);
         if (head) {
@@ -306,7 +310,7 @@ __device__ __forceinline__ void seg_sum(ScShared<F>* sh, uint32_t n, const uint3
         cur = sg;
         F::acc_zero(acc);
       }
-      term(acc, e);
+      accum(acc, cur_ops);
     }
     Elt v = F::reduce(acc);
     if (head) {
@@ -356,31 +360,29 @@ __device__ __noinline__ void sc_round_serial(ScShared<F>* sh, typename F::Elt a0
                                             typename F::Elt* proof0, typename F::Elt* proof2,
                                             typename F::Elt* hb_out) {
   typedef typename F::Elt Elt;
-  // coefficients (eq0 == 1 because logc == 0)
+  // coefficients of p(t) = c0 + c1 t + c2 t^2 (eq0 == 1 because logc == 0)
   Elt c0 = a0, c2 = a2;
   Elt c1 = F::sub(F::sub(F::sub(sh->sum, c0), c0), c2);
-  Elt ev[3];
-  ev[0] = c0;                                       // p(0)
-  ev[1] = F::add(F::add(c0, c1), c2);               // p(1)
-  Elt x2 = F::evalpt(2);
-  ev[2] = F::add(F::mul(F::add(F::mul(c2, x2), c1), x2), c0);  // p(evalpt 2)
-  Elt p0 = F::sub(ev[0], pad[0]), p2 = F::sub(ev[2], pad[1]);
+  // p(0) and p(x2): Horner in the evaluation point (prover_layers.h:395-399)
+  long long q0 = clock64();
+  Elt ev2 = F::add(F::mul_x2(F::add(F::mul_x2(c2), c1)), c0);
+  Elt p0 = F::sub(c0, pad[0]), p2 = F::sub(ev2, pad[1]);
   *proof0 = p0;
   *proof2 = p2;
+  long long q1 = clock64();
   ts_write_elt<F>(&sh->ts, p0);
   ts_write_elt<F>(&sh->ts, p2);
+  long long q2 = clock64();
   Elt rnd = F::ts_elt(&sh->ts);
+  long long q3 = clock64();
+  sh->prof[4] += q1 - q0;
+  sh->prof[5] += q2 - q1;
+  sh->prof[6] += q3 - q2;
   *hb_out = rnd;
-  // sum = evals.eval_lagrange(rnd)
-  Elt t[3] = {ev[0], ev[1], ev[2]};
-#pragma unroll
-  for (int i = 1; i < 3; ++i)
-#pragma unroll
-    for (int k = 2; k >= i; --k) t[k] = F::mul(F::sub(t[k], t[k - 1]), F::newton(k, i));
-  Elt e = t[2];
-  e = F::add(F::mul(e, F::sub(rnd, F::evalpt(1))), t[1]);
-  e = F::add(F::mul(e, F::sub(rnd, F::evalpt(0))), t[0]);
-  sh->sum = e;
+  // new claim = p(rnd).  The reference evaluates the Lagrange form through
+  // Newton differences (poly.h:59-98); it is the same polynomial, so Horner on
+  // the monomial coefficients gives the same field element with two multiplies.
+  sh->sum = F::add(F::mul(F::add(F::mul(c2, rnd), c1), rnd), c0);
   sh->r = rnd;
 }
 
@@ -486,12 +488,26 @@ __device__ __forceinline__ void sumcheck_body(const ZkDims& d, const ZkBufs<type
     {
       const uint32_t *tg = arena + L.bg_g, *tv = arena + L.bg_vi;
       const Elt beta = sh.beta;
-      seg_sum<F>(&sh, L.nterms, arena + L.bg_seg, hqbuf, [&](Acc& acc, uint32_t t) {
-        uint32_t g = tg[t], v = tv[t];
-        Elt dot = F::add(E0[g], E1[g]);
-        if (v & kViOne) F::acc_add_elt(acc, dot);
-        else F::mac(acc, (v & kViZero) ? beta : consts[v & kViMask], dot);
-      });
+      struct BgOps {
+        Elt e0, e1, c;
+        uint32_t v;
+      };
+      seg_sum<F>(
+          &sh, L.nterms, arena + L.bg_seg, hqbuf,
+          [&](uint32_t t) {
+            uint32_t g = tg[t], v = tv[t];
+            BgOps o;
+            o.e0 = E0[g];
+            o.e1 = E1[g];
+            o.v = v;
+            o.c = (v & (kViOne | kViZero)) ? beta : consts[v & kViMask];
+            return o;
+          },
+          [&](Acc& acc, const BgOps& o) {
+            Elt dot = F::add(o.e0, o.e1);
+            if (o.v & kViOne) F::acc_add_elt(acc, dot);
+            else F::mac(acc, o.c, dot);
+          });
     }
 
     const Elt *wcur0 = wl + L.w_off, *wcur1 = wl + L.w_off;  // current array of each hand
@@ -511,8 +527,18 @@ __device__ __forceinline__ void sumcheck_body(const ZkDims& d, const ZkBufs<type
         for (uint32_t i = tid; i < S.n0; i += nth)
           if (roff[i] == roff[i + 1]) QW[i] = F::zero();
         const uint32_t *rc = arena + S.row_c, *rp = arena + S.row_p1;
-        seg_sum<F>(&sh, S.n_in, arena + S.row_r, QW,
-                   [&](Acc& acc, uint32_t e) { F::mac(acc, HQ[rc[e]], Wo[rp[e]]); });
+        struct QwOps {
+          Elt q, w;
+        };
+        seg_sum<F>(
+            &sh, S.n_in, arena + S.row_r, QW,
+            [&](uint32_t e) {
+              QwOps o;
+              o.q = HQ[rc[e]];
+              o.w = Wo[rp[e]];
+              return o;
+            },
+            [&](Acc& acc, const QwOps& o) { F::mac(acc, o.q, o.w); });
       }
       // the two dot products of ProverLayers::evaluations (prover_layers.h:357-402)
       const uint32_t npair = (S.n0 + 1) / 2;
@@ -592,7 +618,7 @@ __device__ __forceinline__ void sumcheck_body(const ZkDims& d, const ZkBufs<type
     if (sh.fail) b.status[p] = -100;  // internal inconsistency: never expected
     sh.prof[2] = clock64() - sh.prof[3];
     long long* dbg = reinterpret_cast<long long*>(hqbuf);  // free after the last layer
-    for (int i = 0; i < 4; ++i) dbg[i] = sh.prof[i];
+    for (int i = 0; i < 8; ++i) dbg[i] = sh.prof[i];
   }
 }
 
@@ -959,6 +985,17 @@ k_lig_finish(ZkDims d, ZkBufs<typename F::Elt> b, const LayerDesc* __restrict__ 
 
   for (uint32_t i = tid; i < n; i += nth) perm[i] = i;
   for (uint32_t i = tid; i < 2 * n; i += nth) mark[i] = 0;
+  // wire words of the four response arrays, converted by the whole CTA (for prime
+  // fields to_wire is a Montgomery multiplication); thread 0 then only hashes.
+  // They are staged at the start of the output slot, which is rewritten below.
+  const uint32_t ny = d.block + 2 * d.dblock;
+  uint32_t* yw = reinterpret_cast<uint32_t*>(out);
+  for (uint32_t i = tid; i < ny; i += nth) {
+    uint32_t w[F::kWords];
+    F::to_wire(w, y[i]);
+#pragma unroll
+    for (int q = 0; q < F::kWords; ++q) yw[(size_t)i * F::kWords + q] = w[q];
+  }
   __syncthreads();
   if (tid == 0) {
     Transcript* gts = reinterpret_cast<Transcript*>(b.ts + p * sizeof(Transcript));
@@ -968,7 +1005,8 @@ k_lig_finish(ZkDims d, ZkBufs<typename F::Elt> b, const LayerDesc* __restrict__ 
     const uint32_t offs[4] = {0, d.block, d.block + d.dblock, d.block + d.dblock + d.block};
     for (int a = 0; a < 4; ++a) {
       ts.begin_array(lens[a]);
-      for (uint32_t i = 0; i < lens[a]; ++i) ts_array_elt<F>(&ts, y[offs[a] + i]);
+      const uint32_t* src = yw + (size_t)offs[a] * F::kWords;
+      for (uint32_t i = 0; i < lens[a] * F::kWords; ++i) ts.sha.put_word_be(bswap32(src[i]));
     }
     // RandomEngine::choose (random.h:92-105)
     for (uint32_t i = 0; i < d.nreq; ++i) {
