@@ -111,6 +111,42 @@ LF_HD __forceinline__ void sha256_compress_zero(uint32_t h[8]) {
   h[0] += a; h[1] += b; h[2] += c; h[3] += d; h[4] += e; h[5] += f; h[6] += g; h[7] += hh;
 }
 
+// The transcript thread's compression: ONE out-of-line copy, 16 rounds per loop
+// iteration (~12 KB of SASS, inside the 32 KB L1.5 instruction cache).  The
+// serial Fiat-Shamir path calls a compression from ~50 sites; inlining the
+// fully unrolled rounds at each of them made the sumcheck kernel > 1 MB of
+// straight-line code that a single warp executes once per call, i.e. every
+// call ran at instruction-fetch speed (profiles/r1_sumcheck_occ8_full.txt).
+// hs/ws may point to shared or local memory.
+#ifdef __CUDACC__
+static __device__ __noinline__ void sha256_compress_fn(uint32_t* hs, const uint32_t* ws) {
+  uint32_t w[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) w[i] = ws[i];
+  uint32_t a = hs[0], b = hs[1], c = hs[2], d = hs[3], e = hs[4], f = hs[5], g = hs[6], hh = hs[7];
+#pragma unroll 1
+  for (int j = 0; j < 64; j += 16) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      if (j) {  // uniform: message schedule from the second pass on
+        uint32_t w15 = w[(i + 1) & 15], w2 = w[(i + 14) & 15];
+        uint32_t s0 = rotr32(w15, 7) ^ rotr32(w15, 18) ^ (w15 >> 3);
+        uint32_t s1 = rotr32(w2, 17) ^ rotr32(w2, 19) ^ (w2 >> 10);
+        w[i] = w[i] + s0 + w[(i + 9) & 15] + s1;
+      }
+      uint32_t S1 = rotr32(e, 6) ^ rotr32(e, 11) ^ rotr32(e, 25);
+      uint32_t ch = (e & f) ^ (~e & g);
+      uint32_t t1 = hh + S1 + ch + kSha256K_dev[j + i] + w[i];
+      uint32_t S0 = rotr32(a, 2) ^ rotr32(a, 13) ^ rotr32(a, 22);
+      uint32_t mj = (a & b) ^ (a & c) ^ (b & c);
+      uint32_t t2 = S0 + mj;
+      hh = g; g = f; f = e; e = d + t1; d = c; c = b; b = a; a = t1 + t2;
+    }
+  }
+  hs[0] += a; hs[1] += b; hs[2] += c; hs[3] += d; hs[4] += e; hs[5] += f; hs[6] += g; hs[7] += hh;
+}
+#endif
+
 // Incremental SHA-256 with a byte-granular buffer (transcript writes are 1, 8,
 // 16 and 32 bytes long).
 struct Sha256 {
@@ -118,20 +154,24 @@ struct Sha256 {
   uint32_t buf[16];  // big-endian words being filled
   uint64_t len;      // bytes absorbed
 
-  // One compression of the buffered block.  h and buf are copied to locals so
-  // that the fully unrolled rounds run out of registers even when *this lives
-  // in shared or local memory (the transcript thread's state).
+  // One compression of the buffered block.
   LF_HD void compress_block() {
-    uint32_t hh[8], ww[16];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) hh[i] = h[i];
-#pragma unroll
+#ifdef __CUDA_ARCH__
+    sha256_compress_fn(h, buf);
+#else
+    uint32_t ww[16];
     for (int i = 0; i < 16; ++i) ww[i] = buf[i];
-    sha256_compress(hh, ww);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) h[i] = hh[i];
+    sha256_compress(h, ww);
+#endif
 #pragma unroll
     for (int i = 0; i < 16; ++i) buf[i] = 0;
+  }
+  LF_HD static void compress_any(uint32_t* hh, uint32_t* w) {
+#ifdef __CUDA_ARCH__
+    sha256_compress_fn(hh, w);
+#else
+    sha256_compress(hh, w);
+#endif
   }
   LF_HD void compress_zero_block() {
     uint32_t hh[8];
@@ -216,14 +256,14 @@ struct Sha256 {
     uint32_t pos = (uint32_t)(len & 63);
     w[pos >> 2] |= 0x80u << (24 - 8 * (pos & 3));
     if (pos >= 56) {
-      sha256_compress(hh, w);
+      compress_any(hh, w);
 #pragma unroll
       for (int i = 0; i < 16; ++i) w[i] = 0;
     }
     uint64_t bits = len * 8;
     w[14] = (uint32_t)(bits >> 32);
     w[15] = (uint32_t)bits;
-    sha256_compress(hh, w);
+    compress_any(hh, w);
 #pragma unroll
     for (int i = 0; i < 8; ++i) out[i] = hh[i];
   }
@@ -387,7 +427,12 @@ struct Transcript {
   LF_HD void elt_words(const uint32_t* e, int nwords) { sha.update_le_words(e, nwords); }
 
   // transcript.h:46-62,89-96
-  LF_HD uint8_t next_byte() {
+  // (re)key the PRF if a write intervened, then produce the next 16-byte block;
+  // one out-of-line copy on the device (see sha256_compress_fn)
+#ifdef __CUDACC__
+  __host__ __device__ __noinline__
+#endif
+  void refill() {
     if (!have_prf) {
       uint32_t d[8], key[8];
       sha.snapshot(d);
@@ -396,14 +441,14 @@ struct Transcript {
       prf.init(key, sbox);
       have_prf = 1;
       nblock = 0;
-      rdptr = 16;
     }
-    if (rdptr == 16) {
-      uint32_t in[4] = {(uint32_t)nblock, (uint32_t)(nblock >> 32), 0, 0};
-      ++nblock;
-      prf.encrypt(in, saved, sbox);
-      rdptr = 0;
-    }
+    uint32_t in[4] = {(uint32_t)nblock, (uint32_t)(nblock >> 32), 0, 0};
+    ++nblock;
+    prf.encrypt(in, saved, sbox);
+    rdptr = 0;
+  }
+  LF_HD uint8_t next_byte() {
+    if (!have_prf || rdptr == 16) refill();
     uint8_t b = (uint8_t)(saved[rdptr >> 2] >> (8 * (rdptr & 3)));
     ++rdptr;
     return b;
@@ -414,7 +459,8 @@ struct Transcript {
   // nwords LE words of challenge bytes
   LF_HD void words(uint32_t* out, int nwords) {
     for (int i = 0; i < nwords; ++i) {
-      if (have_prf && (rdptr & 3) == 0 && rdptr < 16) {
+      if (!have_prf || rdptr == 16) refill();
+      if ((rdptr & 3) == 0) {
         out[i] = saved[rdptr >> 2];
         rdptr += 4;
       } else {

@@ -622,45 +622,20 @@ __device__ __forceinline__ void sumcheck_body(const ZkDims& d, const ZkBufs<type
   }
 }
 
+// One kernel body, three shapes.  NT threads per proof, MINB resident CTAs per SM:
+//   <128, 8>  throughput (default): 8 proofs per SM in flight
+//   < 64,16>  throughput for very large batches: 16 proofs per SM, so that fewer
+//             warps idle at barriers while thread 0 of a CTA runs the transcript
+//   <1024,1>  latency: one CTA per proof on its own SM
 constexpr int kScTpThreads = 128;
-template <class F>
-__global__ void __launch_bounds__(kScTpThreads, 8)
-k_zk_sumcheck_tp(ZkDims d, ZkBufs<typename F::Elt> b, const uint32_t* __restrict__ arena,
-                 const LayerDesc* __restrict__ layers, const StepDesc* __restrict__ steps,
-                 const typename F::Elt* __restrict__ consts) {
+template <class F, int NT, int MINB>
+__global__ void __launch_bounds__(NT, MINB)
+k_zk_sumcheck(ZkDims d, ZkBufs<typename F::Elt> b, const uint32_t* __restrict__ arena,
+              const LayerDesc* __restrict__ layers, const StepDesc* __restrict__ steps,
+              const typename F::Elt* __restrict__ consts) {
   __shared__ ScShared<F> sh;
-  __shared__ typename F::Elt hp[kScTpThreads];
-  __shared__ uint32_t hr[kScTpThreads];
-  if (threadIdx.x == 0) {
-    sh.hp = hp;
-    sh.hr = hr;
-  }
-  __syncthreads();
-  sumcheck_body<F>(d, b, arena, layers, steps, consts, sh);
-}
-template <class F>
-__global__ void __launch_bounds__(kScTpThreads, 4)
-k_zk_sumcheck_tp4(ZkDims d, ZkBufs<typename F::Elt> b, const uint32_t* __restrict__ arena,
-                  const LayerDesc* __restrict__ layers, const StepDesc* __restrict__ steps,
-                  const typename F::Elt* __restrict__ consts) {
-  __shared__ ScShared<F> sh;
-  __shared__ typename F::Elt hp[kScTpThreads];
-  __shared__ uint32_t hr[kScTpThreads];
-  if (threadIdx.x == 0) {
-    sh.hp = hp;
-    sh.hr = hr;
-  }
-  __syncthreads();
-  sumcheck_body<F>(d, b, arena, layers, steps, consts, sh);
-}
-template <class F>
-__global__ void __launch_bounds__(kScMaxThreads, 1)
-k_zk_sumcheck_lat(ZkDims d, ZkBufs<typename F::Elt> b, const uint32_t* __restrict__ arena,
-                  const LayerDesc* __restrict__ layers, const StepDesc* __restrict__ steps,
-                  const typename F::Elt* __restrict__ consts) {
-  __shared__ ScShared<F> sh;
-  __shared__ typename F::Elt hp[kScMaxThreads];
-  __shared__ uint32_t hr[kScMaxThreads];
+  __shared__ typename F::Elt hp[NT];
+  __shared__ uint32_t hr[NT];
   if (threadIdx.x == 0) {
     sh.hp = hp;
     sh.hr = hr;
