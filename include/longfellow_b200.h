@@ -172,7 +172,10 @@ uint64_t lf_ctx_launch_count(const lf_ctx* ctx);
 /* integer-pipe micro-benchmarks (roofline denominators): returns achieved
  * giga-operations per second of `what` on the context's device.
  *   what = 0: IMAD.WIDE  1: LOP3  2: GF(2^128) multiply (Gmul/s)
- *          3: SHA-256 compressions (G/s) */
+ *          3: SHA-256 compressions (G/s)
+ *   what = 100..105: single-thread latency of the transcript primitives, in
+ *          CYCLES per call: compression, digest snapshot, AES-256 key
+ *          schedule, AES block, 16-byte element write, write + challenge */
 int lf_microbench(lf_ctx* ctx, int what, double* gops);
 
 #ifdef __cplusplus

@@ -112,39 +112,47 @@ LF_HD __forceinline__ void sha256_compress_zero(uint32_t h[8]) {
 }
 
 // The transcript thread's compression: ONE out-of-line copy, 16 rounds per loop
-// iteration (~12 KB of SASS, inside the 32 KB L1.5 instruction cache).  The
+// iteration (~10 KB of SASS, inside the 32 KB L1.5 instruction cache).  The
 // serial Fiat-Shamir path calls a compression from ~50 sites; inlining the
 // fully unrolled rounds at each of them made the sumcheck kernel > 1 MB of
 // straight-line code that a single warp executes once per call, i.e. every
 // call ran at instruction-fetch speed (profiles/r1_sumcheck_occ8_full.txt).
 // hs/ws may point to shared or local memory.
 #ifdef __CUDACC__
+#define LF_SHA_ROUND(K, W)                                              \
+  {                                                                     \
+    uint32_t S1 = rotr32(e, 6) ^ rotr32(e, 11) ^ rotr32(e, 25);         \
+    uint32_t ch = (e & f) ^ (~e & g);                                   \
+    uint32_t t1 = hh + S1 + ch + (K) + (W);                             \
+    uint32_t S0 = rotr32(a, 2) ^ rotr32(a, 13) ^ rotr32(a, 22);         \
+    uint32_t mj = (a & b) ^ (a & c) ^ (b & c);                          \
+    uint32_t t2 = S0 + mj;                                              \
+    hh = g; g = f; f = e; e = d + t1; d = c; c = b; b = a; a = t1 + t2; \
+  }
 static __device__ __noinline__ void sha256_compress_fn(uint32_t* hs, const uint32_t* ws) {
   uint32_t w[16];
 #pragma unroll
   for (int i = 0; i < 16; ++i) w[i] = ws[i];
   uint32_t a = hs[0], b = hs[1], c = hs[2], d = hs[3], e = hs[4], f = hs[5], g = hs[6], hh = hs[7];
+  // branch-free bodies: rounds 0..15 straight, then three passes of 16 rounds
+  // with the message schedule (a test inside the body splits it into one basic
+  // block per round and the rounds no longer overlap)
+#pragma unroll
+  for (int i = 0; i < 16; ++i) LF_SHA_ROUND(kSha256K_dev[i], w[i])
 #pragma unroll 1
-  for (int j = 0; j < 64; j += 16) {
+  for (int j = 16; j < 64; j += 16) {
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
-      if (j) {  // uniform: message schedule from the second pass on
-        uint32_t w15 = w[(i + 1) & 15], w2 = w[(i + 14) & 15];
-        uint32_t s0 = rotr32(w15, 7) ^ rotr32(w15, 18) ^ (w15 >> 3);
-        uint32_t s1 = rotr32(w2, 17) ^ rotr32(w2, 19) ^ (w2 >> 10);
-        w[i] = w[i] + s0 + w[(i + 9) & 15] + s1;
-      }
-      uint32_t S1 = rotr32(e, 6) ^ rotr32(e, 11) ^ rotr32(e, 25);
-      uint32_t ch = (e & f) ^ (~e & g);
-      uint32_t t1 = hh + S1 + ch + kSha256K_dev[j + i] + w[i];
-      uint32_t S0 = rotr32(a, 2) ^ rotr32(a, 13) ^ rotr32(a, 22);
-      uint32_t mj = (a & b) ^ (a & c) ^ (b & c);
-      uint32_t t2 = S0 + mj;
-      hh = g; g = f; f = e; e = d + t1; d = c; c = b; b = a; a = t1 + t2;
+      uint32_t w15 = w[(i + 1) & 15], w2 = w[(i + 14) & 15];
+      uint32_t s0 = rotr32(w15, 7) ^ rotr32(w15, 18) ^ (w15 >> 3);
+      uint32_t s1 = rotr32(w2, 17) ^ rotr32(w2, 19) ^ (w2 >> 10);
+      w[i] = w[i] + s0 + w[(i + 9) & 15] + s1;
+      LF_SHA_ROUND(kSha256K_dev[j + i], w[i])
     }
   }
   hs[0] += a; hs[1] += b; hs[2] += c; hs[3] += d; hs[4] += e; hs[5] += f; hs[6] += g; hs[7] += hh;
 }
+#undef LF_SHA_ROUND
 #endif
 
 // Incremental SHA-256 with a byte-granular buffer (transcript writes are 1, 8,
@@ -301,10 +309,30 @@ LF_HD __forceinline__ const uint8_t* aes_default_sbox() {
   return kAesSbox_host;
 #endif
 }
+// S-box plus the four round tables te[k][x] = rotl(Te0[x], 8k), Te0[x] = the
+// MixColumns image (2s, s, s, 3s) of s = S[x] in a little-endian column word.
+struct AesTables {
+  uint32_t te[4][256];
+  uint8_t sbox[256];
+};
 #ifdef __CUDACC__
 // call from all threads of a CTA; sb = __shared__ uint8_t[256]
 __device__ __forceinline__ void aes_stage_sbox(uint8_t* sb) {
   for (uint32_t i = threadIdx.x; i < 256; i += blockDim.x) sb[i] = kAesSbox_dev[i];
+  __syncthreads();
+}
+// call from all threads of a CTA; t = __shared__ AesTables
+__device__ __forceinline__ void aes_stage_tables(AesTables* t) {
+  for (uint32_t i = threadIdx.x; i < 256; i += blockDim.x) {
+    uint32_t s = kAesSbox_dev[i];
+    uint32_t s2 = ((s << 1) ^ ((s >> 7) * 0x11bu)) & 0xffu, s3 = s2 ^ s;
+    uint32_t t0 = s2 | (s << 8) | (s << 16) | (s3 << 24);
+    t->sbox[i] = (uint8_t)s;
+    t->te[0][i] = t0;
+    t->te[1][i] = (t0 << 8) | (t0 >> 24);
+    t->te[2][i] = (t0 << 16) | (t0 >> 16);
+    t->te[3][i] = (t0 << 24) | (t0 >> 8);
+  }
   __syncthreads();
 }
 #endif
@@ -336,6 +364,51 @@ struct Aes256 {
       rk[i] = rk[i - 8] ^ t;
     }
   }
+#ifdef __CUDACC__
+  // Device forms used by the transcript thread.  Key schedule: fully unrolled
+  // over a sliding window of the last eight words (no dependent shared-memory
+  // round trips); block: one table lookup per state byte.
+  __device__ __forceinline__ void init_unrolled(const uint32_t key[8], const uint8_t* sb) {
+    uint32_t w0 = key[0], w1 = key[1], w2 = key[2], w3 = key[3], w4 = key[4], w5 = key[5], w6 = key[6], w7 = key[7];
+    rk[0] = w0; rk[1] = w1; rk[2] = w2; rk[3] = w3; rk[4] = w4; rk[5] = w5; rk[6] = w6; rk[7] = w7;
+    uint32_t rcon = 1;
+#pragma unroll
+    for (int i = 8; i < 60; i += 8) {
+      w0 ^= aes_subword(sb, (w7 >> 8) | (w7 << 24)) ^ rcon;
+      rcon <<= 1;  // seven doublings from 1: stays below 0x80, no reduction
+      w1 ^= w0; w2 ^= w1; w3 ^= w2;
+      rk[i] = w0; rk[i + 1] = w1; rk[i + 2] = w2; rk[i + 3] = w3;
+      if (i + 4 < 60) {
+        w4 ^= aes_subword(sb, w3);
+        w5 ^= w4; w6 ^= w5; w7 ^= w6;
+        rk[i + 4] = w4; rk[i + 5] = w5; rk[i + 6] = w6; rk[i + 7] = w7;
+      }
+    }
+  }
+  __device__ __forceinline__ void encrypt_te(const uint32_t in[4], uint32_t out[4], const AesTables* T) const {
+    uint32_t s0 = in[0] ^ rk[0], s1 = in[1] ^ rk[1], s2 = in[2] ^ rk[2], s3 = in[3] ^ rk[3];
+#pragma unroll 1
+    for (int r = 1; r < 14; ++r) {
+      uint32_t t0 = T->te[0][s0 & 0xff] ^ T->te[1][(s1 >> 8) & 0xff] ^ T->te[2][(s2 >> 16) & 0xff] ^ T->te[3][s3 >> 24];
+      uint32_t t1 = T->te[0][s1 & 0xff] ^ T->te[1][(s2 >> 8) & 0xff] ^ T->te[2][(s3 >> 16) & 0xff] ^ T->te[3][s0 >> 24];
+      uint32_t t2 = T->te[0][s2 & 0xff] ^ T->te[1][(s3 >> 8) & 0xff] ^ T->te[2][(s0 >> 16) & 0xff] ^ T->te[3][s1 >> 24];
+      uint32_t t3 = T->te[0][s3 & 0xff] ^ T->te[1][(s0 >> 8) & 0xff] ^ T->te[2][(s1 >> 16) & 0xff] ^ T->te[3][s2 >> 24];
+      s0 = t0 ^ rk[4 * r];
+      s1 = t1 ^ rk[4 * r + 1];
+      s2 = t2 ^ rk[4 * r + 2];
+      s3 = t3 ^ rk[4 * r + 3];
+    }
+    const uint8_t* sb = T->sbox;
+    out[0] = ((uint32_t)sb[s0 & 0xff] | ((uint32_t)sb[(s1 >> 8) & 0xff] << 8) | ((uint32_t)sb[(s2 >> 16) & 0xff] << 16) |
+              ((uint32_t)sb[s3 >> 24] << 24)) ^ rk[56];
+    out[1] = ((uint32_t)sb[s1 & 0xff] | ((uint32_t)sb[(s2 >> 8) & 0xff] << 8) | ((uint32_t)sb[(s3 >> 16) & 0xff] << 16) |
+              ((uint32_t)sb[s0 >> 24] << 24)) ^ rk[57];
+    out[2] = ((uint32_t)sb[s2 & 0xff] | ((uint32_t)sb[(s3 >> 8) & 0xff] << 8) | ((uint32_t)sb[(s0 >> 16) & 0xff] << 16) |
+              ((uint32_t)sb[s1 >> 24] << 24)) ^ rk[58];
+    out[3] = ((uint32_t)sb[s3 & 0xff] | ((uint32_t)sb[(s0 >> 8) & 0xff] << 8) | ((uint32_t)sb[(s1 >> 16) & 0xff] << 16) |
+              ((uint32_t)sb[s2 >> 24] << 24)) ^ rk[59];
+  }
+#endif
   LF_HD void encrypt(const uint32_t in[4], uint32_t out[4], const uint8_t* sb) const {
     uint32_t s0 = in[0] ^ rk[0], s1 = in[1] ^ rk[1], s2 = in[2] ^ rk[2], s3 = in[3] ^ rk[3];
     for (int r = 1; r <= 14; ++r) {
@@ -378,7 +451,12 @@ struct Transcript {
   uint32_t have_prf;
   uint32_t saved[4];  // LE-packed bytes of the current PRF block
   const uint8_t* sbox;  // AES S-box to use (re-pointed by every kernel after loading the state)
+  const AesTables* tab; // round tables in shared memory, or null: S-box only
 
+  LF_HD void use_tables(const AesTables* t) {
+    tab = t;
+    sbox = t->sbox;
+  }
   LF_HD void raw_byte(uint8_t b) {
     have_prf = 0;
     sha.put_byte(b);
@@ -394,6 +472,7 @@ struct Transcript {
     nblock = 0;
     rdptr = 16;
     sbox = aes_default_sbox();
+    tab = nullptr;
     write_bytes(seed, n);
   }
   // transcript.h:116-121
@@ -438,13 +517,22 @@ struct Transcript {
       sha.snapshot(d);
 #pragma unroll
       for (int i = 0; i < 8; ++i) key[i] = bswap32(d[i]);  // digest bytes, LE-packed
+#ifdef __CUDA_ARCH__
+      prf.init_unrolled(key, sbox);
+#else
       prf.init(key, sbox);
+#endif
       have_prf = 1;
       nblock = 0;
     }
     uint32_t in[4] = {(uint32_t)nblock, (uint32_t)(nblock >> 32), 0, 0};
     ++nblock;
-    prf.encrypt(in, saved, sbox);
+#ifdef __CUDA_ARCH__
+    if (tab)
+      prf.encrypt_te(in, saved, tab);
+    else
+#endif
+      prf.encrypt(in, saved, sbox);
     rdptr = 0;
   }
   LF_HD uint8_t next_byte() {

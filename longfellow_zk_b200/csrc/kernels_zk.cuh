@@ -256,7 +256,7 @@ struct ScShared {
   typename F::Elt r, alpha, beta, sum, wc[2];
   typename F::Elt* hp;  // [blockDim.x] head partials of the segmented sums
   uint32_t* hr;         // [blockDim.x] their segment ids
-  uint8_t sbox[256];    // AES S-box staged in shared memory
+  AesTables aes;        // AES S-box and round tables staged in shared memory
   int fail;
   long long prof[8];    // LF_PROF: cycles of thread 0 per phase
 };
@@ -389,7 +389,7 @@ __device__ __noinline__ void sc_round_serial(ScShared<F>* sh, typename F::Elt a0
 template <class F>
 __device__ __noinline__ void sc_begin(ScShared<F>* sh, const Transcript* src) {
   sh->ts = *src;
-  sh->ts.sbox = sh->sbox;
+  sh->ts.use_tables(&sh->aes);
   sh->ts.have_prf = 0;  // Transcript::clone() carries only the hash (transcript.h:86)
   // begin_circuit: Q[40] then G[40] (transcript_sumcheck.h:49-52)
   for (int i = 0; i < 40; ++i) (void)F::ts_elt(&sh->ts);
@@ -454,7 +454,7 @@ __device__ __forceinline__ void sumcheck_body(const ZkDims& d, const ZkBufs<type
   const Elt* wit = b.wit + p * d.nw;
   Elt* hbs = b.hb + p * d.nhb;
 
-  aes_stage_sbox(sh.sbox);
+  aes_stage_tables(&sh.aes);
   if (tid == 0) {
     for (int i = 0; i < 8; ++i) sh.prof[i] = 0;
     sh.prof[3] = clock64();
@@ -653,13 +653,13 @@ k_zk_sumcheck(ZkDims d, ZkBufs<typename F::Elt> b, const uint32_t* __restrict__ 
 // ----------------------------------------------------------------------------
 template <class F>
 __global__ void k_lig_challenges(ZkDims d, ZkBufs<typename F::Elt> b, size_t nproofs) {
-  __shared__ uint8_t s_sbox[256];
-  aes_stage_sbox(s_sbox);
+  __shared__ AesTables s_aes;
+  aes_stage_tables(&s_aes);
   size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= nproofs || b.status[p] != 0) return;
   Transcript* gts = reinterpret_cast<Transcript*>(b.ts + p * sizeof(Transcript));
   Transcript ts = *gts;
-  ts.sbox = s_sbox;
+  ts.use_tables(&s_aes);
   typename F::Elt* chal = b.chal + p * (size_t)(1 + d.nchal);
   chal[0] = F::ts_elt(&ts);
   uint32_t hashA[8] = {0xefbeaddeu, 0, 0, 0, 0, 0, 0, 0};  // bytes de ad be ef 00 ...
@@ -955,8 +955,8 @@ k_lig_finish(ZkDims d, ZkBufs<typename F::Elt> b, const LayerDesc* __restrict__ 
   uint32_t* eoff = reinterpret_cast<uint32_t*>(flag + ((total + 3) & ~3u));
   uint32_t* path_idx = eoff + total;
   __shared__ uint32_t s_npath, s_req_end;
-  __shared__ uint8_t s_sbox[256];
-  for (uint32_t i = threadIdx.x; i < 256; i += blockDim.x) s_sbox[i] = kAesSbox_dev[i];
+  __shared__ AesTables s_aes;
+  aes_stage_tables(&s_aes);
 
   for (uint32_t i = tid; i < n; i += nth) perm[i] = i;
   for (uint32_t i = tid; i < 2 * n; i += nth) mark[i] = 0;
@@ -975,7 +975,7 @@ k_lig_finish(ZkDims d, ZkBufs<typename F::Elt> b, const LayerDesc* __restrict__ 
   if (tid == 0) {
     Transcript* gts = reinterpret_cast<Transcript*>(b.ts + p * sizeof(Transcript));
     Transcript ts = *gts;
-    ts.sbox = s_sbox;
+    ts.use_tables(&s_aes);
     const uint32_t lens[4] = {d.block, d.dblock, d.r, d.dblock - d.block};
     const uint32_t offs[4] = {0, d.block, d.block + d.dblock, d.block + d.dblock + d.block};
     for (int a = 0; a < 4; ++a) {

@@ -1141,12 +1141,84 @@ int lf_fft_time(lf_ctx* ctx, int field_id, size_t n, int reps, double* ms_per_ff
   return fft_dispatch(ctx, field_id, nullptr, n, 0, reps, ms_per_fft);
 }
 
+}  // extern "C"
+// single-thread latency probes of the transcript primitives (cycles per call);
+// what = 100 + k:  0 compression  1 snapshot  2 AES-256 key schedule  3 AES block
+//                  4 write of one 16-byte element  5 write + 16 challenge bytes
+__global__ void k_probe_serial(long long* out) {
+  __shared__ lf::Transcript ts;
+  __shared__ lf::AesTables aes;
+  lf::aes_stage_tables(&aes);
+  const uint8_t* sbox = aes.sbox;
+  if (threadIdx.x != 0) return;
+  const uint8_t seed[4] = {1, 2, 3, 4};
+  ts.init(seed, 4);
+  ts.use_tables(&aes);
+  uint32_t acc = 0;
+  const int R = 16;
+  long long t0 = clock64();
+  for (int i = 0; i < R; ++i) {
+    ts.sha.buf[3] = i + acc;
+    ts.sha.compress_block();
+  }
+  long long t1 = clock64();
+  for (int i = 0; i < R; ++i) {
+    uint32_t d[8];
+    ts.sha.buf[1] = i + acc;
+    ts.sha.snapshot(d);
+    acc += d[0];
+  }
+  long long t2 = clock64();
+  for (int i = 0; i < R; ++i) {
+    uint32_t key[8] = {acc, 1, 2, 3, 4, 5, 6, (uint32_t)i};
+    ts.prf.init_unrolled(key, sbox);
+    acc += ts.prf.rk[59];
+  }
+  long long t3 = clock64();
+  for (int i = 0; i < R; ++i) {
+    uint32_t in[4] = {acc, 0, 0, (uint32_t)i}, o[4];
+    ts.prf.encrypt_te(in, o, &aes);
+    acc += o[0];
+  }
+  long long t4 = clock64();
+  for (int i = 0; i < R; ++i) {
+    uint32_t e[4] = {acc, 7, 8, (uint32_t)i};
+    ts.write_elt_words(e, 4);
+  }
+  long long t5 = clock64();
+  for (int i = 0; i < R; ++i) {
+    uint32_t e[4] = {acc, 7, 8, (uint32_t)i}, o[4];
+    ts.write_elt_words(e, 4);
+    ts.words(o, 4);
+    acc += o[1];
+  }
+  long long t6 = clock64();
+  out[0] = (t1 - t0) / R;
+  out[1] = (t2 - t1) / R;
+  out[2] = (t3 - t2) / R;
+  out[3] = (t4 - t3) / R;
+  out[4] = (t5 - t4) / R;
+  out[5] = (t6 - t5) / R;
+  out[6] = acc;
+}
+extern "C" {
+
 int lf_microbench(lf_ctx* ctx, int what, double* gops) {
   if (!ctx || !gops) return fail(LF_ERR_ARG, "lf_microbench: null argument");
   LF_CUDA(cudaSetDevice(ctx->device));
   const int blocks = ctx->sm_count * 8, threads = 256;
   void* d;
   LF_CUDA(cudaMalloc(&d, (size_t)blocks * threads * 16));
+  if (what >= 100 && what < 106) {
+    long long h[8];
+    k_probe_serial<<<1, 32, 0, ctx->stream>>>((long long*)d);
+    ctx->launches++;
+    LF_CUDA(cudaMemcpyAsync(h, d, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+    LF_CUDA(cudaStreamSynchronize(ctx->stream));
+    cudaFree(d);
+    *gops = (double)h[what - 100];
+    return 0;
+  }
   cudaEvent_t e0, e1;
   LF_CUDA(cudaEventCreate(&e0));
   LF_CUDA(cudaEventCreate(&e1));

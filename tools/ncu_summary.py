@@ -24,6 +24,15 @@ for r in rows[2:]:
     for k in KEYS:
         if k in h:
             print(f"  {k:70s} {r[h.index(k)]:>18s} {units[h.index(k)]}")
+    print("  pipes (% of peak, active):")
+    for i, c in enumerate(h):
+        if (c.startswith("sm__inst_executed_pipe_") or c.startswith("sm__pipe_")) and "pct_of_peak_sustained_active" in c:
+            try:
+                v = float(r[i].replace(",", ""))
+            except ValueError:
+                continue
+            if v >= 1.0:
+                print(f"    {c:76s} {v:6.1f}")
     st = [(float(r[i].replace(",", "")), c) for i, c in enumerate(h)
           if c.startswith("smsp__pcsamp_warps_issue_stalled_") and not c.endswith("_not_issued")]
     tot = sum(v for v, _ in st) or 1
