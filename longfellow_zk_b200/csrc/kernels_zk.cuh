@@ -204,8 +204,9 @@ k_zk_eval_layer(ZkDims d, ZkBufs<typename F::Elt> b, const uint32_t* __restrict_
                 const typename F::Elt* __restrict__ consts, int is_output) {
   typedef typename F::Elt Elt;
   const size_t p = blockIdx.y;
-  uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
-  if (g >= L.nout) return;
+  const uint32_t gi = blockIdx.x * blockDim.x + threadIdx.x;
+  if (gi >= L.nout) return;
+  const uint32_t g = arena[L.ev_perm + gi];
   const Elt* W = b.wl + p * d.wl_elts + L.w_off;
   const uint32_t* off = arena + L.ev_off;
   const uint32_t *h0 = arena + L.ev_h0, *h1 = arena + L.ev_h1, *vi = arena + L.ev_vi;

@@ -26,6 +26,7 @@ struct LayerDesc {
   // offsets into the uint32 arena
   uint32_t ev_off;   // [nout+1] CSR by gate: eval_circuit
   uint32_t ev_h0, ev_h1, ev_vi;  // [nterms]
+  uint32_t ev_perm;              // [nout] gates sorted by decreasing term count
   uint32_t bg_seg;   // [nterms] initial HQuad corner of each term (canonical order, non-decreasing)
   uint32_t bg_g, bg_vi;          // [nterms]
   uint32_t step0;    // first StepDesc of this layer (2*logw of them)
