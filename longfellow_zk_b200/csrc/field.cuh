@@ -197,9 +197,9 @@ struct FFp {
   // one out-of-line Montgomery product per field (same reason as gf_mul_wide_fn)
   static __device__ __noinline__ Elt mul_fn(Elt a, Elt b) {
     if constexpr (T::kP256) {
-      return fp_mul_p256(a, b, T::C().m);
+      return fp_mul_p256_dev(a, b, T::C().m);
     } else {
-      return fp_mul_generic<W>(a, b, T::C().m, T::C().mprime);
+      return fp_mul_generic_dev<W>(a, b, T::C().m, T::C().mprime);
     }
   }
   __device__ static __forceinline__ Elt zero() {

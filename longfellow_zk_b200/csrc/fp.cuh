@@ -173,6 +173,131 @@ LF_HDI fpw<8> fp_mul_p256(const fpw<8>& a, const fpw<8>& b, const uint32_t* m) {
   return r;
 }
 
+#ifdef __CUDACC__
+// ---------------------------------------------------------------------------
+// Device product: W x W limbs -> 2W limbs with carry-chained wide multiply-adds.
+// Within a row the products a_j * b_i for even j sit side by side as 64-bit
+// values (and so do the ones for odd j, one limb higher), so one carry chain
+//   mad.lo.cc / madc.hi.cc / madc.lo.cc / ... / addc
+// adds W/2 of them; ptxas fuses each lo/hi pair into one IMAD.WIDE.U32(.X) with
+// the carry in a predicate, i.e. W*W wide multiplies and almost no separate adds.
+template <int N>
+__device__ __forceinline__ void fp_mad_chain(uint32_t* acc, const uint32_t* a /* stride 2 */, uint32_t b);
+template <>
+__device__ __forceinline__ void fp_mad_chain<4>(uint32_t* acc, const uint32_t* a, uint32_t b) {
+  asm("mad.lo.cc.u32 %0, %9, %13, %0;\n\t"
+      "madc.hi.cc.u32 %1, %9, %13, %1;\n\t"
+      "madc.lo.cc.u32 %2, %10, %13, %2;\n\t"
+      "madc.hi.cc.u32 %3, %10, %13, %3;\n\t"
+      "madc.lo.cc.u32 %4, %11, %13, %4;\n\t"
+      "madc.hi.cc.u32 %5, %11, %13, %5;\n\t"
+      "madc.lo.cc.u32 %6, %12, %13, %6;\n\t"
+      "madc.hi.cc.u32 %7, %12, %13, %7;\n\t"
+      "addc.u32 %8, %8, 0;"
+      : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "+r"(acc[4]), "+r"(acc[5]), "+r"(acc[6]),
+        "+r"(acc[7]), "+r"(acc[8])
+      : "r"(a[0]), "r"(a[2]), "r"(a[4]), "r"(a[6]), "r"(b));
+}
+template <>
+__device__ __forceinline__ void fp_mad_chain<2>(uint32_t* acc, const uint32_t* a, uint32_t b) {
+  asm("mad.lo.cc.u32 %0, %5, %7, %0;\n\t"
+      "madc.hi.cc.u32 %1, %5, %7, %1;\n\t"
+      "madc.lo.cc.u32 %2, %6, %7, %2;\n\t"
+      "madc.hi.cc.u32 %3, %6, %7, %3;\n\t"
+      "addc.u32 %4, %4, 0;"
+      : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "+r"(acc[4])
+      : "r"(a[0]), "r"(a[2]), "r"(b));
+}
+template <>
+__device__ __forceinline__ void fp_mad_chain<1>(uint32_t* acc, const uint32_t* a, uint32_t b) {
+  asm("mad.lo.cc.u32 %0, %3, %4, %0;\n\t"
+      "madc.hi.cc.u32 %1, %3, %4, %1;\n\t"
+      "addc.u32 %2, %2, 0;"
+      : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2])
+      : "r"(a[0]), "r"(b));
+}
+
+// t[0..2W+1] = a * b (two spare limbs absorb chain carries; they end up zero).
+// One accumulator: for every row the even-j chain covers limbs i..i+W-1 and
+// the odd-j chain limbs i+1..i+W, so consecutive chains depend on each other
+// and at most ~W/2 carries are live at a time.  (With separate even/odd
+// accumulators ptxas interleaves twice as many chains, runs out of the seven
+// predicate registers and spills carries through P2R/ISETP.)
+template <int W>
+__device__ __forceinline__ void fp_mul_wide_dev(const uint32_t* a, const uint32_t* b, uint32_t* t) {
+#pragma unroll
+  for (int i = 0; i < 2 * W + 2; ++i) t[i] = 0;
+#pragma unroll
+  for (int i = 0; i < W; ++i) {
+    fp_mad_chain<W / 2>(t + i, a, b[i]);
+    fp_mad_chain<W / 2>(t + i + 1, a + 1, b[i]);
+  }
+}
+
+// P-256 Montgomery product: wide product, then the eight multiply-free
+// reduction steps of fp_mul_p256 in closed form.  Step i adds q_i * p * 2^(32 i)
+// with q_i = (limb i of the running value): -q_i at limb i (clearing it), +q_i
+// at limbs i+3, i+6, i+8 and -q_i at limb i+7 (p = 2^256 - 2^224 + 2^192 + 2^96 - 1).
+// REDC is a function, so the limbs equal the interleaved form's.
+__device__ __forceinline__ fpw<8> fp_mul_p256_dev(const fpw<8>& a, const fpw<8>& b, const uint32_t* m) {
+  uint32_t t[18];
+  fp_mul_wide_dev<8>(a.w, b.w, t);
+  uint32_t q[8];
+  int64_t c = 0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    int64_t v = (int64_t)t[i] + c;
+    if (i >= 3) v += q[i - 3];
+    if (i >= 6) v += q[i - 6];
+    if (i >= 7) v -= q[i - 7];
+    q[i] = (uint32_t)v;
+    c = v >> 32;  // (v - q_i) / 2^32
+  }
+  fpw<8> r, sb;
+#pragma unroll
+  for (int k = 8; k < 16; ++k) {
+    int64_t v = (int64_t)t[k] + c + q[k - 8];
+    if (k - 3 < 8) v += q[k - 3];
+    if (k - 6 < 8) v += q[k - 6];
+    if (k - 7 < 8) v -= q[k - 7];
+    r.w[k - 8] = (uint32_t)v;
+    c = v >> 32;
+  }
+  uint32_t br = fp_subn<8>(sb.w, r.w, m);
+  bool take = c != 0 || br == 0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) r.w[i] = take ? sb.w[i] : r.w[i];
+  return r;
+}
+
+// Generic modulus: wide product, then W reduction rows q_i = t[i] * mprime,
+// t += q_i * m * 2^(32 i), with the same carry-chained rows; limb i becomes
+// zero and its carry travels up the chain.
+template <int W>
+__device__ __forceinline__ fpw<W> fp_mul_generic_dev(const fpw<W>& a, const fpw<W>& b, const uint32_t* m,
+                                                     uint32_t mprime) {
+  uint32_t t[2 * W + 2];
+  fp_mul_wide_dev<W>(a.w, b.w, t);
+  uint32_t mm[W];
+#pragma unroll
+  for (int i = 0; i < W; ++i) mm[i] = m[i];
+#pragma unroll
+  for (int i = 0; i < W; ++i) {
+    const uint32_t q = t[i] * mprime;
+    fp_mad_chain<W / 2>(t + i, mm, q);
+    fp_mad_chain<W / 2>(t + i + 1, mm + 1, q);
+  }
+  fpw<W> r, sb;
+#pragma unroll
+  for (int i = 0; i < W; ++i) r.w[i] = t[W + i];
+  uint32_t br = fp_subn<W>(sb.w, r.w, m);
+  bool take = t[2 * W] != 0 || br == 0;
+#pragma unroll
+  for (int i = 0; i < W; ++i) r.w[i] = take ? sb.w[i] : r.w[i];
+  return r;
+}
+#endif  // __CUDACC__
+
 }  // namespace lf
 
 // ---------------------------------------------------------------------------
