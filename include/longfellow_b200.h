@@ -70,7 +70,11 @@ int lf_elt_mul(lf_ctx* ctx, int field_id, const void* a, const void* b, void* ou
  * field's standard one: BN254 (order 2^28, fft_test.cc:38-44), Fp128 and
  * Goldilocks (order 2^32, reed_solomon_test.cc:358-360).  For LF_FIELD_P256 the
  * transform is over Fp2 = Fp[i]/(i^2+1) (fft_test.cc:168-172): elts are n pairs
- * (re, im) and the root is the order-2^31 element of mdoc_zk.cc:83-88. */
+ * (re, im) and the root is the order-2^31 element of mdoc_zk.cc:83-88.
+ * For LF_FIELD_GF2_128 it is the additive FFT LCH14<GF2_128>::FFT(l, 0, B)
+ * (forward != 0: novel-basis coefficients -> evaluations on the span of
+ * beta_0..beta_{l-1}) resp. ::IFFT (forward == 0), lib/gf2k/lch14.h:106-146,
+ * n = 2^l <= 65536. */
 int lf_fft(lf_ctx* ctx, int field_id, void* elts, size_t n, int forward);
 /* device-resident timing of fftb at size n (CUDA events on the context stream) */
 int lf_fft_time(lf_ctx* ctx, int field_id, size_t n, int reps, double* ms_per_fft);

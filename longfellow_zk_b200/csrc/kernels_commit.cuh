@@ -117,6 +117,33 @@ k_rs_gf_rows(typename F::Elt* __restrict__ data, size_t row_stride, size_t batch
 }
 
 // ---------------------------------------------------------------------------
+// Large rows (2 * fftn elements do not fit in shared memory, e.g. the
+// 16384 -> 65536 shape of lch14_reed_solomon_test.cc:72-107) and the
+// stand-alone LCH14::FFT / IFFT (lch14.h:106-146): the same schedule, one
+// launch per step over a global-memory work array.  blockIdx.y = row.
+// ---------------------------------------------------------------------------
+template <class F>
+__global__ void k_rs_gf_gstep(typename F::Elt* __restrict__ work, size_t work_stride, RsStep st, uint32_t coset,
+                              const typename F::Elt* __restrict__ d_tw) {
+  const uint32_t t = st.t0 + blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= st.t1) return;
+  const uint32_t half = 1u << st.stage;
+  const uint32_t q = st.base + ((t >> st.stage) << (st.stage + 1)) + (t & (half - 1));
+  typename F::Elt tw = d_tw[tw_offset(st.stage) + ((coset + q) >> (st.stage + 1))];
+  rs_butterfly<F>(work + (size_t)blockIdx.y * work_stride, q, half, st.kind, tw);
+}
+// dst[row][i] = i in [lo, hi) ? src[row][i] : 0   for i < count (zero-extending copy)
+template <class F>
+__global__ void k_rs_gf_copy(typename F::Elt* __restrict__ dst, size_t dst_stride,
+                             const typename F::Elt* __restrict__ src, size_t src_stride, uint32_t count, uint32_t lo,
+                             uint32_t hi) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  dst[(size_t)blockIdx.y * dst_stride + i] =
+      (i >= lo && i < hi) ? src[(size_t)blockIdx.y * src_stride + i] : F::zero();
+}
+
+// ---------------------------------------------------------------------------
 // Prime-field RS extension (lib/algebra/reed_solomon.h:27-41,93-110):
 //   p(k) = lead[k-d] * sum_{i<n} x_i / (k - i),  x_i = (-1)^i C(d,i) p(i),  d = n-1
 // The reference evaluates the sum as an FFT convolution with the table 1/i

@@ -136,4 +136,23 @@ __global__ void k_rs_finish(typename F::Elt* __restrict__ rows, size_t row_strid
   y[k] = F::mul(lead[k - (n - 1)], x[(size_t)blockIdx.y * N + k]);
 }
 
+// the same pad / finish steps for a real row carried in the real parts of Fp2
+// elements (P-256 rows too long for the shared-memory real-FFT kernel)
+template <class F>
+__global__ void k_rs_pad_cx(const typename F::Elt* __restrict__ rows, size_t row_stride, Cx<F>* __restrict__ x,
+                            uint32_t n, uint32_t N, const typename F::Elt* __restrict__ binom) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  const typename F::Elt* y = rows + (size_t)blockIdx.y * row_stride;
+  x[(size_t)blockIdx.y * N + i] = Cx<F>{i < n ? F::mul(binom[i], y[i]) : F::zero(), F::zero()};
+}
+template <class F>
+__global__ void k_rs_finish_cx(typename F::Elt* __restrict__ rows, size_t row_stride, const Cx<F>* __restrict__ x,
+                               uint32_t n, uint32_t m, uint32_t N, const typename F::Elt* __restrict__ lead) {
+  uint32_t k = n + blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= m) return;
+  typename F::Elt* y = rows + (size_t)blockIdx.y * row_stride;
+  y[k] = F::mul(lead[k - (n - 1)], x[(size_t)blockIdx.y * N + k].re);
+}
+
 }  // namespace lf

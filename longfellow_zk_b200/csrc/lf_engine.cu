@@ -159,6 +159,7 @@ static void gen_bidir(std::vector<RsStep>& out, uint32_t i, uint32_t base, uint3
 struct RsPlanHost {
   RsPlan plan;
   RsStep* d_steps = nullptr;
+  std::vector<RsStep> steps;  // host copy: the large-row path launches one kernel per step
 };
 
 static void parse_dec_words(const char* s, uint32_t* out, int W) {
@@ -378,9 +379,70 @@ static int ctx_rs_plan(lf_ctx* ctx, size_t n, size_t m, RsPlanHost** out) {
       LF_CUDA(cudaStreamSynchronize(ctx->stream));
     }
     ph.plan.steps = ph.d_steps;
+    ph.steps = steps;
     it = ctx->rs_plans.emplace(key, ph).first;
   }
   *out = &it->second;
+  return 0;
+}
+
+// One step of an LCH14 schedule over `rows` global-memory work arrays.
+static void gf_gstep(lf_ctx* ctx, gf128* work, size_t work_stride, size_t rows, const RsStep& st, uint32_t coset) {
+  if (st.t1 <= st.t0) return;
+  dim3 grid((st.t1 - st.t0 + 255) / 256, (unsigned)rows);
+  k_rs_gf_gstep<FGf128><<<grid, 256, 0, ctx->stream>>>(work, work_stride, st, coset, ctx->d_tw);
+  ctx->launches++;
+}
+
+// Rows whose first coset does not fit in shared memory: the schedule of
+// k_rs_gf_rows with one launch per step (lch14_reed_solomon.h:49-103).
+static int launch_rs_gf_global(lf_ctx* ctx, gf128* d_rows, size_t row_stride, size_t nrows, size_t batch_stride,
+                               size_t nbatch, const RsPlanHost& ph) {
+  const uint32_t n = ph.plan.n, m = ph.plan.m, l = ph.plan.l, fftn = ph.plan.fftn;
+  gf128 *C = nullptr, *D = nullptr;
+  LF_CUDA(cudaMalloc(&C, nrows * (size_t)fftn * sizeof(gf128)));
+  if (m > fftn && cudaMalloc(&D, nrows * (size_t)fftn * sizeof(gf128)) != cudaSuccess) {
+    cudaFree(C);
+    return fail(LF_ERR_CUDA, "rs: out of device memory for the coset work array");
+  }
+  const dim3 cgrid((fftn + 255) / 256, (unsigned)nrows);
+  for (size_t bi = 0; bi < nbatch; ++bi) {
+    gf128* y = d_rows + bi * batch_stride;
+    // C = y[0..n) zero-extended; truncated transform on the first coset
+    k_rs_gf_copy<FGf128><<<cgrid, 256, 0, ctx->stream>>>(C, fftn, y, row_stride, fftn, 0, n);
+    ctx->launches++;
+    for (const RsStep& st : ph.steps) gf_gstep(ctx, C, fftn, nrows, st, 0);
+    // evaluations n..fftn of the first coset go out; C keeps the n coefficients
+    if (fftn > n) {
+      const uint32_t hi = std::min(fftn, m);
+      LF_CUDA(cudaMemcpy2DAsync(y + n, row_stride * sizeof(gf128), C + n, (size_t)fftn * sizeof(gf128),
+                                (size_t)(hi - n) * sizeof(gf128), nrows, cudaMemcpyDeviceToDevice, ctx->stream));
+    }
+    for (uint32_t b = fftn; b < m; b += fftn) {
+      k_rs_gf_copy<FGf128><<<cgrid, 256, 0, ctx->stream>>>(D, fftn, C, fftn, fftn, 0, n);
+      ctx->launches++;
+      for (uint32_t st = l; st-- > 0;) gf_gstep(ctx, D, fftn, nrows, RsStep{0, st, 0, 0, fftn / 2}, b);
+      const uint32_t cnt = std::min(fftn, m - b);
+      LF_CUDA(cudaMemcpy2DAsync(y + b, row_stride * sizeof(gf128), D, (size_t)fftn * sizeof(gf128),
+                                (size_t)cnt * sizeof(gf128), nrows, cudaMemcpyDeviceToDevice, ctx->stream));
+    }
+  }
+  LF_CUDA(cudaGetLastError());
+  LF_CUDA(cudaStreamSynchronize(ctx->stream));
+  cudaFree(C);
+  if (D) cudaFree(D);
+  return 0;
+}
+
+// LCH14::FFT(l, coset, B) / IFFT (lch14.h:106-146) on one device array of 2^l elements
+static int launch_lch14_fft(lf_ctx* ctx, gf128* d, uint32_t l, uint32_t coset, bool forward) {
+  const uint32_t n = 1u << l;
+  if (forward) {
+    for (uint32_t st = l; st-- > 0;) gf_gstep(ctx, d, n, 1, RsStep{0, st, 0, 0, n / 2}, coset);
+  } else {
+    for (uint32_t st = 0; st < l; ++st) gf_gstep(ctx, d, n, 1, RsStep{1, st, 0, 0, n / 2}, coset);
+  }
+  LF_CUDA(cudaGetLastError());
   return 0;
 }
 
@@ -393,7 +455,7 @@ static int launch_rs_gf(lf_ctx* ctx, gf128* d_rows, size_t row_stride, size_t nr
   int rc = ctx_rs_plan(ctx, n, m, &ph);
   if (rc) return rc;
   size_t smem = 2 * (size_t)ph->plan.fftn * sizeof(gf128);
-  if (smem > 200 * 1024) return fail(LF_ERR_UNSUPPORTED, "rs: n > 4096 over GF(2^128) not built yet");
+  if (smem > 200 * 1024) return launch_rs_gf_global(ctx, d_rows, row_stride, nrows, batch_stride, nbatch, *ph);
   static bool attr_set = false;
   if (!attr_set) {
     LF_CUDA(cudaFuncSetAttribute(k_rs_gf_rows<FGf128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -508,11 +570,18 @@ static int ctx_rs_fp_tables(lf_ctx* ctx, size_t n, size_t m, RsFpTables** out) {
   return 0;
 }
 
+static int rs_conv_run_p256(lf_ctx* ctx, fpw<8>* d_rows, size_t row_stride, size_t nrows, size_t n, size_t m);
 static int launch_rs_p256(lf_ctx* ctx, fpw<8>* d_rows, size_t row_stride, size_t nrows, size_t batch_stride,
                           size_t nbatch, size_t n, size_t m) {
   if (n == 0 || m < n || m > (1u << 24)) return fail(LF_ERR_ARG, "rs: need 0 < n <= m <= 2^24");
   if (nrows == 0 || nbatch == 0 || m == n) return 0;
-  if (m > 6400) return fail(LF_ERR_UNSUPPORTED, "rs: m > 6400 over Fp256 needs a global-memory FFT (not built yet)");
+  if (m > 6400) {
+    for (size_t bi = 0; bi < nbatch; ++bi) {
+      int rc2 = rs_conv_run_p256(ctx, d_rows + bi * batch_stride, row_stride, nrows, n, m);
+      if (rc2) return rc2;
+    }
+    return 0;
+  }
   RsFpTables* t;
   int rc = ctx_rs_fp_tables(ctx, n, m, &t);
   if (rc) return rc;
@@ -686,6 +755,67 @@ static int rs_conv_run(lf_ctx* ctx, const H& Hf, typename F::Elt* d_rows, size_t
   if (rc == 0) {
     k_rs_finish<F><<<dim3((unsigned)((m - n + 255) / 256), (unsigned)nrows), 256, 0, ctx->stream>>>(
         d_rows, row_stride, x, (uint32_t)n, (uint32_t)m, (uint32_t)N, (const Elt*)t->d_lead);
+    ctx->launches++;
+    cudaError_t ce = cudaStreamSynchronize(ctx->stream);
+    if (ce != cudaSuccess) rc = fail(LF_ERR_CUDA, cudaGetErrorString(ce));
+  }
+  cudaFree(x);
+  return rc;
+}
+
+// P-256 rows too long for k_rs_fp_fft_rows: the same convolution with the real
+// row embedded in Fp2 (imaginary parts zero) and global-memory stage-group FFTs
+// over Fp2 (FFTExtConvolution, lib/algebra/convolution.h:128-191; exact, so the
+// real part of the result is the convolution).
+static int rs_conv_run_p256(lf_ctx* ctx, fpw<8>* d_rows, size_t row_stride, size_t nrows, size_t n, size_t m) {
+  typedef FFp256 F;
+  typedef AlgCx<F> A;
+  typedef Cx<F> CxE;
+  const P256Host& H = p256_host();
+  uint32_t logN = 0;
+  while (((size_t)1 << logN) < m) ++logN;
+  const size_t N = (size_t)1 << logN;
+  CxE* d_tw;
+  int rc = fft_twiddles_p256(ctx, logN, &d_tw);
+  if (rc) return rc;
+  auto key = std::make_pair((int)LF_FIELD_P256, std::make_pair(n, m));
+  auto it = ctx->rs_conv.find(key);
+  if (it == ctx->rs_conv.end()) {
+    std::vector<fpw<8>> inv, lead, binom;
+    rs_tables_host(H, n, m, inv, lead, binom);
+    fpw<8> nn = H.one();
+    for (uint32_t i = 0; i < logN; ++i) nn = H.add(nn, nn);
+    const fpw<8> ninv = H.inv(nn);
+    for (auto& v : lead) v = H.mul(v, ninv);
+    auto* t = new RsConvTables;
+    t->logN = logN;
+    std::vector<HCx> ypad(N, HCx{H.zero(), H.zero()});
+    for (size_t i = 0; i < inv.size(); ++i) ypad[i].re = inv[i];
+    LF_CUDA(cudaMalloc(&t->d_yh, N * sizeof(HCx)));
+    LF_CUDA(cudaMalloc(&t->d_lead, lead.size() * 32));
+    LF_CUDA(cudaMalloc(&t->d_binom, n * 32));
+    LF_CUDA(cudaMemcpy(t->d_yh, ypad.data(), N * sizeof(HCx), cudaMemcpyHostToDevice));
+    LF_CUDA(cudaMemcpy(t->d_lead, lead.data(), lead.size() * 32, cudaMemcpyHostToDevice));
+    LF_CUDA(cudaMemcpy(t->d_binom, binom.data(), n * 32, cudaMemcpyHostToDevice));
+    if ((rc = fft_run<A>(ctx, (CxE*)t->d_yh, 0, 1, logN, d_tw, /*inverse_root=*/true, /*dif=*/true, false))) return rc;
+    LF_CUDA(cudaStreamSynchronize(ctx->stream));
+    it = ctx->rs_conv.emplace(key, (void*)t).first;
+  }
+  auto* t = (RsConvTables*)it->second;
+  CxE* x;
+  LF_CUDA(cudaMalloc(&x, nrows * N * sizeof(CxE)));
+  k_rs_pad_cx<F><<<dim3((unsigned)((N + 255) / 256), (unsigned)nrows), 256, 0, ctx->stream>>>(
+      d_rows, row_stride, x, (uint32_t)n, (uint32_t)N, (const fpw<8>*)t->d_binom);
+  ctx->launches++;
+  if ((rc = fft_run<A>(ctx, x, N, nrows, logN, d_tw, true, true, false)) == 0) {
+    k_fft_pointwise<A><<<dim3((unsigned)((N + 255) / 256), (unsigned)nrows), 256, 0, ctx->stream>>>(
+        x, (const CxE*)t->d_yh, N);
+    ctx->launches++;
+    rc = fft_run<A>(ctx, x, N, nrows, logN, d_tw, false, false, false);
+  }
+  if (rc == 0) {
+    k_rs_finish_cx<F><<<dim3((unsigned)((m - n + 255) / 256), (unsigned)nrows), 256, 0, ctx->stream>>>(
+        d_rows, row_stride, x, (uint32_t)n, (uint32_t)m, (uint32_t)N, (const fpw<8>*)t->d_lead);
     ctx->launches++;
     cudaError_t ce = cudaStreamSynchronize(ctx->stream);
     if (ce != cudaSuccess) rc = fail(LF_ERR_CUDA, cudaGetErrorString(ce));
@@ -1110,6 +1240,39 @@ int fft_p256_t(lf_ctx* ctx, void* elts, size_t n, uint32_t logn, int forward, in
   cudaFree(d);
   return rc;
 }
+// GF(2^128): the additive FFT of LCH14 on the span of beta_0..beta_{l-1}, coset 0
+// (lch14.h:106-146): forward = evaluate the novel-basis coefficients, else IFFT
+int fft_gf_t(lf_ctx* ctx, void* elts, size_t n, uint32_t logn, int forward, int reps, double* ms) {
+  if (logn > 16) return fail(LF_ERR_ARG, "fft: the LCH14 subspace has dimension 16 (lch14.h:45-47), n <= 65536");
+  gf128* d = nullptr;
+  LF_CUDA(cudaMalloc(&d, n * sizeof(gf128)));
+  if (elts) {
+    LF_CUDA(cudaMemcpyAsync(d, elts, n * sizeof(gf128), cudaMemcpyHostToDevice, ctx->stream));
+  } else {
+    LF_CUDA(cudaMemsetAsync(d, 0x5a, n * sizeof(gf128), ctx->stream));
+  }
+  cudaEvent_t e0, e1;
+  LF_CUDA(cudaEventCreate(&e0));
+  LF_CUDA(cudaEventCreate(&e1));
+  LF_CUDA(cudaEventRecord(e0, ctx->stream));
+  int rc = 0;
+  for (int r = 0; r < reps && !rc; ++r) rc = launch_lch14_fft(ctx, d, logn, 0, forward != 0);
+  LF_CUDA(cudaEventRecord(e1, ctx->stream));
+  LF_CUDA(cudaEventSynchronize(e1));
+  if (ms) {
+    float t;
+    LF_CUDA(cudaEventElapsedTime(&t, e0, e1));
+    *ms = t / reps;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  if (!rc && elts) {
+    LF_CUDA(cudaMemcpyAsync(elts, d, n * sizeof(gf128), cudaMemcpyDeviceToHost, ctx->stream));
+    LF_CUDA(cudaStreamSynchronize(ctx->stream));
+  }
+  cudaFree(d);
+  return rc;
+}
 int fft_dispatch(lf_ctx* ctx, int field_id, void* elts, size_t n, int forward, int reps, double* ms) {
   if (n == 0 || (n & (n - 1))) return fail(LF_ERR_ARG, "fft: n must be a power of two");
   uint32_t logn = 0;
@@ -1120,7 +1283,8 @@ int fft_dispatch(lf_ctx* ctx, int field_id, void* elts, size_t n, int forward, i
     case LF_FIELD_FP128: return fft_scalar_t<FFp128>(ctx, fp128_host(), elts, n, logn, forward, reps, ms);
     case LF_FIELD_GOLDILOCKS: return fft_scalar_t<FFpGold>(ctx, gold_host(), elts, n, logn, forward, reps, ms);
     case LF_FIELD_P256: return fft_p256_t(ctx, elts, n, logn, forward, reps, ms);
-    default: return fail(LF_ERR_UNSUPPORTED, "fft: field has no FFT here (GF(2^128) uses the LCH14 transform inside RS)");
+    case LF_FIELD_GF2_128: return fft_gf_t(ctx, elts, n, logn, forward, reps, ms);
+    default: return fail(LF_ERR_UNSUPPORTED, "fft: unknown field");
   }
 }
 }  // namespace

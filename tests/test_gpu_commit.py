@@ -36,6 +36,29 @@ def test_rs_interpolate_matches_oracle(ctx, oracle, n, m):
     assert (got == want).all()
 
 
+@pytest.mark.parametrize("n,m", [(16384, 65536), (5000, 20000), (8192, 8200)])
+def test_rs_large_rows_match_oracle(ctx, oracle, n, m):
+    """rows whose first coset does not fit in shared memory take the one-launch-per-step
+    path (lch14_reed_solomon_test.cc:72-107 benchmarks 16384 -> 65536)"""
+    import longfellow_zk_b200 as lf
+    rs = np.random.default_rng(n + m)
+    rows = rs.integers(0, 256, (2, m, 16), dtype=np.uint8)
+    got = lf.LCH14ReedSolomonFactory(ctx).make(n, m).interpolate(rows)
+    assert (got == oracle.lch14_interpolate(n, m, rows)).all()
+
+
+@pytest.mark.parametrize("l", [0, 1, 5, 10, 16])
+def test_lch14_fft_matches_oracle(ctx, oracle, l):
+    """LCH14::FFT(l, 0, B) and ::IFFT through lf_fft (lch14.h:106-146; lch14_test.cc:199-243 runs l = 16)"""
+    rs = np.random.default_rng(100 + l)
+    n = 1 << l
+    B = rs.integers(0, 256, (n, 16), dtype=np.uint8)
+    ev = ctx.fft(GF, B, n, True)
+    assert (ev == oracle.lch14("fft", l, 0, B)).all()
+    assert (ctx.fft(GF, B, n, False) == oracle.lch14("ifft", l, 0, B)).all()
+    assert (ctx.fft(GF, ev, n, False) == B).all()  # IFFT o FFT = id
+
+
 def test_rs_is_linear_and_idempotent_at_scale(ctx):
     """size-independent properties on a production-sized batch (1024 rows)."""
     import longfellow_zk_b200 as lf

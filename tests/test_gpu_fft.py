@@ -72,6 +72,32 @@ def test_rs_matches_oracle(ctx, oracle, fid, n, m):
     assert (got == oracle.rs_interpolate(fid, n, m, rows)).all()
 
 
+@pytest.mark.parametrize("n,m", [(3300, 8000), (5000, 20000)])
+def test_rs_p256_large_rows_match_oracle(ctx, oracle, n, m):
+    """P-256 rows beyond the shared-memory real-FFT kernel (m > 6400): Fp2 convolution in global memory"""
+    import longfellow_zk_b200 as lf
+    rs = np.random.default_rng(n + m)
+    rows = rand_elts(rs, 1, m).reshape(1, m, 32)
+    got = lf.ReedSolomonFactory(ctx, 1).make(n, m).interpolate(rows)
+    assert (got == oracle.rs_interpolate(1, n, m, rows)).all()
+
+
+def test_rs_p256_benchmark_shape_is_consistent(ctx):
+    """ReedSolomon(65536, 262144) over Fp256 (reed_solomon_test.cc:337-401) is too slow for the
+    scalar oracle; check it through the code's defining property instead: the extension of a
+    polynomial of degree < n' <= n computed with (n, m) equals the one computed with (n', m)."""
+    import longfellow_zk_b200 as lf
+    rs = np.random.default_rng(77)
+    n, m, small = 65536, 262144, 455
+    base = rand_elts(rs, 1, 4096).reshape(1, 4096, 32)
+    cw = lf.ReedSolomonFactory(ctx, 1).make(small, 4096).interpolate(base)   # degree < 455 on 0..4095
+    cw = lf.ReedSolomonFactory(ctx, 1).make(4096, m).interpolate(
+        np.concatenate([cw, np.zeros((1, m - 4096, 32), np.uint8)], axis=1))  # the same polynomial on 0..m-1
+    again = cw.copy()
+    again[:, n:] = 0
+    assert (lf.ReedSolomonFactory(ctx, 1).make(n, m).interpolate(again) == cw).all()
+
+
 def test_fft_timing_reports(ctx):
     import json
     import os
