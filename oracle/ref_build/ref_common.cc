@@ -58,6 +58,10 @@
 #include "zk/zk_proof.h"
 #include "zk/zk_verifier.h"
 
+#ifdef LF_WITH_GPU_ADAPTERS
+#include "longfellow_b200_adapters.h"
+#endif
+
 namespace proofs {
 
 // RandomEngine that replays caller-supplied bytes, so that the reference and
@@ -552,5 +556,86 @@ double ref_zk_bench(void* handle,
   auto t1 = std::chrono::steady_clock::now();
   return std::chrono::duration<double>(t1 - t0).count();
 }
+
+#ifdef LF_WITH_GPU_ADAPTERS
+// ---- libref_gpu.so only: the reference driving the CUDA back end through
+// include/longfellow_b200_adapters.h (tests/test_gpu_adapters.py).  This is the
+// reference-side binding of INTEGRATION.md compiled for real.
+
+// (1) the UNMODIFIED reference ZkProver (sumcheck, Ligero, Merkle, transcript on
+//     the CPU) with the GPU Reed-Solomon injected at the interpolator-factory seam
+int ref_zk_prove_gpu_rs(void* handle, const uint8_t* wit, const uint8_t* rng, size_t rng_len,
+                        const uint8_t* tinit, size_t tinit_len, size_t rate, size_t nreq, uint8_t* out,
+                        size_t out_cap, size_t* out_len) {
+  auto* h = static_cast<CircuitHandle*>(handle);
+  lf_ctx* ctx = nullptr;
+  if (lf_ctx_create(0, nullptr, &ctx) != LF_OK) return -200;
+  int rc;
+  size_t used = 0;
+  if (h->field_id == GF2_128_ID) {
+    longfellow_b200::GpuReedSolomonFactory<GF> rsf(ctx, LF_FIELD_GF2_128, gf());
+    rc = zk_prove_t(gf(), rsf, h->gf.get(), wit, rng, rng_len, tinit, tinit_len, rate, nreq, 0, out, out_cap,
+                    out_len, &used, nullptr);
+  } else if (h->field_id == P256_ID) {
+    longfellow_b200::GpuReedSolomonFactory<Fp256Base> rsf(ctx, LF_FIELD_P256, p256_base);
+    rc = zk_prove_t(p256_base, rsf, h->p256.get(), wit, rng, rng_len, tinit, tinit_len, rate, nreq, 0, out,
+                    out_cap, out_len, &used, nullptr);
+  } else {
+    rc = -100;
+  }
+  lf_ctx_destroy(ctx);
+  return rc;
+}
+
+}  // extern "C"
+// (2) the whole prover replaced: GpuZkProver fed from the reference's Circuit,
+//     Dense witness and RandomEngine objects
+template <class Field>
+static int zk_prove_gpu_t(const Field& F, FieldID fid, const Circuit<Field>* c, const uint8_t* wit,
+                          const uint8_t* rng, size_t rng_len, const uint8_t* tinit, size_t tinit_len,
+                          size_t rate, size_t nreq, size_t copies, uint8_t* out, size_t out_cap,
+                          size_t* out_len) {
+  lf_ctx* ctx = nullptr;
+  if (lf_ctx_create(0, nullptr, &ctx) != LF_OK) return -200;
+  int rc = 0;
+  {
+    longfellow_b200::GpuZkProver<Field> prover(ctx, *c, F, fid, rate, nreq);
+    Dense<Field> W(1, c->ninputs);
+    for (size_t i = 0; i < c->ninputs; ++i) W.v_[i] = F.of_bytes_field(wit + i * Field::kBytes).value();
+    std::vector<const Dense<Field>*> Ws(copies, &W);
+    // every copy replays the same coins, so all proofs must be identical
+    std::vector<uint8_t> coins;
+    for (size_t i = 0; i < copies; ++i) coins.insert(coins.end(), rng, rng + prover.info().rng_bytes);
+    (void)rng_len;
+    BufferRandomEngine eng(coins.data(), coins.size());
+    std::vector<std::vector<uint8_t>> proofs;
+    std::vector<bool> ok = prover.prove_batch(Ws, tinit, tinit_len, eng, proofs);
+    for (size_t i = 0; i < copies; ++i) {
+      if (!ok[i]) rc = -3;
+      if (proofs[i] != proofs[0]) rc = -5;
+    }
+    if (rc == 0) {
+      *out_len = proofs[0].size();
+      if (proofs[0].size() > out_cap) rc = -4;
+      else memcpy(out, proofs[0].data(), proofs[0].size());
+    }
+  }
+  lf_ctx_destroy(ctx);
+  return rc;
+}
+extern "C" {
+int ref_zk_prove_gpu(void* handle, const uint8_t* wit, const uint8_t* rng, size_t rng_len, const uint8_t* tinit,
+                     size_t tinit_len, size_t rate, size_t nreq, size_t copies, uint8_t* out, size_t out_cap,
+                     size_t* out_len) {
+  auto* h = static_cast<CircuitHandle*>(handle);
+  if (h->field_id == GF2_128_ID)
+    return zk_prove_gpu_t(gf(), GF2_128_ID, h->gf.get(), wit, rng, rng_len, tinit, tinit_len, rate, nreq, copies,
+                          out, out_cap, out_len);
+  if (h->field_id == P256_ID)
+    return zk_prove_gpu_t(p256_base, P256_ID, h->p256.get(), wit, rng, rng_len, tinit, tinit_len, rate, nreq,
+                          copies, out, out_cap, out_len);
+  return -100;
+}
+#endif  // LF_WITH_GPU_ADAPTERS
 
 }  // extern "C"

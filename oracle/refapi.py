@@ -12,6 +12,8 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIBREF = os.path.join(_HERE, "_ref", "libref.so")
+# the same wrapper + include/longfellow_b200_adapters.h, linked against the CUDA back end
+LIBREF_GPU = os.path.join(_HERE, "_ref", "libref_gpu.so")
 
 GF2_128_ID = 4  # proto/circuit_io.h:24-36
 P256_ID = 1
@@ -40,6 +42,24 @@ def lib():
         _lib.ref_transcript_script.restype = C.c_size_t
         _lib.ref_circuit_info.restype = C.c_size_t
     return _lib
+
+
+_gpu_lib = None
+
+
+def gpu_adapters_available():
+    return os.path.exists(LIBREF_GPU)
+
+
+def gpu_lib():
+    """libref_gpu.so: the reference driving the CUDA back end through the C++ adapters."""
+    global _gpu_lib
+    if _gpu_lib is None:
+        _gpu_lib = C.CDLL(LIBREF_GPU)
+        _gpu_lib.ref_circuit_load.restype = C.c_void_p
+        _gpu_lib.ref_circuit_load.argtypes = [C.c_int, C.c_char_p, C.c_size_t]
+        _gpu_lib.ref_circuit_free.argtypes = [C.c_void_p]
+    return _gpu_lib
 
 
 def _u8(a):
@@ -236,6 +256,38 @@ class Circuit:
                                   C.c_size_t(rng.size), C.c_size_t(rate), C.c_size_t(nreq),
                                   C.c_size_t(nthreads), C.c_size_t(per_thread), lat)
         return float(secs), [float(x) for x in lat]
+
+
+class GpuAdapterCircuit:
+    """A reference Circuit object inside libref_gpu.so, proved (1) by the reference's own
+    ZkProver with GpuReedSolomonFactory injected, (2) by GpuZkProver."""
+
+    def __init__(self, field_id, circ_bytes):
+        self.h = gpu_lib().ref_circuit_load(C.c_int(field_id), C.c_char_p(circ_bytes), C.c_size_t(len(circ_bytes)))
+        if not self.h:
+            raise ValueError("reference CircuitReader rejected the circuit")
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            gpu_lib().ref_circuit_free(C.c_void_p(self.h))
+            self.h = None
+
+    def _call(self, fn, witness, rng, tinit, rate, nreq, *extra):
+        rng = _u8(np.frombuffer(rng, np.uint8) if isinstance(rng, (bytes, bytearray)) else rng)
+        out = np.zeros(1 << 21, np.uint8)
+        out_len = C.c_size_t()
+        rc = fn(C.c_void_p(self.h), C.c_char_p(witness), _p(rng), C.c_size_t(rng.size), C.c_char_p(tinit),
+                C.c_size_t(len(tinit)), C.c_size_t(rate), C.c_size_t(nreq), *extra, _p(out), C.c_size_t(out.size),
+                C.byref(out_len))
+        if rc != 0:
+            raise RuntimeError(f"adapter prover failed rc={rc}")
+        return out[:out_len.value].tobytes()
+
+    def prove_reference_with_gpu_rs(self, witness, rng, tinit=b"test", rate=7, nreq=132):
+        return self._call(gpu_lib().ref_zk_prove_gpu_rs, witness, rng, tinit, rate, nreq)
+
+    def prove_gpu(self, witness, rng, tinit=b"test", rate=7, nreq=132, copies=1):
+        return self._call(gpu_lib().ref_zk_prove_gpu, witness, rng, tinit, rate, nreq, C.c_size_t(copies))
 
 
 def fft(fid, data, n, fwd=False):
