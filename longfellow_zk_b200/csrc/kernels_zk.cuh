@@ -10,6 +10,7 @@
 //   ZkCommon::verifier_constraints + LigeroProver::prove k_lig_*
 //   ZkProof::write (zk/zk_proof.h:90-184)                k_zk_serialize
 #pragma once
+#include <cooperative_groups.h>
 #include <stdint.h>
 
 #include "field.cuh"
@@ -257,6 +258,11 @@ struct ScShared {
   typename F::Elt r, alpha, beta, sum, wc[2];
   typename F::Elt* hp;  // [blockDim.x] head partials of the segmented sums
   uint32_t* hr;         // [blockDim.x] their segment ids
+  // cluster mode (one proof on several SMs): per-CTA results that the other CTAs
+  // of the cluster read through distributed shared memory
+  typename F::Elt lead_val;      // sum of the leading run of head partials of this CTA ...
+  uint32_t lead_seg;             // ... and its segment id (kNone if the CTA starts a segment)
+  typename F::Elt cred[2][16];   // leader only: a0 / a2 partial of every CTA
   AesTables aes;        // AES S-box and round tables staged in shared memory
   int fail;
   long long prof[8];    // LF_PROF: cycles of thread 0 per phase
@@ -274,20 +280,52 @@ __device__ __forceinline__ typename F::Elt warp_sum(typename F::Elt s) {
   return s;
 }
 
+// Work distribution of one proof: CL == false, one CTA (tid/nth); CL == true, a
+// thread-block cluster of C CTAs on C SMs, gtid/gnth run over all of them,
+// barriers are cluster barriers and the leader CTA (rank 0) owns the transcript.
+template <bool CL>
+struct ScPar {
+  uint32_t tid, nth, rank, ncta, gtid, gnth;
+  __device__ __forceinline__ ScPar() {
+    tid = threadIdx.x;
+    nth = blockDim.x;
+    if (CL) {
+      cooperative_groups::cluster_group cl = cooperative_groups::this_cluster();
+      rank = cl.block_rank();
+      ncta = cl.num_blocks();
+    } else {
+      rank = 0;
+      ncta = 1;
+    }
+    gtid = rank * nth + tid;
+    gnth = ncta * nth;
+  }
+  __device__ __forceinline__ void sync() const {
+    if (CL) cooperative_groups::this_cluster().sync();  // release/acquire: orders global memory too
+    else __syncthreads();
+  }
+  template <class T>
+  __device__ __forceinline__ T* remote(T* p, uint32_t r) const {
+    if (CL) return cooperative_groups::this_cluster().map_shared_rank(p, r);
+    return p;
+  }
+};
+
 // out[seg] = sum over the entries e of that segment of term(e); seg[] is
 // non-decreasing over e in [0, n).  Segments without entries are not touched.
-// Contains two __syncthreads(); all threads of the CTA must call it.
+// Contains barriers; all threads of the proof must call it.
 // fetch(e) loads the operands of entry e; accum(acc, ops) adds the entry's term.
 // (Issuing the loads one entry ahead was tried and measured slower: the kernel
 // is bound by the multiply pipes and barriers, not by load latency.)
-template <class F, class Fetch, class Accum>
-__device__ __forceinline__ void seg_sum(ScShared<F>* sh, uint32_t n, const uint32_t* __restrict__ seg,
-                                        typename F::Elt* __restrict__ out, Fetch fetch, Accum accum) {
+template <class F, bool CL, class Fetch, class Accum>
+__device__ __forceinline__ void seg_sum(ScShared<F>* sh, const ScPar<CL>& P, uint32_t n,
+                                        const uint32_t* __restrict__ seg, typename F::Elt* __restrict__ out,
+                                        Fetch fetch, Accum accum) {
   typedef typename F::Elt Elt;
   typedef typename F::Acc Acc;
-  const uint32_t tid = threadIdx.x, nth = blockDim.x;
-  const uint32_t per = (n + nth - 1) / nth;
-  const uint32_t e0 = min(n, tid * per), e1 = min(n, e0 + per);
+  const uint32_t tid = P.tid, nth = P.nth;
+  const uint32_t per = (n + P.gnth - 1) / P.gnth;
+  const uint32_t e0 = min(n, P.gtid * per), e1 = min(n, e0 + per);
   const uint32_t kNone = 0xffffffffu;
   sh->hr[tid] = kNone;
   uint32_t own_last = kNone;  // segment whose start this slice owns and which is still open at e1
@@ -341,6 +379,20 @@ __device__ __forceinline__ void seg_sum(ScShared<F>* sh, uint32_t n, const uint3
     sh->hp[tid] = v;  // each thread rewrites only its own slot
   }
   __syncthreads();
+  if (CL) {
+    // a segment that began in an earlier CTA: this CTA's share of it is the run of
+    // head partials starting at thread 0; its owner (in an earlier CTA) collects it
+    if (tid == 0) {
+      const uint32_t ls = sh->hr[0];
+      sh->lead_seg = ls;
+      if (ls != kNone) {
+        Elt v = sh->hp[0];
+        for (uint32_t t = 32; t < nth && sh->hr[t] == ls; t += 32) v = F::add(v, sh->hp[t]);
+        sh->lead_val = v;
+      }
+    }
+    P.sync();
+  }
   if (own_last != kNone) {
     Elt v = out[own_last];
     uint32_t t = tid + 1;
@@ -348,9 +400,16 @@ __device__ __forceinline__ void seg_sum(ScShared<F>* sh, uint32_t n, const uint3
       v = F::add(v, sh->hp[t]);  // sum of this warp's part of the run starting at t
       t = (t | 31u) + 1;         // first thread of the next warp
     }
+    if (CL && t >= nth) {
+      for (uint32_t c = P.rank + 1; c < P.ncta; ++c) {
+        const ScShared<F>* rs = P.remote(sh, c);
+        if (rs->lead_seg != own_last) break;
+        v = F::add(v, rs->lead_val);
+      }
+    }
     out[own_last] = v;
   }
-  __syncthreads();
+  P.sync();
 }
 
 // serial part of one round, thread 0 only (prover_layers.h:244-251,320-329,
@@ -430,10 +489,12 @@ __device__ __noinline__ void sc_end_layer(ScShared<F>* sh, typename F::Elt hquad
   ts_array_elt<F>(&sh->ts, t1);
 }
 
-// The kernel body is shared by two launch configurations (throughput: many
-// small CTAs per SM so that one proof's serial transcript hides under the
-// others' parallel work; latency: one large CTA per proof).
-template <class F>
+// The kernel body is shared by the launch configurations below (throughput:
+// many small CTAs per SM so that one proof's serial transcript hides under the
+// others' parallel work; latency: one large CTA per proof, or -- CL -- a
+// thread-block cluster per proof, the parallel phases spread over its SMs and
+// the leader CTA's thread 0 running the transcript).
+template <class F, bool CL>
 __device__ __forceinline__ void sumcheck_body(const ZkDims& d, const ZkBufs<typename F::Elt>& b,
                                               const uint32_t* __restrict__ arena,
                                               const LayerDesc* __restrict__ layers,
@@ -441,9 +502,13 @@ __device__ __forceinline__ void sumcheck_body(const ZkDims& d, const ZkBufs<type
                                               const typename F::Elt* __restrict__ consts, ScShared<F>& sh) {
   typedef typename F::Elt Elt;
   typedef typename F::Acc Acc;
-  const size_t p = blockIdx.x;
-  const uint32_t tid = threadIdx.x, nth = blockDim.x;
-  if (b.status[p] != 0) return;  // witness already rejected by eval_circuit
+  const ScPar<CL> P;
+  const size_t p = CL ? blockIdx.x / P.ncta : blockIdx.x;
+  const uint32_t tid = P.tid, nth = P.nth, gtid = P.gtid, gnth = P.gnth;
+  const bool leader = gtid == 0;  // thread 0 of the (leader) CTA: the transcript thread
+  if (b.status[p] != 0) return;   // witness already rejected by eval_circuit (uniform over the proof)
+  // the leader CTA's shared state, as seen from this CTA
+  const ScShared<F>* lead = P.remote(&sh, 0);
 
   Elt* wl = b.wl + p * d.wl_elts;
   Elt* whbuf = b.wh + p * 4 * (size_t)d.max_nw;
@@ -456,45 +521,45 @@ __device__ __forceinline__ void sumcheck_body(const ZkDims& d, const ZkBufs<type
   Elt* hbs = b.hb + p * d.nhb;
 
   aes_stage_tables(&sh.aes);
-  if (tid == 0) {
+  if (leader) {
     for (int i = 0; i < 8; ++i) sh.prof[i] = 0;
     sh.prof[3] = clock64();
+    sc_begin<F>(&sh, reinterpret_cast<const Transcript*>(b.ts + p * sizeof(Transcript)));
   }
-  if (tid == 0) sc_begin<F>(&sh, reinterpret_cast<const Transcript*>(b.ts + p * sizeof(Transcript)));
-  __syncthreads();
+  P.sync();
 
   uint32_t logv = d.logv;
   for (uint32_t ly = 0; ly < d.nl; ++ly) {
     const LayerDesc L = layers[ly];
-    if (tid == 0) {
+    if (leader) {
       sc_begin_layer<F>(&sh, &b.alphas[p * d.nl + ly]);
       E0[0] = F::one();
       E1[0] = sh.alpha;
     }
-    __syncthreads();
+    P.sync();
     // EQ tables: E0[i] = EQ(G0, i), E1[i] = alpha * EQ(G1, i)  (eqs.h:46-78)
     for (uint32_t l = 0; l < logv; ++l) {
       const uint32_t S = 1u << l;
-      const Elt g0 = sh.G[0][l], g1 = sh.G[1][l];
-      for (uint32_t i = tid; i < 2 * S; i += nth) {
-        uint32_t k = i & (S - 1);
+      const Elt g0 = lead->G[0][l], g1 = lead->G[1][l];
+      for (uint32_t i = gtid; i < 2 * S; i += gnth) {
+        uint32_t kk = i & (S - 1);
         Elt* E = (i < S) ? E0 : E1;
-        Elt v = E[k], hi = F::mul(v, (i < S) ? g0 : g1);
-        E[k] = F::sub(v, hi);
-        E[k + S] = hi;
+        Elt v = E[kk], hi = F::mul(v, (i < S) ? g0 : g1);
+        E[kk] = F::sub(v, hi);
+        E[kk + S] = hi;
       }
-      __syncthreads();
+      P.sync();
     }
     // Quad::bind_g (quad.h:152-185): initial HQuad values, one segment per corner
     {
       const uint32_t *tg = arena + L.bg_g, *tv = arena + L.bg_vi;
-      const Elt beta = sh.beta;
+      const Elt beta = lead->beta;
       struct BgOps {
         Elt e0, e1, c;
         uint32_t v;
       };
-      seg_sum<F>(
-          &sh, L.nterms, arena + L.bg_seg, hqbuf,
+      seg_sum<F, CL>(
+          &sh, P, L.nterms, arena + L.bg_seg, hqbuf,
           [&](uint32_t t) {
             uint32_t g = tg[t], v = tv[t];
             BgOps o;
@@ -525,14 +590,14 @@ __device__ __forceinline__ void sumcheck_body(const ZkDims& d, const ZkBufs<type
       // QW[l] = sum_r Q[l,r] W[r]  (prover_layers.h:230-243)
       {
         const uint32_t* roff = arena + S.row_off;
-        for (uint32_t i = tid; i < S.n0; i += nth)
+        for (uint32_t i = gtid; i < S.n0; i += gnth)
           if (roff[i] == roff[i + 1]) QW[i] = F::zero();
         const uint32_t *rc = arena + S.row_c, *rp = arena + S.row_p1;
         struct QwOps {
           Elt q, w;
         };
-        seg_sum<F>(
-            &sh, S.n_in, arena + S.row_r, QW,
+        seg_sum<F, CL>(
+            &sh, P, S.n_in, arena + S.row_r, QW,
             [&](uint32_t e) {
               QwOps o;
               o.q = HQ[rc[e]];
@@ -547,7 +612,7 @@ __device__ __forceinline__ void sumcheck_body(const ZkDims& d, const ZkBufs<type
         Acc a0, a2;
         F::acc_zero(a0);
         F::acc_zero(a2);
-        for (uint32_t i = tid; i < npair; i += nth) {
+        for (uint32_t i = gtid; i < npair; i += gnth) {
           Elt qw0 = QW[2 * i], w0 = Wh[2 * i];
           // odd tail (prover_layers.h:377-384): a2 += qw0*w0 = (0-qw0)*(0-w0)
           const bool two = 2 * i + 1 < S.n0;
@@ -560,14 +625,27 @@ __device__ __forceinline__ void sumcheck_body(const ZkDims& d, const ZkBufs<type
           sh.red[0][tid >> 5] = s0;
           sh.red[1][tid >> 5] = s2;
         }
+        __syncthreads();
+        // warp 0 folds the CTA's warps and hands the pair to the leader CTA
+        if (tid < 32) {
+          const uint32_t nw = nth >> 5;
+          Elt r0 = tid < nw ? sh.red[0][tid] : F::zero(), r2 = tid < nw ? sh.red[1][tid] : F::zero();
+          r0 = warp_sum<F>(r0);
+          r2 = warp_sum<F>(r2);
+          if (tid == 0) {
+            ScShared<F>* ld = P.remote(&sh, 0);
+            ld->cred[0][P.rank] = r0;
+            ld->cred[1][P.rank] = r2;
+          }
+        }
       }
-      __syncthreads();
+      P.sync();
       long long tp0 = clock64();
-      if (tid == 0) {
-        Elt s0 = sh.red[0][0], s2 = sh.red[1][0];
-        for (uint32_t k = 1; k < nth / 32; ++k) {
-          s0 = F::add(s0, sh.red[0][k]);
-          s2 = F::add(s2, sh.red[1][k]);
+      if (leader) {
+        Elt s0 = sh.cred[0][0], s2 = sh.cred[1][0];
+        for (uint32_t c = 1; c < P.ncta; ++c) {
+          s0 = F::add(s0, sh.cred[0][c]);
+          s2 = F::add(s2, sh.cred[1][c]);
         }
         // pad order: (round, hand, k in {0,2}); proof order: (round, k, hand)
         sc_round_serial<F>(&sh, s0, s2, pad + 4 * round + 2 * hand, sc + L.sc_off + 4 * round + hand,
@@ -576,11 +654,11 @@ __device__ __forceinline__ void sumcheck_body(const ZkDims& d, const ZkBufs<type
         sh.prof[0] += clock64() - tp0;
         sh.prof[1] += 1;
       }
-      __syncthreads();
-      const Elt r = sh.r;
+      P.sync();
+      const Elt r = lead->r;
       // Dense::bind (dense.h:70-89)
       Elt* Wn = whbuf + (size_t)(2 * hand + (hand ? wpar1 : wpar0)) * d.max_nw;
-      for (uint32_t i = tid; i < npair; i += nth) {
+      for (uint32_t i = gtid; i < npair; i += gnth) {
         // affine_interpolation_nz_z(r, f0) == affine_interpolation(r, f0, 0) (affine.h:25-52)
         Elt f0 = Wh[2 * i], f1 = (2 * i + 1 < S.n0) ? Wh[2 * i + 1] : F::zero();
         Wn[i] = affine<F>(r, f0, f1);
@@ -588,7 +666,7 @@ __device__ __forceinline__ void sumcheck_body(const ZkDims& d, const ZkBufs<type
       // HQuad::bind_h (hquad.h:89-123) through the merge plan
       Elt* HQn = hqbuf + (size_t)(hqpar ^ 1) * d.max_hq;
       const uint32_t* mg = arena + S.merge;
-      for (uint32_t j = tid; j < S.n_out; j += nth) {
+      for (uint32_t j = gtid; j < S.n_out; j += gnth) {
         // pair: (v0, v1); lone even corner: (v0, 0); lone odd corner: (0, v0) -- the
         // three affine_interpolation variants of hquad.h:99-115 are one formula
         uint32_t m = mg[j], src = m >> 2, kind = m & 3;
@@ -597,7 +675,7 @@ __device__ __forceinline__ void sumcheck_body(const ZkDims& d, const ZkBufs<type
         Elt f1 = kind == 0 ? HQ[src + 1] : (kind == 2 ? v : F::zero());
         HQn[j] = affine<F>(r, f0, f1);
       }
-      __syncthreads();
+      P.sync();
       if (hand) {
         wcur1 = Wn;
         wpar1 ^= 1;
@@ -608,13 +686,13 @@ __device__ __forceinline__ void sumcheck_body(const ZkDims& d, const ZkBufs<type
       hqpar ^= 1;
     }
     // end of layer (prover_layers.h:263-270,331-344)
-    if (tid == 0)
+    if (leader)
       sc_end_layer<F>(&sh, hqbuf[(size_t)hqpar * d.max_hq], wcur0[0], wcur1[0], pad + 4 * L.logw,
                       sc + L.sc_off + 4 * L.logw, &b.bq[p * d.nl + ly]);
-    __syncthreads();
+    P.sync();
     logv = L.logw;
   }
-  if (tid == 0) {
+  if (leader) {
     *reinterpret_cast<Transcript*>(b.ts + p * sizeof(Transcript)) = sh.ts;
     if (sh.fail) b.status[p] = -100;  // internal inconsistency: never expected
     sh.prof[2] = clock64() - sh.prof[3];
@@ -623,11 +701,12 @@ __device__ __forceinline__ void sumcheck_body(const ZkDims& d, const ZkBufs<type
   }
 }
 
-// One kernel body, three shapes.  NT threads per proof, MINB resident CTAs per SM:
+// One kernel body, four shapes.  NT threads per CTA, MINB resident CTAs per SM:
 //   <128, 8>  throughput (default): 8 proofs per SM in flight
-//   < 64,16>  throughput for very large batches: 16 proofs per SM, so that fewer
-//             warps idle at barriers while thread 0 of a CTA runs the transcript
+//   < 64,16>  16 proofs per SM (LF_SC_THREADS=64; measured no faster)
 //   <1024,1>  latency: one CTA per proof on its own SM
+//   cluster   latency, very few proofs: a thread-block cluster of 8 or 16 CTAs
+//             (one per SM) per proof; launched with cudaLaunchKernelEx
 constexpr int kScTpThreads = 128;
 template <class F, int NT, int MINB>
 __global__ void __launch_bounds__(NT, MINB)
@@ -642,7 +721,23 @@ k_zk_sumcheck(ZkDims d, ZkBufs<typename F::Elt> b, const uint32_t* __restrict__ 
     sh.hr = hr;
   }
   __syncthreads();
-  sumcheck_body<F>(d, b, arena, layers, steps, consts, sh);
+  sumcheck_body<F, false>(d, b, arena, layers, steps, consts, sh);
+}
+constexpr int kScClThreads = 512;
+template <class F>
+__global__ void __launch_bounds__(kScClThreads, 1)
+k_zk_sumcheck_cluster(ZkDims d, ZkBufs<typename F::Elt> b, const uint32_t* __restrict__ arena,
+                      const LayerDesc* __restrict__ layers, const StepDesc* __restrict__ steps,
+                      const typename F::Elt* __restrict__ consts) {
+  __shared__ ScShared<F> sh;
+  __shared__ typename F::Elt hp[kScClThreads];
+  __shared__ uint32_t hr[kScClThreads];
+  if (threadIdx.x == 0) {
+    sh.hp = hp;
+    sh.hr = hr;
+  }
+  __syncthreads();
+  sumcheck_body<F, true>(d, b, arena, layers, steps, consts, sh);
 }
 
 // ----------------------------------------------------------------------------
