@@ -249,6 +249,7 @@ k_zk_eval_layer(ZkDims d, ZkBufs<typename F::Elt> b, const uint32_t* __restrict_
 // sums, so the regrouping cannot change the result.
 // ----------------------------------------------------------------------------
 constexpr int kScMaxThreads = 1024;
+constexpr uint32_t kScSoloWork = 1536;  // cluster mode: steps with n_in + n0 below this run on the leader CTA alone
 
 template <class F>
 struct ScShared {
@@ -286,27 +287,39 @@ __device__ __forceinline__ typename F::Elt warp_sum(typename F::Elt s) {
 template <bool CL>
 struct ScPar {
   uint32_t tid, nth, rank, ncta, gtid, gnth;
+  bool cl;  // barriers and work distribution span the cluster (else: this CTA alone)
   __device__ __forceinline__ ScPar() {
     tid = threadIdx.x;
     nth = blockDim.x;
     if (CL) {
-      cooperative_groups::cluster_group cl = cooperative_groups::this_cluster();
-      rank = cl.block_rank();
-      ncta = cl.num_blocks();
+      cooperative_groups::cluster_group cg = cooperative_groups::this_cluster();
+      rank = cg.block_rank();
+      ncta = cg.num_blocks();
     } else {
       rank = 0;
       ncta = 1;
     }
+    cl = CL;
     gtid = rank * nth + tid;
     gnth = ncta * nth;
   }
+  // the same CTA working alone (leader CTA of a cluster during the small steps)
+  __device__ __forceinline__ ScPar solo() const {
+    ScPar s = *this;
+    s.rank = 0;
+    s.ncta = 1;
+    s.gtid = tid;
+    s.gnth = nth;
+    s.cl = false;
+    return s;
+  }
   __device__ __forceinline__ void sync() const {
-    if (CL) cooperative_groups::this_cluster().sync();  // release/acquire: orders global memory too
+    if (CL && cl) cooperative_groups::this_cluster().sync();  // release/acquire: orders global memory too
     else __syncthreads();
   }
   template <class T>
   __device__ __forceinline__ T* remote(T* p, uint32_t r) const {
-    if (CL) return cooperative_groups::this_cluster().map_shared_rank(p, r);
+    if (CL && cl) return cooperative_groups::this_cluster().map_shared_rank(p, r);
     return p;
   }
 };
@@ -379,7 +392,7 @@ __device__ __forceinline__ void seg_sum(ScShared<F>* sh, const ScPar<CL>& P, uin
     sh->hp[tid] = v;  // each thread rewrites only its own slot
   }
   __syncthreads();
-  if (CL) {
+  if (CL && P.cl) {
     // a segment that began in an earlier CTA: this CTA's share of it is the run of
     // head partials starting at thread 0; its owner (in an earlier CTA) collects it
     if (tid == 0) {
@@ -400,7 +413,7 @@ __device__ __forceinline__ void seg_sum(ScShared<F>* sh, const ScPar<CL>& P, uin
       v = F::add(v, sh->hp[t]);  // sum of this warp's part of the run starting at t
       t = (t | 31u) + 1;         // first thread of the next warp
     }
-    if (CL && t >= nth) {
+    if (CL && P.cl && t >= nth) {
       for (uint32_t c = P.rank + 1; c < P.ncta; ++c) {
         const ScShared<F>* rs = P.remote(sh, c);
         if (rs->lead_seg != own_last) break;
@@ -503,9 +516,11 @@ __device__ __forceinline__ void sumcheck_body(const ZkDims& d, const ZkBufs<type
   typedef typename F::Elt Elt;
   typedef typename F::Acc Acc;
   const ScPar<CL> P;
+  const ScPar<CL> Psolo = P.solo();
   const size_t p = CL ? blockIdx.x / P.ncta : blockIdx.x;
-  const uint32_t tid = P.tid, nth = P.nth, gtid = P.gtid, gnth = P.gnth;
-  const bool leader = gtid == 0;  // thread 0 of the (leader) CTA: the transcript thread
+  const uint32_t tid = P.tid, nth = P.nth;
+  uint32_t gtid = P.gtid, gnth = P.gnth;
+  const bool leader = P.gtid == 0;  // thread 0 of the (leader) CTA: the transcript thread
   if (b.status[p] != 0) return;   // witness already rejected by eval_circuit (uniform over the proof)
   // the leader CTA's shared state, as seen from this CTA
   const ScShared<F>* lead = P.remote(&sh, 0);
@@ -581,9 +596,19 @@ __device__ __forceinline__ void sumcheck_body(const ZkDims& d, const ZkBufs<type
     uint32_t hqpar = 0;
     const Elt* pad = wit + d.n_witness + L.pad_off;
 
+    bool solo = false;
     for (uint32_t t = 0; t < 2 * L.logw; ++t) {
       const StepDesc S = steps[L.step0 + t];
       const uint32_t hand = t & 1, round = t >> 1;
+      // Cluster mode: once a layer's steps are small, a cluster-wide phase costs
+      // more (barrier + an L2 round trip per phase, ~2 us) than its work; the
+      // leader CTA then finishes the layer alone with CTA barriers and the other
+      // CTAs wait at the end-of-layer barrier.  (Steps only shrink within a layer.)
+      if (CL && !solo && S.n_in + S.n0 <= d.solo_work) solo = true;
+      if (CL && solo && P.rank != 0) continue;  // pointer bookkeeping below is only needed by the leader
+      const ScPar<CL>& Q = (CL && solo) ? Psolo : P;
+      gtid = Q.gtid;
+      gnth = Q.gnth;
       const Elt* Wh = hand ? wcur1 : wcur0;
       const Elt* Wo = hand ? wcur0 : wcur1;
       const Elt* HQ = hqbuf + (size_t)hqpar * d.max_hq;
@@ -597,7 +622,7 @@ __device__ __forceinline__ void sumcheck_body(const ZkDims& d, const ZkBufs<type
           Elt q, w;
         };
         seg_sum<F, CL>(
-            &sh, P, S.n_in, arena + S.row_r, QW,
+            &sh, Q, S.n_in, arena + S.row_r, QW,
             [&](uint32_t e) {
               QwOps o;
               o.q = HQ[rc[e]];
@@ -633,17 +658,17 @@ __device__ __forceinline__ void sumcheck_body(const ZkDims& d, const ZkBufs<type
           r0 = warp_sum<F>(r0);
           r2 = warp_sum<F>(r2);
           if (tid == 0) {
-            ScShared<F>* ld = P.remote(&sh, 0);
-            ld->cred[0][P.rank] = r0;
-            ld->cred[1][P.rank] = r2;
+            ScShared<F>* ld = Q.remote(&sh, 0);
+            ld->cred[0][Q.rank] = r0;
+            ld->cred[1][Q.rank] = r2;
           }
         }
       }
-      P.sync();
+      Q.sync();
       long long tp0 = clock64();
       if (leader) {
         Elt s0 = sh.cred[0][0], s2 = sh.cred[1][0];
-        for (uint32_t c = 1; c < P.ncta; ++c) {
+        for (uint32_t c = 1; c < Q.ncta; ++c) {
           s0 = F::add(s0, sh.cred[0][c]);
           s2 = F::add(s2, sh.cred[1][c]);
         }
@@ -654,8 +679,8 @@ __device__ __forceinline__ void sumcheck_body(const ZkDims& d, const ZkBufs<type
         sh.prof[0] += clock64() - tp0;
         sh.prof[1] += 1;
       }
-      P.sync();
-      const Elt r = lead->r;
+      Q.sync();
+      const Elt r = Q.remote(&sh, 0)->r;
       // Dense::bind (dense.h:70-89)
       Elt* Wn = whbuf + (size_t)(2 * hand + (hand ? wpar1 : wpar0)) * d.max_nw;
       for (uint32_t i = gtid; i < npair; i += gnth) {
@@ -675,7 +700,7 @@ __device__ __forceinline__ void sumcheck_body(const ZkDims& d, const ZkBufs<type
         Elt f1 = kind == 0 ? HQ[src + 1] : (kind == 2 ? v : F::zero());
         HQn[j] = affine<F>(r, f0, f1);
       }
-      P.sync();
+      Q.sync();
       if (hand) {
         wcur1 = Wn;
         wpar1 ^= 1;
@@ -685,6 +710,8 @@ __device__ __forceinline__ void sumcheck_body(const ZkDims& d, const ZkBufs<type
       }
       hqpar ^= 1;
     }
+    gtid = P.gtid;
+    gnth = P.gnth;
     // end of layer (prover_layers.h:263-270,331-344)
     if (leader)
       sc_end_layer<F>(&sh, hqbuf[(size_t)hqpar * d.max_hq], wcur0[0], wcur1[0], pad + 4 * L.logw,

@@ -66,6 +66,7 @@ struct ZkDims {
   uint32_t max_proof_bytes;
   uint32_t tinit_len;
   uint32_t debug_stop;  // LF_DEBUG_STOP: early exit point inside k_lig_finish (bisecting)
+  uint32_t solo_work;   // cluster sumcheck: steps with n_in + n0 <= this run on the leader CTA alone
 };
 
 // per-proof device buffers: base pointer + stride (in elements of the pointee)
