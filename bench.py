@@ -9,10 +9,15 @@ A step = one batch of B independent proofs (fresh witness buffer, RNG bytes and
 transcript per proof) through the whole prover hot path: tableau layout, RS row
 encode, Merkle commit, on-device Fiat-Shamir transcript, eval_circuit, the layered
 sumcheck, Ligero prove and proof serialization.  `value` = proofs/s with inputs
-and outputs resident in HBM (CUDA events on the launching stream, max over
-ranks); `e2e` = the same through the C-ABI call with pinned HOST buffers, H2D and
-D2H inside the timed region.  Independent proofs shard across GPUs with no
-collective (weak scaling: B proofs per GPU).
+and outputs resident in HBM: the K steps are issued alternately on two
+contexts/streams (so one batch's thinly parallel kernels run under the other's
+sumcheck) and timed by one CUDA-event interval that encloses all of them, max
+over ranks; `streams.one_stream` is the same K steps back to back on one stream.
+`e2e` = the same through the host-pointer C-ABI call (lf_zk_prove_batch) with
+pinned HOST buffers, H2D and D2H inside the timed region, two batches in flight
+from two host threads; `e2e.one_batch_at_a_time` is the strictly serial figure.
+Independent proofs shard across GPUs with no collective (weak scaling: B proofs
+per GPU).
 """
 import argparse
 import json
@@ -185,6 +190,18 @@ def measure_other(lf, ctx, stream, workload, B, steps=3):
     dev()
     stages = prover.stage_ms()
     prover.set_profiling(False)
+    # single-proof latency (batch of one, device resident)
+    def one():
+        prover.prove_batch_ptr(1, d_wit.data_ptr(), d_rng.data_ptr(), rstride, d_out.data_ptr(), pb,
+                               d_len.data_ptr(), d_st.data_ptr(), device=True)
+    for _ in range(2):
+        one()
+    e0.record(stream)
+    for _ in range(5):
+        one()
+    e1.record(stream)
+    torch.cuda.synchronize()
+    lat1 = e0.elapsed_time(e1) / 5
     host()
     t0 = time.perf_counter()
     for _ in range(2):
@@ -192,7 +209,7 @@ def measure_other(lf, ctx, stream, workload, B, steps=3):
     t1 = time.perf_counter()
     assert int(h_st.abs().sum().item()) == 0
     return dict(workload=desc, proofs_per_step=B, value=B * steps / (ms * 1e-3), unit=UNIT,
-                e2e=dict(value=2 * B / (t1 - t0), unit=UNIT), stage_ms=stages,
+                e2e=dict(value=2 * B / (t1 - t0), unit=UNIT), stage_ms=stages, latency_ms_per_proof_batch1=lat1,
                 proof_bytes=int(d_len[0].item()), total_mults_per_proof=info["total_mults"])
 
 
@@ -242,6 +259,40 @@ def run_ours(args):
         prover.prove_batch_ptr(B, d_wit.data_ptr(), d_rng.data_ptr(), rstride, d_out.data_ptr(), pb,
                                d_len.data_ptr(), d_st.data_ptr(), device=True)
 
+    # A second context on its own stream: consecutive steps (batches) alternate between the two
+    # streams, so the thinly parallel kernels of one batch (zero-block hashing of the transcript,
+    # proof serialisation, Merkle tree top) run under the other batch's sumcheck.
+    stream2 = torch.cuda.Stream()
+    ctx2 = lf.Context(local, stream=stream2.cuda_stream)
+    prover2 = lf.ZkProver(lf.Circuit(ctx2, lf.FIELD_GF2_128, circ))
+    d_out2 = torch.empty((B, pb), dtype=torch.uint8, device="cuda")
+    d_len2 = torch.zeros(B, dtype=torch.int64, device="cuda")
+    d_st2 = torch.zeros(B, dtype=torch.int32, device="cuda")
+
+    def step_dev2():
+        prover2.prove_batch_ptr(B, d_wit.data_ptr(), d_rng.data_ptr(), rstride, d_out2.data_ptr(), pb,
+                                d_len2.data_ptr(), d_st2.data_ptr(), device=True)
+
+    def timed_two_streams(steps):
+        """K steps issued alternately on the two streams; one CUDA-event interval on `stream`
+        that starts before the first launch on either stream and ends after the last on both."""
+        barrier()
+        e0, e1, ej = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True),
+                      torch.cuda.Event())
+        e0.record(stream)
+        stream2.wait_event(e0)
+        for i in range(steps):
+            (step_dev2 if i & 1 else step_dev)()
+        ej.record(stream2)
+        stream.wait_event(ej)
+        e1.record(stream)
+        torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
+        if dist is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        barrier()
+        return float(t.item())
+
     def step_host():
         prover.prove_batch_ptr(B, h_wit.data_ptr(), h_rng.data_ptr(), rstride, h_out.data_ptr(), pb,
                                h_len.data_ptr(), h_st.data_ptr(), device=False)
@@ -272,18 +323,22 @@ def run_ours(args):
     # ---- warm-up + correctness of what is being timed
     for _ in range(max(args.warmup, 3)):
         step_dev()
+        step_dev2()
     torch.cuda.synchronize()
-    assert int(d_st.abs().sum().item()) == 0, "prover reported failures"
+    assert int(d_st.abs().sum().item()) == 0 and int(d_st2.abs().sum().item()) == 0, "prover reported failures"
     lens = d_len.cpu().numpy()
     assert (lens > 100000).all()
+    assert torch.equal(d_out[:4], d_out2[:4])  # same inputs, same proofs on either stream
 
-    # ---- device-resident throughput (value)
+    # ---- device-resident throughput (value): K steps, alternating between the two streams
     sampler = ClockSampler(local) if rank == 0 else None
-    l0 = ctx.launch_count
-    ms_total = timed(step_dev, args.steps, use_events=True)
-    launches = ctx.launch_count - l0
+    l0 = ctx.launch_count + ctx2.launch_count
+    ms_total = timed_two_streams(args.steps)
+    launches = ctx.launch_count + ctx2.launch_count - l0
     clocks = sampler.stop() if sampler else None
     value = world * B * args.steps / (ms_total * 1e-3)
+    # the same K steps back to back on ONE stream (no overlap between batches)
+    ms_one_stream = timed(step_dev, args.steps, use_events=True)
 
     # ---- per-stage device times of one more batch (roofline of the dominant kernel)
     prover.set_profiling(True)
@@ -300,8 +355,29 @@ def run_ours(args):
         step_host()
     e2e_steps = max(2, min(args.steps, 5))
     ms_e2e = timed(step_host, e2e_steps, use_events=False)
-    e2e_value = world * B * e2e_steps / (ms_e2e * 1e-3)
+    e2e_serial = world * B * e2e_steps / (ms_e2e * 1e-3)
     assert int(h_st.abs().sum().item()) == 0
+    # the same call from two host threads, each with its own context / stream / pinned buffers, so
+    # that one batch's PCIe copies overlap the other batch's kernels (what a serving loop does)
+    import threading
+    h2 = [h_wit.clone().pin_memory(), h_rng.clone().pin_memory(), torch.empty((B, pb), dtype=torch.uint8).pin_memory(),
+          torch.zeros(B, dtype=torch.int64).pin_memory(), torch.zeros(B, dtype=torch.int32).pin_memory()]
+
+    def step_host2():
+        prover2.prove_batch_ptr(B, h2[0].data_ptr(), h2[1].data_ptr(), rstride, h2[2].data_ptr(), pb,
+                                h2[3].data_ptr(), h2[4].data_ptr(), device=False)
+    step_host2()
+
+    def both():
+        th = threading.Thread(target=lambda: [step_host2() for _ in range(e2e_steps)])
+        th.start()
+        for _ in range(e2e_steps):
+            step_host()
+        th.join()
+    ms_pipe = timed(both, 1, use_events=False)
+    e2e_value = world * B * 2 * e2e_steps / (ms_pipe * 1e-3)
+    assert int(h2[4].abs().sum().item()) == 0 and int(h2[3][0].item()) == int(h_len[0].item())
+    ms_e2e_step = ms_pipe / (2 * e2e_steps)
     # the proofs that came back through the host path equal the device-resident ones
     torch.cuda.synchronize()
     n0 = int(h_len[0].item())
@@ -375,8 +451,15 @@ def run_ours(args):
                             ninputs=info["ninputs"], nterms=info["nterms"], tableau=[info["nrow"], info["block_enc"]],
                             proof_bytes=int(lens[0])),
                 clocks=clocks,
-                e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=B * (wb + rstride),
-                         d2h_bytes_per_step=B * (pb + 12), ms_per_step=ms_e2e / e2e_steps),
+                streams=dict(n=2, note="steps alternate between two contexts/streams; the interval is one "
+                                       "CUDA-event pair on the first stream enclosing all launches of both",
+                             one_stream=dict(value=world * B * args.steps / (ms_one_stream * 1e-3),
+                                             ms_per_step=ms_one_stream / args.steps)),
+                e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=B * (wb + rb),
+                         d2h_bytes_per_step=B * (((int(lens.max()) + 15) & ~15) + 12), ms_per_step=ms_e2e_step,
+                         how="lf_zk_prove_batch with pinned host buffers; two batches in flight (two host "
+                             "threads, two contexts/streams) so PCIe copies overlap the other batch's kernels",
+                         one_batch_at_a_time=dict(value=e2e_serial, ms_per_step=ms_e2e / e2e_steps)),
                 gpu_launches=launches, roofline=roofline, cpu_baseline=cpu,
                 latency_ms_per_proof_batch1=lat_ms,
                 ms_per_proof=ms_total / args.steps / B, other_workloads=other)
@@ -388,7 +471,7 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=6)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--batch", type=int, default=1024, help="independent proofs per step per GPU")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
