@@ -257,6 +257,7 @@ struct ScShared {
   typename F::Elt G[2][40];   // bindings of the previous layer (Proof::kMaxBindings)
   typename F::Elt red[2][kScMaxThreads / 32];  // per-warp partials of a0, a2
   typename F::Elt r, alpha, beta, sum, wc[2];
+  typename F::Elt pc[3];  // monomial coefficients of the current round polynomial
   typename F::Elt* hp;  // [blockDim.x] head partials of the segmented sums
   uint32_t* hr;         // [blockDim.x] their segment ids
   // cluster mode (one proof on several SMs): per-CTA results that the other CTAs
@@ -328,8 +329,8 @@ struct ScPar {
 // non-decreasing over e in [0, n).  Segments without entries are not touched.
 // Contains barriers; all threads of the proof must call it.
 // fetch(e) loads the operands of entry e; accum(acc, ops) adds the entry's term.
-// (Issuing the loads one entry ahead was tried and measured slower: the kernel
-// is bound by the multiply pipes and barriers, not by load latency.)
+// (Issuing the loads one entry ahead into registers, and register-free
+// prefetch.global.L1 of the next entry's gathers, were both measured slower.)
 template <class F, bool CL, class Fetch, class Accum>
 __device__ __forceinline__ void seg_sum(ScShared<F>* sh, const ScPar<CL>& P, uint32_t n,
                                         const uint32_t* __restrict__ seg, typename F::Elt* __restrict__ out,
@@ -452,11 +453,20 @@ __device__ __noinline__ void sc_round_serial(ScShared<F>* sh, typename F::Elt a0
   sh->prof[5] += q2 - q1;
   sh->prof[6] += q3 - q2;
   *hb_out = rnd;
-  // new claim = p(rnd).  The reference evaluates the Lagrange form through
-  // Newton differences (poly.h:59-98); it is the same polynomial, so Horner on
-  // the monomial coefficients gives the same field element with two multiplies.
-  sh->sum = F::add(F::mul(F::add(F::mul(c2, rnd), c1), rnd), c0);
   sh->r = rnd;
+  // the new claim p(rnd) is not needed before the next round's serial part: the
+  // caller computes it (sc_new_claim) after releasing the other threads
+  sh->pc[0] = c0;
+  sh->pc[1] = c1;
+  sh->pc[2] = c2;
+}
+// new claim = p(rnd).  The reference evaluates the Lagrange form through
+// Newton differences (poly.h:59-98); it is the same polynomial, so Horner on
+// the monomial coefficients gives the same field element with two multiplies.
+template <class F>
+__device__ __forceinline__ void sc_new_claim(ScShared<F>* sh) {
+  const typename F::Elt rnd = sh->r;
+  sh->sum = F::add(F::mul(F::add(F::mul(sh->pc[2], rnd), sh->pc[1]), rnd), sh->pc[0]);
 }
 
 template <class F>
@@ -681,6 +691,7 @@ __device__ __forceinline__ void sumcheck_body(const ZkDims& d, const ZkBufs<type
       }
       Q.sync();
       const Elt r = Q.remote(&sh, 0)->r;
+      if (leader) sc_new_claim<F>(&sh);  // off the critical path: the others are already binding
       // Dense::bind (dense.h:70-89)
       Elt* Wn = whbuf + (size_t)(2 * hand + (hand ? wpar1 : wpar0)) * d.max_nw;
       for (uint32_t i = gtid; i < npair; i += gnth) {
