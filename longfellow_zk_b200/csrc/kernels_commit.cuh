@@ -221,7 +221,7 @@ __device__ __forceinline__ Cx<F> cx_mul(const Cx<F>& a, const Cx<F>& b) {
 }
 
 template <class F>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(512, 1)
 k_rs_fp_fft_rows(typename F::Elt* __restrict__ data, size_t row_stride, size_t batch_stride, uint32_t n,
                  uint32_t m, uint32_t logM, const Cx<F>* __restrict__ Wk /* [M] W^k */,
                  const Cx<F>* __restrict__ Yh /* [M+1] */, const typename F::Elt* __restrict__ lead,
@@ -240,8 +240,22 @@ k_rs_fp_fft_rows(typename F::Elt* __restrict__ data, size_t row_stride, size_t b
     a[j] = z;
   }
   __syncthreads();
-  // forward: decimation in frequency, twiddle V^-e = conj(W^(2e))
-  for (uint32_t lg = logM; lg >= 1; --lg) {
+  // forward: decimation in frequency, twiddle V^-e = conj(W^(2e)).
+  // The input is zero beyond nz = ceil(n/2) complex points, so while a block's
+  // lower half still holds all of them (half >= nz) the upper input v is zero:
+  // the butterfly degenerates to (u, u * w) on the nz live points of each block.
+  const uint32_t nz = (n + 1) / 2;
+  uint32_t lg = logM;
+  for (; lg >= 1 && (1u << (lg - 1)) >= nz; --lg) {
+    const uint32_t half = 1u << (lg - 1), step = M >> lg, nblk = M >> lg;
+    for (uint32_t t = tid; t < nblk * nz; t += nth) {
+      const uint32_t j = t % nz, i = (t / nz) << lg;
+      const Cx<F> u = a[i + j];
+      a[i + j + half] = (j == 0) ? u : cx_mul<F>(u, cx_conj<F>(Wk[2 * j * step]));
+    }
+    __syncthreads();
+  }
+  for (; lg >= 1; --lg) {
     const uint32_t half = 1u << (lg - 1), step = M >> lg;
     for (uint32_t t = tid; t < M / 2; t += nth) {
       uint32_t j = t & (half - 1), i = (t >> (lg - 1)) << lg;
@@ -265,8 +279,9 @@ k_rs_fp_fft_rows(typename F::Elt* __restrict__ data, size_t row_stride, size_t b
       Cx<F> zk = a[bk], zk2c = cx_conj<F>(a[bk2]);
       Cx<F> e2 = cx_add<F>(zk, zk2c), o2 = cx_mulmi<F>(cx_sub<F>(zk, zk2c));
       const Cx<F> w = Wk[k];
-      Cx<F> xk = cx_add<F>(e2, cx_mul<F>(cx_conj<F>(w), o2));
-      Cx<F> xk2 = cx_sub<F>(cx_conj<F>(e2), cx_mul<F>(w, cx_conj<F>(o2)));
+      const Cx<F> wo = cx_mul<F>(cx_conj<F>(w), o2);  // and w * conj(o2) = conj(wo)
+      Cx<F> xk = cx_add<F>(e2, wo);
+      Cx<F> xk2 = cx_sub<F>(cx_conj<F>(e2), cx_conj<F>(wo));
       Cx<F> pk = cx_mul<F>(xk, Yh[k]), pk2c = cx_conj<F>(cx_mul<F>(xk2, Yh[k2]));
       Cx<F> pe = cx_add<F>(pk, pk2c), po = cx_mul<F>(cx_sub<F>(pk, pk2c), w);
       Cx<F> qk = cx_add<F>(pe, cx_muli<F>(po));
