@@ -100,3 +100,18 @@ def test_reference_verifier_accepts_gpu_proofs(sha, ref):
     for pr, st in zip(proofs, status):
         assert st == 0
         assert rc.verify(b"", pr) == 0
+
+
+@pytest.mark.parametrize("rate,nreq,block_enc,tinit", [(4, 189, 0, b"test"), (7, 132, 4151, b"mdoc-style block_enc"),
+                                                       (2, 64, 0, b""), (16, 40, 0, b"x" * 100)])
+def test_sha_proof_other_ligero_parameters(ctx, oracle, rate, nreq, block_enc, tinit):
+    """other (rate, nreq, block_enc) choices of LigeroParam (ligero_param.h:116-307; the mdoc specs use
+    block_enc 4151, zk_spec.cc:47-49) and other transcript seeds, against the oracle"""
+    import longfellow_zk_b200 as lf
+    circ, wit = load("sha1_gf128")
+    c = lf.Circuit(ctx, GF, circ, rate=rate, nreq=nreq, block_enc=block_enc)
+    rng = rng_bytes(9, c.info["rng_bytes"])
+    want = oracle.Circuit(GF, circ).prove(wit, rng, tinit=tinit, rate=rate, nreq=nreq, block_enc=block_enc)
+    assert c.info["rng_bytes"] == want["rng_used"]
+    proofs, status = lf.ZkProver(c).prove_batch(np.frombuffer(wit, np.uint8)[None, :], rng[None, :], tinit=tinit)
+    assert status[0] == 0 and proofs[0] == want["proof"]
