@@ -115,3 +115,26 @@ def test_sha_proof_other_ligero_parameters(ctx, oracle, rate, nreq, block_enc, t
     assert c.info["rng_bytes"] == want["rng_used"]
     proofs, status = lf.ZkProver(c).prove_batch(np.frombuffer(wit, np.uint8)[None, :], rng[None, :], tinit=tinit)
     assert status[0] == 0 and proofs[0] == want["proof"]
+
+
+@pytest.mark.parametrize("name,fid,B", [("sha1_gf128", 4, 20), ("sha1_gf128", 4, 300), ("ecdsa1_p256", 1, 20),
+                                        ("ecdsa1_p256", 1, 300)])
+def test_every_sumcheck_shape_matches_oracle(ctx, oracle, name, fid, B):
+    """The batch size selects the sumcheck launch shape (cluster per proof for B <= 9, one 1024-thread
+    CTA per proof below 148, 128-thread throughput CTAs from 148 on).  Every proof of a batch that mixes
+    four coin streams must equal the oracle's proof for its stream, wherever it sits in the batch."""
+    import longfellow_zk_b200 as lf
+    circ, wit = load(name)
+    c = lf.Circuit(ctx, fid, circ)
+    n = c.info["rng_bytes"]
+    streams = [rng_bytes(40 + s, 1 << 19)[:n].copy() for s in range(4)]
+    if fid == 1:
+        for s in streams:
+            s[31::32] &= 0x7F  # every 32-byte sample below p: no rejection in either implementation
+    want = [oracle.Circuit(fid, circ).prove(wit, s)["proof"] for s in streams]
+    rng = np.stack([streams[i % 4] for i in range(B)])
+    W = np.repeat(np.frombuffer(wit, np.uint8)[None, :], B, axis=0)
+    proofs, status = lf.ZkProver(c).prove_batch(W, rng)
+    assert (status == 0).all()
+    for i, pr in enumerate(proofs):
+        assert pr == want[i % 4], f"proof {i} of {B}"
