@@ -143,6 +143,24 @@ class ClockSampler:
                     reasons=reasons, samples=len(sm))
 
 
+def stage_rates(info, stage_ms, B, mul_peak, sha_peak):
+    """per-stage achieved integer-op rates against the measured peaks of this box (lf_microbench):
+    field multiplications/s of the stages that are multiply bound, compressions/s of the Merkle commit"""
+    out = {}
+    for stage, key in (("rs_encode", "rs_mults"), ("eval_circuit", "eval_mults"), ("sumcheck", "sumcheck_mults"),
+                       ("ligero_prove", "ligero_mults")):
+        ms = stage_ms.get(stage, 0.0)
+        if ms > 0:
+            g = info[key] * B / (ms * 1e-3) / 1e9
+            out[stage] = dict(ms=ms, mults_per_proof=info[key], achieved_gmul_s=g, frac_of_mul_peak=g / mul_peak)
+    ms = stage_ms.get("merkle", 0.0)
+    if ms > 0:
+        g = info["merkle_compressions"] * B / (ms * 1e-3) / 1e9
+        out["merkle"] = dict(ms=ms, compressions_per_proof=info["merkle_compressions"], achieved_gcomp_s=g,
+                             frac_of_sha_peak=g / sha_peak)
+    return out
+
+
 def measure_other(lf, ctx, stream, workload, B, steps=3):
     """device-resident and end-to-end proofs/s of another circuit (single GPU, rank 0)"""
     import numpy as np
@@ -210,6 +228,7 @@ def measure_other(lf, ctx, stream, workload, B, steps=3):
     assert int(h_st.abs().sum().item()) == 0
     return dict(workload=desc, proofs_per_step=B, value=B * steps / (ms * 1e-3), unit=UNIT,
                 e2e=dict(value=2 * B / (t1 - t0), unit=UNIT), stage_ms=stages, latency_ms_per_proof_batch1=lat1,
+                kernels=stage_rates(info, stages, B, ctx.microbench(4 if fid == 1 else 2), ctx.microbench(3)),
                 proof_bytes=int(d_len[0].item()), total_mults_per_proof=info["total_mults"])
 
 
@@ -422,7 +441,8 @@ def run_ours(args):
                         achieved_gmul_s=info["sumcheck_mults"] * B / (sc_ms * 1e-3) / 1e9,
                         peak_gmul_s=gmul_peak,
                         frac=info["sumcheck_mults"] * B / (sc_ms * 1e-3) / 1e9 / gmul_peak),
-                    stage_ms=stage_acc, top_stage=top)
+                    stage_ms=stage_acc, top_stage=top,
+                    kernels=stage_rates(info, stage_acc, B, gmul_peak, ctx.microbench(3)))
 
     # ---- the reference CPU prover on this box's host cores (bounded sample)
     nthreads = os.cpu_count() or 1

@@ -126,6 +126,9 @@ typedef struct lf_circuit_info {
   size_t total_mults;
   /* per-proof SHA-256 compressions (Merkle leaves + tree + transcript) */
   size_t sha_compressions;
+  /* the same total split by stage (SURVEY.md 8(d) formulas): RS row encodes of commit,
+   * eval_circuit, Ligero prove (incl. its RS rows); Merkle commit compressions */
+  size_t rs_mults, eval_mults, ligero_mults, merkle_compressions;
 } lf_circuit_info;
 int lf_circuit_get_info(const lf_circuit* c, lf_circuit_info* info);
 
@@ -176,7 +179,7 @@ uint64_t lf_ctx_launch_count(const lf_ctx* ctx);
 /* integer-pipe micro-benchmarks (roofline denominators): returns achieved
  * giga-operations per second of `what` on the context's device.
  *   what = 0: IMAD.WIDE  1: LOP3  2: GF(2^128) multiply (Gmul/s)
- *          3: SHA-256 compressions (G/s)
+ *          3: SHA-256 compressions (G/s)  4: P-256 Montgomery multiply (Gmul/s)
  *   what = 100..105: single-thread latency of the transcript primitives, in
  *          CYCLES per call: compression, digest snapshot, AES-256 key
  *          schedule, AES block, 16-byte element write, write + challenge */

@@ -19,7 +19,8 @@ class CircuitInfo(C.Structure):
     _fields_ = [(n, C.c_size_t) for n in (
         "ninputs", "npub_in", "nl", "nterms", "kbytes", "witness_bytes", "rng_bytes",
         "max_proof_bytes", "block_enc", "block", "dblock", "block_ext", "nrow", "r", "w", "nwrow",
-        "nqtriples", "nreq", "nw", "sumcheck_alg_bytes", "sumcheck_mults", "total_mults", "sha_compressions")]
+        "nqtriples", "nreq", "nw", "sumcheck_alg_bytes", "sumcheck_mults", "total_mults", "sha_compressions",
+        "rs_mults", "eval_mults", "ligero_mults", "merkle_compressions")]
 
 
 EXPORTS = [

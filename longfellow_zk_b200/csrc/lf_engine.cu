@@ -922,6 +922,22 @@ __global__ void k_bench_gfmul(gf128* out, int iters) {
   }
   out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = gf_add(a, b);
 }
+__global__ void k_bench_p256mul(fpw<8>* out, int iters) {
+  typedef FFp256 F;
+  fpw<8> a, b;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    a.w[i] = threadIdx.x * 2654435761u + i;
+    b.w[i] = blockIdx.x * 40503u + 7 * i + 1;
+  }
+  a.w[7] &= 0x7fffffffu;
+  b.w[7] &= 0x7fffffffu;
+  for (int i = 0; i < iters; ++i) {
+    a = fp_mul_p256_dev(a, b, c_p256.m);
+    b = fp_mul_p256_dev(b, a, c_p256.m);
+  }
+  out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = fp_add<8>(a, b, c_p256.m);
+}
 __global__ void k_bench_sha(uint32_t* out, int iters) {
   uint32_t h[8], w[16];
   sha256_iv(h);
@@ -1372,7 +1388,7 @@ int lf_microbench(lf_ctx* ctx, int what, double* gops) {
   LF_CUDA(cudaSetDevice(ctx->device));
   const int blocks = ctx->sm_count * 8, threads = 256;
   void* d;
-  LF_CUDA(cudaMalloc(&d, (size_t)blocks * threads * 16));
+  LF_CUDA(cudaMalloc(&d, (size_t)blocks * threads * 32));
   if (what >= 100 && what < 106) {
     long long h[8];
     k_probe_serial<<<1, 32, 0, ctx->stream>>>((long long*)d);
@@ -1386,8 +1402,9 @@ int lf_microbench(lf_ctx* ctx, int what, double* gops) {
   cudaEvent_t e0, e1;
   LF_CUDA(cudaEventCreate(&e0));
   LF_CUDA(cudaEventCreate(&e1));
-  int iters = what == 0 ? 4096 : what == 1 ? 4096 : what == 2 ? 256 : 256;
-  double ops_per_thread = what == 0 ? 32.0 * iters : what == 1 ? 32.0 * 3 * iters : what == 2 ? 2.0 * iters : 1.0 * iters;
+  int iters = what == 0 ? 4096 : what == 1 ? 4096 : 256;
+  double ops_per_thread = what == 0 ? 32.0 * iters : what == 1 ? 32.0 * 3 * iters
+                          : (what == 2 || what == 4) ? 2.0 * iters : 1.0 * iters;
   float best = 1e30f;
   for (int rep = 0; rep < 4; ++rep) {
     LF_CUDA(cudaEventRecord(e0, ctx->stream));
@@ -1395,6 +1412,7 @@ int lf_microbench(lf_ctx* ctx, int what, double* gops) {
     else if (what == 1) k_bench_lop3<<<blocks, threads, 0, ctx->stream>>>((uint32_t*)d, iters);
     else if (what == 2) k_bench_gfmul<<<blocks, threads, 0, ctx->stream>>>((gf128*)d, iters);
     else if (what == 3) k_bench_sha<<<blocks, threads, 0, ctx->stream>>>((uint32_t*)d, iters);
+    else if (what == 4) k_bench_p256mul<<<blocks, threads, 0, ctx->stream>>>((fpw<8>*)d, iters);
     else return fail(LF_ERR_ARG, "lf_microbench: unknown benchmark");
     ctx->launches++;
     LF_CUDA(cudaEventRecord(e1, ctx->stream));
