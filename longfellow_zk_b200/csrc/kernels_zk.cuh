@@ -22,8 +22,10 @@ namespace lf {
 // transcript writes of an element: tag + wire bytes (transcript.h:136-153)
 // (elements are taken by value and their words absorbed with a fully unrolled
 // loop, so the wire words stay in registers)
+// One out-of-line copy each: they are called from a dozen sites of the serial
+// path and every inlined copy carries the word-by-word buffer handling.
 template <class F>
-__device__ __forceinline__ void ts_array_elt(Transcript* ts, typename F::Elt e) {
+__device__ __noinline__ void ts_array_elt(Transcript* ts, typename F::Elt e) {
   uint32_t w[F::kWords];
   F::to_wire(w, e);
 #pragma unroll
@@ -33,6 +35,11 @@ template <class F>
 __device__ __forceinline__ void ts_write_elt(Transcript* ts, typename F::Elt e) {
   ts->raw_byte(1);  // TAG_FIELD_ELEM
   ts_array_elt<F>(ts, e);
+}
+// Field::sample on the transcript (random.h:37-41), out of line for the same reason
+template <class F>
+__device__ __noinline__ typename F::Elt ts_challenge(Transcript* ts) {
+  return F::ts_elt(ts);
 }
 
 // ----------------------------------------------------------------------------
@@ -447,7 +454,7 @@ __device__ __noinline__ void sc_round_serial(ScShared<F>* sh, typename F::Elt a0
   ts_write_elt<F>(&sh->ts, p0);
   ts_write_elt<F>(&sh->ts, p2);
   long long q2 = clock64();
-  Elt rnd = F::ts_elt(&sh->ts);
+  Elt rnd = ts_challenge<F>(&sh->ts);
   long long q3 = clock64();
   sh->prof[4] += q1 - q0;
   sh->prof[5] += q2 - q1;
@@ -475,9 +482,9 @@ __device__ __noinline__ void sc_begin(ScShared<F>* sh, const Transcript* src) {
   sh->ts.use_tables(&sh->aes);
   sh->ts.have_prf = 0;  // Transcript::clone() carries only the hash (transcript.h:86)
   // begin_circuit: Q[40] then G[40] (transcript_sumcheck.h:49-52)
-  for (int i = 0; i < 40; ++i) (void)F::ts_elt(&sh->ts);
+  for (int i = 0; i < 40; ++i) (void)ts_challenge<F>(&sh->ts);
   for (int i = 0; i < 40; ++i) {
-    typename F::Elt g = F::ts_elt(&sh->ts);
+    typename F::Elt g = ts_challenge<F>(&sh->ts);
     sh->G[0][i] = g;
     sh->G[1][i] = g;
   }
@@ -488,8 +495,8 @@ __device__ __noinline__ void sc_begin(ScShared<F>* sh, const Transcript* src) {
 
 template <class F>
 __device__ __noinline__ void sc_begin_layer(ScShared<F>* sh, typename F::Elt* alpha_out) {
-  sh->alpha = F::ts_elt(&sh->ts);
-  sh->beta = F::ts_elt(&sh->ts);
+  sh->alpha = ts_challenge<F>(&sh->ts);
+  sh->beta = ts_challenge<F>(&sh->ts);
   *alpha_out = sh->alpha;
   sh->sum = F::add(sh->wc[0], F::mul(sh->alpha, sh->wc[1]));
 }
