@@ -155,6 +155,38 @@ int lf_zk_prove_batch_dev(lf_circuit* c, size_t nproofs, const void* d_witnesses
                           void* d_proofs_out, size_t proof_stride, void* d_proof_lens,
                           void* d_status);
 
+/* ---- commit and prove as separate calls on a caller-owned transcript ------ */
+/* The reference's ZkProver::commit and ::prove take the caller's Transcript
+ * (lib/zk/zk_prover.h:72-149), and run_mdoc_prover interleaves two provers on
+ * ONE transcript: commit(hash), commit(sig), MAC key from the transcript, patch
+ * of public inputs, prove(hash), prove(sig) (lib/circuits/mdoc/mdoc_zk.cc:459-503).
+ * lf_transcript is the state that crosses: the SHA-256 state of everything
+ * written so far plus the read position of the challenge stream
+ * (lib/random/transcript.h:46-62,70-190). */
+typedef struct lf_transcript {
+  uint32_t h[8];       /* SHA-256 chaining value */
+  uint32_t buf[16];    /* buffered message bytes, big-endian words */
+  uint64_t len;        /* bytes absorbed */
+  uint64_t nblock;     /* FSPRF: next AES block counter */
+  uint32_t rdptr, have_prf;
+  uint32_t saved[4];   /* current FSPRF block */
+} lf_transcript;
+/* Transcript(seed, n); write(data, n); bytes(out, n)  -- on the host */
+void lf_transcript_init(lf_transcript* ts, const uint8_t* seed, size_t n);
+void lf_transcript_write_bytes(lf_transcript* ts, const uint8_t* data, size_t n);
+void lf_transcript_challenge_bytes(lf_transcript* ts, uint8_t* out, size_t n);
+/* ZkProver::commit for nproofs proofs: ts[i] (in/out) receives the commitment
+ * (root i, also returned in roots_out[32*i], may be NULL).  The committed
+ * tableaux stay on the device inside `c` until the matching prove call. */
+int lf_zk_commit_batch(lf_circuit* c, size_t nproofs, const uint8_t* witnesses, const uint8_t* rng,
+                       size_t rng_stride, lf_transcript* ts, uint8_t* roots_out, int* status);
+/* ZkProver::prove + ZkProof::write for the batch committed last on `c`.
+ * witnesses: the same inputs; PUBLIC inputs may differ from the commit call
+ * (they are not committed).  ts[i] in: the transcript to continue from; out:
+ * the transcript as the prover left it. */
+int lf_zk_prove_committed_batch(lf_circuit* c, size_t nproofs, const uint8_t* witnesses, lf_transcript* ts,
+                                uint8_t* proofs_out, size_t proof_stride, size_t* proof_lens, int* status);
+
 /* ---- stage read-back for parity tests ---------------------------------- */
 enum lf_stage {
   LF_STAGE_WITNESS = 1,   /* Ligero witness vector, nw elements */

@@ -23,12 +23,20 @@ class CircuitInfo(C.Structure):
         "rs_mults", "eval_mults", "ligero_mults", "merkle_compressions")]
 
 
+class Transcript(C.Structure):
+    """lf_transcript: the transcript state that crosses the C ABI"""
+    _fields_ = [("h", C.c_uint32 * 8), ("buf", C.c_uint32 * 16), ("len", C.c_uint64), ("nblock", C.c_uint64),
+                ("rdptr", C.c_uint32), ("have_prf", C.c_uint32), ("saved", C.c_uint32 * 4)]
+
+
 EXPORTS = [
     "lf_ctx_create", "lf_ctx_destroy", "lf_ctx_synchronize", "lf_last_error", "lf_version",
     "lf_elt_mul", "lf_rs_interpolate", "lf_rs_interpolate_dev", "lf_merkle_commit",
     "lf_circuit_upload", "lf_circuit_free", "lf_circuit_get_info", "lf_zk_prove_batch",
     "lf_zk_prove_batch_dev", "lf_zk_debug_fetch", "lf_ctx_launch_count", "lf_microbench",
     "lf_circuit_set_profiling", "lf_circuit_get_stage_ms", "lf_fft", "lf_fft_time",
+    "lf_zk_commit_batch", "lf_zk_prove_committed_batch", "lf_transcript_init", "lf_transcript_write_bytes",
+    "lf_transcript_challenge_bytes",
 ]
 
 

@@ -80,6 +80,24 @@ class Context:
         return g.value
 
 
+def transcripts(n, seed=b"test"):
+    """n caller-owned transcripts, each Transcript(seed) (lf_transcript_init)"""
+    arr = (_native.Transcript * n)()
+    for i in range(n):
+        _native.lib().lf_transcript_init(C.byref(arr[i]), seed, len(seed))
+    return arr
+
+
+def transcript_write(ts, data):
+    _native.lib().lf_transcript_write_bytes(C.byref(ts), data, len(data))
+
+
+def transcript_challenge(ts, n):
+    out = (C.c_uint8 * n)()
+    _native.lib().lf_transcript_challenge_bytes(C.byref(ts), out, n)
+    return bytes(out)
+
+
 class _Interpolator:
     def __init__(self, ctx, field_id, n, m):
         self.ctx, self.field_id, self.n, self.m = ctx, field_id, n, m
@@ -177,6 +195,32 @@ class ZkProver:
         status = np.zeros(B, np.int32)
         check(_native.lib().lf_zk_prove_batch(self.c._h, B, _p(witnesses), _p(rng), rng.shape[1], tinit,
                                               len(tinit), _p(out), stride, _p(lens), _p(status)))
+        return [out[i, :int(lens[i])].tobytes() for i in range(B)], status
+
+    def commit_batch(self, witnesses, rng, transcripts):
+        """ZkProver::commit on caller-owned transcripts (lf_zk_commit_batch).  transcripts: a
+        ctypes array of _native.Transcript, updated in place.  Returns (roots (B, 32), status)."""
+        info = self.c.info
+        witnesses, rng = _u8(witnesses), _u8(rng)
+        B = witnesses.shape[0]
+        assert witnesses.shape[1] == info["witness_bytes"] and rng.shape[0] == B and len(transcripts) == B
+        roots = np.zeros((B, 32), np.uint8)
+        status = np.zeros(B, np.int32)
+        check(_native.lib().lf_zk_commit_batch(self.c._h, B, _p(witnesses), _p(rng), rng.shape[1], transcripts,
+                                               _p(roots), _p(status)))
+        return roots, status
+
+    def prove_committed_batch(self, witnesses, transcripts):
+        """ZkProver::prove + ZkProof::write for the batch committed last (lf_zk_prove_committed_batch)."""
+        info = self.c.info
+        witnesses = _u8(witnesses)
+        B = witnesses.shape[0]
+        stride = info["max_proof_bytes"]
+        out = np.zeros((B, stride), np.uint8)
+        lens = np.zeros(B, np.uint64)
+        status = np.zeros(B, np.int32)
+        check(_native.lib().lf_zk_prove_committed_batch(self.c._h, B, _p(witnesses), transcripts, _p(out), stride,
+                                                        _p(lens), _p(status)))
         return [out[i, :int(lens[i])].tobytes() for i in range(B)], status
 
     STAGES = ["layout", "rs_encode", "merkle", "transcript_init", "eval_circuit", "sumcheck", "ligero_prove"]

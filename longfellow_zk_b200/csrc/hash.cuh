@@ -443,6 +443,18 @@ struct Aes256 {
 };
 
 // ------------------------------------------------------------- Transcript
+// What crosses the C ABI (lf_transcript in longfellow_b200.h, same layout): the
+// SHA-256 state of everything written so far plus the read position of the
+// challenge stream.  The AES key schedule is re-derived from the hash on import.
+struct TranscriptState {
+  uint32_t h[8];
+  uint32_t buf[16];  // buffered message bytes as big-endian words
+  uint64_t len;
+  uint64_t nblock;
+  uint32_t rdptr, have_prf;
+  uint32_t saved[4];
+};
+
 struct Transcript {
   Sha256 sha;
   Aes256 prf;
@@ -453,6 +465,30 @@ struct Transcript {
   const uint8_t* sbox;  // AES S-box to use (re-pointed by every kernel after loading the state)
   const AesTables* tab; // round tables in shared memory, or null: S-box only
 
+  LF_HD void export_state(TranscriptState* o) const {
+    for (int i = 0; i < 8; ++i) o->h[i] = sha.h[i];
+    for (int i = 0; i < 16; ++i) o->buf[i] = sha.buf[i];
+    o->len = sha.len;
+    o->nblock = nblock;
+    o->rdptr = rdptr;
+    o->have_prf = have_prf;
+    for (int i = 0; i < 4; ++i) o->saved[i] = saved[i];
+  }
+  // sbox (and tab) must be set before a state with a live challenge stream is imported
+  LF_HD void import_state(const TranscriptState* s) {
+    for (int i = 0; i < 8; ++i) sha.h[i] = s->h[i];
+    for (int i = 0; i < 16; ++i) sha.buf[i] = s->buf[i];
+    sha.len = s->len;
+    have_prf = 0;
+    nblock = 0;
+    rdptr = 16;
+    if (s->have_prf) {
+      refill();  // re-keys from the hash (block 0 is recomputed and dropped)
+      nblock = s->nblock;
+      rdptr = s->rdptr;
+      for (int i = 0; i < 4; ++i) saved[i] = s->saved[i];
+    }
+  }
   LF_HD void use_tables(const AesTables* t) {
     tab = t;
     sbox = t->sbox;

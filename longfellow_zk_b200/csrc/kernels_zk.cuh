@@ -166,22 +166,32 @@ k_zk_layout(ZkDims d, ZkBufs<typename F::Elt> b, const uint32_t* __restrict__ ro
 // k_zk_transcript_init: Transcript(tinit) ; write(root) ; then
 // initialize_sumcheck_fiat_shamir (zk_common.h:163-180).  One thread per proof.
 // ----------------------------------------------------------------------------
+// ext == nullptr: the proof owns its transcript, Transcript(tinit) and the root are
+// written here.  ext != nullptr: the caller's transcript (already holding this and
+// possibly other commitments, lf_zk_commit_batch) continues.
 template <class F>
 __global__ void k_zk_transcript_init(ZkDims d, ZkBufs<typename F::Elt> b, const uint8_t* __restrict__ tinit,
-                                     const uint8_t* __restrict__ circuit_id, size_t nproofs) {
+                                     const uint8_t* __restrict__ circuit_id, size_t nproofs,
+                                     const TranscriptState* __restrict__ ext) {
   __shared__ uint8_t s_sbox[256];
   aes_stage_sbox(s_sbox);
   size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= nproofs) return;
   Transcript ts;
-  ts.init(tinit, d.tinit_len);
-  ts.sbox = s_sbox;
-  // ligero_transcript.h:31-34 write_commitment: root digest is node 1
-  const uint32_t* root = b.nodes + p * (size_t)(2 * d.block_ext * 8) + 8;
-  uint32_t rw[8];
+  if (ext) {
+    ts.sbox = s_sbox;
+    ts.tab = nullptr;
+    ts.import_state(ext + p);
+  } else {
+    ts.init(tinit, d.tinit_len);
+    ts.sbox = s_sbox;
+    // ligero_transcript.h:31-34 write_commitment: root digest is node 1
+    const uint32_t* root = b.nodes + p * (size_t)(2 * d.block_ext * 8) + 8;
+    uint32_t rw[8];
 #pragma unroll
-  for (int k = 0; k < 8; ++k) rw[k] = bswap32(root[k]);
-  ts.write_bytes_words(rw, 8);
+    for (int k = 0; k < 8; ++k) rw[k] = bswap32(root[k]);
+    ts.write_bytes_words(rw, 8);
+  }
   ts.write_bytes(circuit_id, 32);
   for (uint32_t i = 0; i < d.npub; ++i) {
     // the wire bytes of the public inputs go into the transcript unchanged
@@ -199,6 +209,38 @@ __global__ void k_zk_transcript_init(ZkDims d, ZkBufs<typename F::Elt> b, const 
   }
   ts.write0(d.nterms);
   *reinterpret_cast<Transcript*>(b.ts + p * sizeof(Transcript)) = ts;
+}
+
+// ZkProver::commit's transcript step on a caller-owned transcript: write the root
+// (ligero_transcript.h:31-34) and hand the state back; also returns the roots.
+template <class F>
+__global__ void k_zk_transcript_commit(ZkDims d, ZkBufs<typename F::Elt> b, TranscriptState* __restrict__ ext,
+                                       uint8_t* __restrict__ roots_out, size_t nproofs) {
+  __shared__ uint8_t s_sbox[256];
+  aes_stage_sbox(s_sbox);
+  size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= nproofs) return;
+  Transcript ts;
+  ts.sbox = s_sbox;
+  ts.tab = nullptr;
+  ts.import_state(ext + p);
+  const uint32_t* root = b.nodes + p * (size_t)(2 * d.block_ext * 8) + 8;
+  uint32_t rw[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    rw[k] = bswap32(root[k]);
+    reinterpret_cast<uint32_t*>(roots_out)[p * 8 + k] = rw[k];
+  }
+  ts.write_bytes_words(rw, 8);
+  ts.export_state(ext + p);
+}
+// the transcript as the prover left it (after LigeroProver::prove), for the caller
+template <class F>
+__global__ void k_zk_transcript_export(ZkBufs<typename F::Elt> b, TranscriptState* __restrict__ ext,
+                                       size_t nproofs) {
+  size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= nproofs) return;
+  reinterpret_cast<const Transcript*>(b.ts + p * sizeof(Transcript))->export_state(ext + p);
 }
 
 // ----------------------------------------------------------------------------

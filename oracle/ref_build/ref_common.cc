@@ -557,6 +557,50 @@ double ref_zk_bench(void* handle,
   return std::chrono::duration<double>(t1 - t0).count();
 }
 
+// Two provers on ONE transcript, the structure of run_mdoc_prover
+// (circuits/mdoc/mdoc_zk.cc:459-503): commit(A), commit(B), challenge bytes drawn
+// from the transcript (there: the MAC key), prove(A), prove(B).  A is a
+// GF(2^128) circuit, B an Fp256 circuit; both draw their coins from one engine.
+int ref_zk_prove_pair(void* handle_a, void* handle_b, const uint8_t* wit_a, const uint8_t* wit_b,
+                      const uint8_t* rng, size_t rng_len, const uint8_t* tinit, size_t tinit_len, size_t rate,
+                      size_t nreq, uint8_t* challenge16, uint8_t* out_a, size_t cap_a, size_t* len_a,
+                      uint8_t* out_b, size_t cap_b, size_t* len_b, size_t* rng_used_a, size_t* rng_used_total) {
+  set_log_level(ERROR);
+  auto* ha = static_cast<CircuitHandle*>(handle_a);
+  auto* hb = static_cast<CircuitHandle*>(handle_b);
+  if (ha->field_id != GF2_128_ID || hb->field_id != P256_ID) return -100;
+  const Circuit<GF>* ca = ha->gf.get();
+  const Circuit<Fp256Base>* cb = hb->p256.get();
+  Dense<GF> Wa(1, ca->ninputs);
+  for (size_t i = 0; i < ca->ninputs; ++i) Wa.v_[i] = gf().of_bytes_field(wit_a + i * GF::kBytes).value();
+  Dense<Fp256Base> Wb(1, cb->ninputs);
+  for (size_t i = 0; i < cb->ninputs; ++i)
+    Wb.v_[i] = p256_base.of_bytes_field(wit_b + i * Fp256Base::kBytes).value();
+  BufferRandomEngine eng(rng, rng_len);
+  Transcript tp(tinit, tinit_len);
+  LCH14ReedSolomonFactory<GF> rsa(gf());
+  ZkProof<GF> za(*ca, rate, nreq);
+  ZkProof<Fp256Base> zb(*cb, rate, nreq);
+  ZkProver<GF, LCH14ReedSolomonFactory<GF>> pa(*ca, gf(), rsa);
+  ZkProver<Fp256Base, P256RS> pb(*cb, p256_base, p256ctx().rs);
+  pa.commit(za, Wa, tp, eng);
+  *rng_used_a = eng.consumed();
+  pb.commit(zb, Wb, tp, eng);
+  *rng_used_total = eng.consumed();
+  tp.bytes(challenge16, 16);
+  if (!pa.prove(za, Wa, tp)) return -3;
+  if (!pb.prove(zb, Wb, tp)) return -3;
+  std::vector<uint8_t> ba, bb;
+  za.write(ba, gf());
+  zb.write(bb, p256_base);
+  *len_a = ba.size();
+  *len_b = bb.size();
+  if (ba.size() > cap_a || bb.size() > cap_b) return -4;
+  memcpy(out_a, ba.data(), ba.size());
+  memcpy(out_b, bb.data(), bb.size());
+  return 0;
+}
+
 #ifdef LF_WITH_GPU_ADAPTERS
 // ---- libref_gpu.so only: the reference driving the CUDA back end through
 // include/longfellow_b200_adapters.h (tests/test_gpu_adapters.py).  This is the

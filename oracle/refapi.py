@@ -258,6 +258,23 @@ class Circuit:
         return float(secs), [float(x) for x in lat]
 
 
+def prove_pair(circ_a, circ_b, wit_a, wit_b, rng, tinit=b"test", rate=7, nreq=132):
+    """commit(A), commit(B), 16 challenge bytes, prove(A), prove(B) on ONE reference Transcript
+    (the structure of run_mdoc_prover).  circ_a: GF(2^128) Circuit, circ_b: Fp256 Circuit."""
+    rng = _u8(np.frombuffer(rng, np.uint8) if isinstance(rng, (bytes, bytearray)) else rng)
+    oa, ob = np.zeros(1 << 21, np.uint8), np.zeros(1 << 21, np.uint8)
+    la, lb, ua, ut = C.c_size_t(), C.c_size_t(), C.c_size_t(), C.c_size_t()
+    ch = np.zeros(16, np.uint8)
+    rc = lib().ref_zk_prove_pair(C.c_void_p(circ_a.h), C.c_void_p(circ_b.h), C.c_char_p(wit_a), C.c_char_p(wit_b),
+                                 _p(rng), C.c_size_t(rng.size), C.c_char_p(tinit), C.c_size_t(len(tinit)),
+                                 C.c_size_t(rate), C.c_size_t(nreq), _p(ch), _p(oa), C.c_size_t(oa.size),
+                                 C.byref(la), _p(ob), C.c_size_t(ob.size), C.byref(lb), C.byref(ua), C.byref(ut))
+    if rc != 0:
+        raise RuntimeError(f"reference pair prover failed rc={rc}")
+    return dict(proof_a=oa[:la.value].tobytes(), proof_b=ob[:lb.value].tobytes(), challenge=ch.tobytes(),
+                rng_used_a=ua.value, rng_used_total=ut.value)
+
+
 class GpuAdapterCircuit:
     """A reference Circuit object inside libref_gpu.so, proved (1) by the reference's own
     ZkProver with GpuReedSolomonFactory injected, (2) by GpuZkProver."""

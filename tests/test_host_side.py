@@ -113,3 +113,24 @@ def test_oracle_matches_unmodified_reference(oracle, ref):
         x[:, -1] &= 0x1f
         for fwd in (False, True):
             assert (ref.fft(fid, x, 256, fwd) == oracle.fft(fid, x, 256, fwd)).all()
+
+
+def test_host_transcript_helpers_match_oracle(oracle):
+    """lf_transcript_init / write_bytes / challenge_bytes (host side of the commit/prove split):
+    the state crosses the ABI between every operation, including in the middle of a challenge block"""
+    import longfellow_zk_b200 as lf
+    from longfellow_zk_b200 import api
+    u32 = lambda v: struct.pack("<I", v)
+    ts = api.transcripts(1, b"test")[0]
+    got = b""
+    api.transcript_write(ts, b"hello")
+    got += api.transcript_challenge(ts, 40)
+    got += api.transcript_challenge(ts, 5)     # continues inside the third AES block
+    got += api.transcript_challenge(ts, 20)
+    api.transcript_write(ts, bytes(range(100)))
+    got += api.transcript_challenge(ts, 16)
+    api.transcript_write(ts, b"")
+    got += api.transcript_challenge(ts, 1)
+    s = (b"B" + u32(5) + b"hello" + b"R" + u32(40) + b"R" + u32(5) + b"R" + u32(20) + b"B" + u32(100) +
+         bytes(range(100)) + b"R" + u32(16) + b"B" + u32(0) + b"R" + u32(1))
+    assert got == oracle.transcript_script(b"test", s)
