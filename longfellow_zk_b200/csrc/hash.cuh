@@ -152,6 +152,30 @@ static __device__ __noinline__ void sha256_compress_fn(uint32_t* hs, const uint3
   }
   hs[0] += a; hs[1] += b; hs[2] += c; hs[3] += d; hs[4] += e; hs[5] += f; hs[6] += g; hs[7] += hh;
 }
+// The 64 rounds alone, on an already expanded message schedule w64[64] (for long
+// messages whose bytes are known up front other threads expand the schedules, so
+// that only this part stays serial)
+static __device__ __noinline__ void sha256_rounds_fn(uint32_t* hs, const uint32_t* w64) {
+  uint32_t a = hs[0], b = hs[1], c = hs[2], d = hs[3], e = hs[4], f = hs[5], g = hs[6], hh = hs[7];
+#pragma unroll 1
+  for (int j = 0; j < 64; j += 16) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) LF_SHA_ROUND(kSha256K_dev[j + i], w64[j + i])
+  }
+  hs[0] += a; hs[1] += b; hs[2] += c; hs[3] += d; hs[4] += e; hs[5] += f; hs[6] += g; hs[7] += hh;
+}
+// message schedule of one block given as 16 big-endian words
+static __device__ __forceinline__ void sha256_expand(const uint32_t* w16, uint32_t* w64) {
+#pragma unroll
+  for (int i = 0; i < 16; ++i) w64[i] = w16[i];
+#pragma unroll 4
+  for (int i = 16; i < 64; ++i) {
+    uint32_t w15 = w64[i - 15], w2 = w64[i - 2];
+    uint32_t s0 = rotr32(w15, 7) ^ rotr32(w15, 18) ^ (w15 >> 3);
+    uint32_t s1 = rotr32(w2, 17) ^ rotr32(w2, 19) ^ (w2 >> 10);
+    w64[i] = w64[i - 16] + s0 + w64[i - 7] + s1;
+  }
+}
 #undef LF_SHA_ROUND
 #endif
 

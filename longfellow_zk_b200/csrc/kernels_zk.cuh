@@ -1143,29 +1143,79 @@ k_lig_finish(ZkDims d, ZkBufs<typename F::Elt> b, const LayerDesc* __restrict__ 
 
   for (uint32_t i = tid; i < n; i += nth) perm[i] = i;
   for (uint32_t i = tid; i < 2 * n; i += nth) mark[i] = 0;
-  // wire words of the four response arrays, converted by the whole CTA (for prime
-  // fields to_wire is a Montgomery multiplication); thread 0 then only hashes.
-  // They are staged at the start of the output slot, which is rewritten below.
-  const uint32_t ny = d.block + 2 * d.dblock;
-  uint32_t* yw = reinterpret_cast<uint32_t*>(out);
-  for (uint32_t i = tid; i < ny; i += nth) {
-    uint32_t w[F::kWords];
-    F::to_wire(w, y[i]);
-#pragma unroll
-    for (int q = 0; q < F::kWords; ++q) yw[(size_t)i * F::kWords + q] = w[q];
+  // ---- the four response arrays enter the transcript (ligero_prover.h:84-146) ----
+  // Their bytes are known up front, so only the 64 rounds per block have to be serial:
+  // the CTA assembles the byte stream (the transcript's pending buffer bytes, the array
+  // headers, the wire bytes of the elements -- for prime fields to_wire is a Montgomery
+  // multiplication) at the start of the output slot, which is rewritten below, and expands
+  // the message schedules of a chunk of blocks into shared memory; thread 0 runs the rounds.
+  constexpr uint32_t kChunk = 32;
+  __shared__ uint32_t s_w[kChunk][64];
+  __shared__ uint32_t s_pos0, s_h[8];
+  __shared__ uint64_t s_len0;
+  const uint32_t lens[4] = {d.block, d.dblock, d.r, d.dblock - d.block};
+  const uint32_t offs[4] = {0, d.block, d.block + d.dblock, d.block + d.dblock + d.block};
+  Transcript* gts = reinterpret_cast<Transcript*>(b.ts + p * sizeof(Transcript));
+  uint8_t* msg = out;
+  if (tid == 0) {
+    const Sha256& sh0 = gts->sha;
+    const uint32_t pos0 = (uint32_t)(sh0.len & 63);
+    s_pos0 = pos0;
+    s_len0 = sh0.len;
+    for (int k = 0; k < 8; ++k) s_h[k] = sh0.h[k];
+    for (uint32_t k = 0; k < pos0; ++k) msg[k] = (uint8_t)(sh0.buf[k >> 2] >> (24 - 8 * (k & 3)));
   }
   __syncthreads();
+  const uint32_t pos0 = s_pos0;
+  uint32_t abase[5];
+  abase[0] = pos0;
+  for (int a = 0; a < 4; ++a) abase[a + 1] = abase[a] + 9 + lens[a] * F::kBytes;
+  const uint32_t tbytes = abase[4];  // bytes of the pending block(s) once everything is appended
+  if (tid < 4) {
+    uint8_t* h = msg + abase[tid];
+    h[0] = 2;  // TAG_ARRAY, then the 64-bit little-endian length (transcript.h:144-153,160-171)
+    for (int k = 0; k < 8; ++k) h[1 + k] = k < 4 ? (uint8_t)(lens[tid] >> (8 * k)) : 0;
+  }
+  const uint32_t nelt = lens[0] + lens[1] + lens[2] + lens[3];
+  for (uint32_t i = tid; i < nelt; i += nth) {
+    uint32_t a = 0, j = i;
+    while (j >= lens[a]) j -= lens[a++];
+    uint32_t w[F::kWords];
+    F::to_wire(w, y[offs[a] + j]);
+    uint8_t* o = msg + abase[a] + 9 + (size_t)j * F::kBytes;
+#pragma unroll
+    for (int q = 0; q < F::kWords; ++q) {
+      o[4 * q] = (uint8_t)w[q];
+      o[4 * q + 1] = (uint8_t)(w[q] >> 8);
+      o[4 * q + 2] = (uint8_t)(w[q] >> 16);
+      o[4 * q + 3] = (uint8_t)(w[q] >> 24);
+    }
+  }
+  __syncthreads();
+  const uint32_t nblk = tbytes / 64;
+  for (uint32_t c0 = 0; c0 < nblk; c0 += kChunk) {
+    const uint32_t cnt = min(kChunk, nblk - c0);
+    for (uint32_t j = tid; j < cnt; j += nth) {
+      const uint32_t* src = reinterpret_cast<const uint32_t*>(msg + (size_t)(c0 + j) * 64);
+      uint32_t w16[16];
+#pragma unroll
+      for (int k = 0; k < 16; ++k) w16[k] = bswap32(src[k]);
+      sha256_expand(w16, s_w[j]);
+    }
+    __syncthreads();
+    if (tid == 0)
+      for (uint32_t j = 0; j < cnt; ++j) sha256_rounds_fn(s_h, s_w[j]);
+    __syncthreads();
+  }
   if (tid == 0) {
-    Transcript* gts = reinterpret_cast<Transcript*>(b.ts + p * sizeof(Transcript));
     Transcript ts = *gts;
     ts.use_tables(&s_aes);
-    const uint32_t lens[4] = {d.block, d.dblock, d.r, d.dblock - d.block};
-    const uint32_t offs[4] = {0, d.block, d.block + d.dblock, d.block + d.dblock + d.block};
-    for (int a = 0; a < 4; ++a) {
-      ts.begin_array(lens[a]);
-      const uint32_t* src = yw + (size_t)offs[a] * F::kWords;
-      for (uint32_t i = 0; i < lens[a] * F::kWords; ++i) ts.sha.put_word_be(bswap32(src[i]));
-    }
+    ts.have_prf = 0;  // a write drops the challenge stream (transcript.h:174-178)
+    for (int k = 0; k < 8; ++k) ts.sha.h[k] = s_h[k];
+    ts.sha.len = s_len0 + (tbytes - pos0);
+    for (int k = 0; k < 16; ++k) ts.sha.buf[k] = 0;
+    for (uint32_t k = nblk * 64; k < tbytes; ++k)
+      ts.sha.buf[(k & 63) >> 2] |= (uint32_t)msg[k] << (24 - 8 * (k & 3));
     // RandomEngine::choose (random.h:92-105)
     for (uint32_t i = 0; i < d.nreq; ++i) {
       uint32_t j = i + ts.nat(n - i);

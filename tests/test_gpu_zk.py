@@ -138,3 +138,16 @@ def test_every_sumcheck_shape_matches_oracle(ctx, oracle, name, fid, B):
     assert (status == 0).all()
     for i, pr in enumerate(proofs):
         assert pr == want[i % 4], f"proof {i} of {B}"
+
+
+def test_growing_and_shrinking_batches_on_one_circuit(sha, oracle):
+    """staging and per-proof buffers are re-allocated when a later batch is larger"""
+    import longfellow_zk_b200 as lf
+    c, circ, wit = sha
+    p = lf.ZkProver(c)
+    want = oracle.Circuit(GF, circ).prove(wit, rng_bytes(1, c.info["rng_bytes"]))["proof"]
+    for B in (1, 3, 2, 11, 5):
+        rng = np.stack([rng_bytes(1 + i, c.info["rng_bytes"]) for i in range(B)])
+        W = np.repeat(np.frombuffer(wit, np.uint8)[None, :], B, axis=0)
+        proofs, status = p.prove_batch(W, rng)
+        assert (status == 0).all() and proofs[0] == want, B
