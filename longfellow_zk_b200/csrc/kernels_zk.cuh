@@ -1113,8 +1113,11 @@ __device__ __forceinline__ void put_digest(uint8_t* dst, const uint32_t* be_word
   }
 }
 
+// 128 threads, 8 CTAs per SM: the kernel is bound by one thread per proof running the
+// SHA-256 rounds, so a whole batch of 1024 proofs should be resident at once (at 256
+// threads and 124 registers only 2 CTAs fitted an SM: 3.5 waves).
 template <class F>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(128, 8)
 k_lig_finish(ZkDims d, ZkBufs<typename F::Elt> b, const LayerDesc* __restrict__ layers) {
   typedef typename F::Elt Elt;
   const size_t p = blockIdx.x;
