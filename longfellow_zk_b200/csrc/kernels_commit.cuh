@@ -201,6 +201,10 @@ __device__ __forceinline__ Cx<F> cx_sub(const Cx<F>& a, const Cx<F>& b) {
   return Cx<F>{F::sub(a.re, b.re), F::sub(a.im, b.im)};
 }
 template <class F>
+__device__ __forceinline__ Cx<F> cx_neg(const Cx<F>& a) {
+  return Cx<F>{F::neg(a.re), F::neg(a.im)};
+}
+template <class F>
 __device__ __forceinline__ Cx<F> cx_conj(const Cx<F>& a) {
   return Cx<F>{a.re, F::neg(a.im)};
 }
@@ -255,14 +259,39 @@ k_rs_fp_fft_rows(typename F::Elt* __restrict__ data, size_t row_stride, size_t b
     }
     __syncthreads();
   }
-  for (; lg >= 1; --lg) {
-    const uint32_t half = 1u << (lg - 1), step = M >> lg;
+  // Remaining stages two at a time (radix 4: three twiddle multiplications per four
+  // points instead of four, half the barriers).  W^(e) for e in [0, 2M): W^M = -1.
+  // J = W^(M/2) is the element of order 4, i.e. +i or -i; multiplying by it is free.
+  const bool j_is_i = (M >= 2) && F::eq(Wk[M / 2].im, F::one());
+  auto Wpow = [&](uint32_t e) { return e < M ? Wk[e] : cx_neg<F>(Wk[e - M]); };
+  auto mulJ = [&](const Cx<F>& z) { return j_is_i ? cx_muli<F>(z) : cx_mulmi<F>(z); };     // z * J
+  auto mulJinv = [&](const Cx<F>& z) { return j_is_i ? cx_mulmi<F>(z) : cx_muli<F>(z); };  // z / J
+  for (; lg >= 2; lg -= 2) {
+    const uint32_t q = 1u << (lg - 2), step = M >> lg;  // block 4q, twiddle base e1 = 2 j step
+    for (uint32_t t = tid; t < M / 4; t += nth) {
+      const uint32_t j = t & (q - 1), i = (t >> (lg - 2)) << lg, e1 = 2 * j * step;
+      const Cx<F> a0 = a[i + j], a1 = a[i + j + q], a2 = a[i + j + 2 * q], a3 = a[i + j + 3 * q];
+      const Cx<F> t0 = cx_add<F>(a0, a2), t1 = cx_add<F>(a1, a3), t2 = cx_sub<F>(a0, a2),
+                  t3 = mulJinv(cx_sub<F>(a1, a3));
+      const Cx<F> c1 = cx_sub<F>(t0, t1), c2 = cx_add<F>(t2, t3), c3 = cx_sub<F>(t2, t3);
+      a[i + j] = cx_add<F>(t0, t1);
+      if (j == 0) {
+        a[i + j + q] = c1;
+        a[i + j + 2 * q] = c2;
+        a[i + j + 3 * q] = c3;
+      } else {
+        a[i + j + q] = cx_mul<F>(c1, cx_conj<F>(Wpow(2 * e1)));
+        a[i + j + 2 * q] = cx_mul<F>(c2, cx_conj<F>(Wpow(e1)));
+        a[i + j + 3 * q] = cx_mul<F>(c3, cx_conj<F>(Wpow(3 * e1)));
+      }
+    }
+    __syncthreads();
+  }
+  if (lg == 1) {  // one radix-2 stage left (distance 1, twiddle 1)
     for (uint32_t t = tid; t < M / 2; t += nth) {
-      uint32_t j = t & (half - 1), i = (t >> (lg - 1)) << lg;
-      Cx<F> u = a[i + j], v = a[i + j + half];
-      a[i + j] = cx_add<F>(u, v);
-      Cx<F> dlt = cx_sub<F>(u, v);
-      a[i + j + half] = (j == 0) ? dlt : cx_mul<F>(dlt, cx_conj<F>(Wk[2 * j * step]));
+      Cx<F> u = a[2 * t], v = a[2 * t + 1];
+      a[2 * t] = cx_add<F>(u, v);
+      a[2 * t + 1] = cx_sub<F>(u, v);
     }
     __syncthreads();
   }
@@ -291,16 +320,37 @@ k_rs_fp_fft_rows(typename F::Elt* __restrict__ data, size_t row_stride, size_t b
   }
   __syncthreads();
   // inverse: decimation in time on the bit-reversed array, twiddle V^e = W^(2e)
-  for (uint32_t lg = 1; lg <= logM; ++lg) {
-    const uint32_t half = 1u << (lg - 1), step = M >> lg;
-    for (uint32_t t = tid; t < M / 2; t += nth) {
-      uint32_t j = t & (half - 1), i = (t >> (lg - 1)) << lg;
-      Cx<F> u = a[i + j], v = a[i + j + half];
-      Cx<F> tv = (j == 0) ? v : cx_mul<F>(v, Wk[2 * j * step]);
-      a[i + j] = cx_add<F>(u, tv);
-      a[i + j + half] = cx_sub<F>(u, tv);
+  {
+    uint32_t li = 1;
+    if (logM & 1) {  // odd number of stages: the first one (distance 1, twiddle 1) alone
+      for (uint32_t t = tid; t < M / 2; t += nth) {
+        Cx<F> u = a[2 * t], v = a[2 * t + 1];
+        a[2 * t] = cx_add<F>(u, v);
+        a[2 * t + 1] = cx_sub<F>(u, v);
+      }
+      __syncthreads();
+      li = 2;
     }
-    __syncthreads();
+    for (; li + 1 <= logM; li += 2) {  // stages li and li+1 together: block 4q = 2^(li+1)
+      const uint32_t lgb = li + 1, q = 1u << (li - 1), step = M >> lgb;
+      for (uint32_t t = tid; t < M / 4; t += nth) {
+        const uint32_t j = t & (q - 1), i = (t >> (li - 1)) << lgb, e1 = 2 * j * step;
+        const Cx<F> x0 = a[i + j];
+        Cx<F> A = a[i + j + q], B = a[i + j + 2 * q], C = a[i + j + 3 * q];
+        if (j != 0) {
+          A = cx_mul<F>(A, Wpow(2 * e1));
+          B = cx_mul<F>(B, Wpow(e1));
+          C = cx_mul<F>(C, Wpow(3 * e1));
+        }
+        const Cx<F> s0 = cx_add<F>(x0, A), s1 = cx_sub<F>(x0, A), s2 = cx_add<F>(B, C),
+                    s3 = mulJ(cx_sub<F>(B, C));
+        a[i + j] = cx_add<F>(s0, s2);
+        a[i + j + q] = cx_add<F>(s1, s3);
+        a[i + j + 2 * q] = cx_sub<F>(s0, s2);
+        a[i + j + 3 * q] = cx_sub<F>(s1, s3);
+      }
+      __syncthreads();
+    }
   }
   for (uint32_t k = n + tid; k < m; k += nth) {
     const Cx<F>& q = a[k >> 1];
