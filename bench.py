@@ -9,13 +9,13 @@ A step = one batch of B independent proofs (fresh witness buffer, RNG bytes and
 transcript per proof) through the whole prover hot path: tableau layout, RS row
 encode, Merkle commit, on-device Fiat-Shamir transcript, eval_circuit, the layered
 sumcheck, Ligero prove and proof serialization.  `value` = proofs/s with inputs
-and outputs resident in HBM: the K steps are issued alternately on two
-contexts/streams (so one batch's thinly parallel kernels run under the other's
+and outputs resident in HBM: the K steps are issued round robin on three
+contexts/streams (so one batch's thinly parallel kernels run under another's
 sumcheck) and timed by one CUDA-event interval that encloses all of them, max
 over ranks; `streams.one_stream` is the same K steps back to back on one stream.
 `e2e` = the same through the host-pointer C-ABI call (lf_zk_prove_batch) with
-pinned HOST buffers, H2D and D2H inside the timed region, two batches in flight
-from two host threads; `e2e.one_batch_at_a_time` is the strictly serial figure.
+pinned HOST buffers, H2D and D2H inside the timed region, three batches in flight
+from three host threads; `e2e.one_batch_at_a_time` is the strictly serial figure.
 Independent proofs shard across GPUs with no collective (weak scaling: B proofs
 per GPU).
 """
@@ -278,32 +278,38 @@ def run_ours(args):
         prover.prove_batch_ptr(B, d_wit.data_ptr(), d_rng.data_ptr(), rstride, d_out.data_ptr(), pb,
                                d_len.data_ptr(), d_st.data_ptr(), device=True)
 
-    # A second context on its own stream: consecutive steps (batches) alternate between the two
+    # More contexts on their own streams: consecutive steps (batches) go round robin over the
     # streams, so the thinly parallel kernels of one batch (zero-block hashing of the transcript,
-    # proof serialisation, Merkle tree top) run under the other batch's sumcheck.
-    stream2 = torch.cuda.Stream()
-    ctx2 = lf.Context(local, stream=stream2.cuda_stream)
-    prover2 = lf.ZkProver(lf.Circuit(ctx2, lf.FIELD_GF2_128, circ))
-    d_out2 = torch.empty((B, pb), dtype=torch.uint8, device="cuda")
-    d_len2 = torch.zeros(B, dtype=torch.int64, device="cuda")
-    d_st2 = torch.zeros(B, dtype=torch.int32, device="cuda")
+    # proof serialisation, Merkle tree top) run under another batch's sumcheck.
+    NS = 3  # streams in flight (tools/streams_sweep.py: 1: 11.5 k, 2: 12.1 k, 3: 12.6 k, 4: 12.7 k proofs/s)
+    xstreams = [torch.cuda.Stream() for _ in range(NS - 1)]
+    xctx = [lf.Context(local, stream=s.cuda_stream) for s in xstreams]
+    xprover = [lf.ZkProver(lf.Circuit(cx, lf.FIELD_GF2_128, circ)) for cx in xctx]
+    xout = [(torch.empty((B, pb), dtype=torch.uint8, device="cuda"), torch.zeros(B, dtype=torch.int64, device="cuda"),
+             torch.zeros(B, dtype=torch.int32, device="cuda")) for _ in range(NS - 1)]
 
-    def step_dev2():
-        prover2.prove_batch_ptr(B, d_wit.data_ptr(), d_rng.data_ptr(), rstride, d_out2.data_ptr(), pb,
-                                d_len2.data_ptr(), d_st2.data_ptr(), device=True)
+    def step_dev_x(k):
+        o = xout[k]
+        xprover[k].prove_batch_ptr(B, d_wit.data_ptr(), d_rng.data_ptr(), rstride, o[0].data_ptr(), pb,
+                                   o[1].data_ptr(), o[2].data_ptr(), device=True)
 
-    def timed_two_streams(steps):
-        """K steps issued alternately on the two streams; one CUDA-event interval on `stream`
-        that starts before the first launch on either stream and ends after the last on both."""
+    def timed_streams(steps):
+        """K steps issued round robin on the NS streams; one CUDA-event interval on `stream`
+        that starts before the first launch on any stream and ends after the last on all."""
         barrier()
-        e0, e1, ej = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True),
-                      torch.cuda.Event())
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
-        stream2.wait_event(e0)
+        for s in xstreams:
+            s.wait_event(e0)
         for i in range(steps):
-            (step_dev2 if i & 1 else step_dev)()
-        ej.record(stream2)
-        stream.wait_event(ej)
+            if i % NS == 0:
+                step_dev()
+            else:
+                step_dev_x(i % NS - 1)
+        for s in xstreams:
+            ej = torch.cuda.Event()
+            ej.record(s)
+            stream.wait_event(ej)
         e1.record(stream)
         torch.cuda.synchronize()
         t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
@@ -342,18 +348,20 @@ def run_ours(args):
     # ---- warm-up + correctness of what is being timed
     for _ in range(max(args.warmup, 3)):
         step_dev()
-        step_dev2()
+        for k in range(NS - 1):
+            step_dev_x(k)
     torch.cuda.synchronize()
-    assert int(d_st.abs().sum().item()) == 0 and int(d_st2.abs().sum().item()) == 0, "prover reported failures"
+    assert int(d_st.abs().sum().item()) == 0, "prover reported failures"
     lens = d_len.cpu().numpy()
     assert (lens > 100000).all()
-    assert torch.equal(d_out[:4], d_out2[:4])  # same inputs, same proofs on either stream
+    for o in xout:  # same inputs, same proofs on every stream
+        assert int(o[2].abs().sum().item()) == 0 and torch.equal(d_out[:4], o[0][:4])
 
-    # ---- device-resident throughput (value): K steps, alternating between the two streams
+    # ---- device-resident throughput (value): K steps, round robin over the NS streams
     sampler = ClockSampler(local) if rank == 0 else None
-    l0 = ctx.launch_count + ctx2.launch_count
-    ms_total = timed_two_streams(args.steps)
-    launches = ctx.launch_count + ctx2.launch_count - l0
+    l0 = ctx.launch_count + sum(cx.launch_count for cx in xctx)
+    ms_total = timed_streams(args.steps)
+    launches = ctx.launch_count + sum(cx.launch_count for cx in xctx) - l0
     clocks = sampler.stop() if sampler else None
     value = world * B * args.steps / (ms_total * 1e-3)
     # the same K steps back to back on ONE stream (no overlap between batches)
@@ -376,27 +384,33 @@ def run_ours(args):
     ms_e2e = timed(step_host, e2e_steps, use_events=False)
     e2e_serial = world * B * e2e_steps / (ms_e2e * 1e-3)
     assert int(h_st.abs().sum().item()) == 0
-    # the same call from two host threads, each with its own context / stream / pinned buffers, so
-    # that one batch's PCIe copies overlap the other batch's kernels (what a serving loop does)
+    # the same call from NS host threads, each with its own context / stream / pinned buffers, so
+    # that one batch's PCIe copies overlap the other batches' kernels (what a serving loop does)
     import threading
-    h2 = [h_wit.clone().pin_memory(), h_rng.clone().pin_memory(), torch.empty((B, pb), dtype=torch.uint8).pin_memory(),
-          torch.zeros(B, dtype=torch.int64).pin_memory(), torch.zeros(B, dtype=torch.int32).pin_memory()]
+    hx = [[h_wit.clone().pin_memory(), h_rng.clone().pin_memory(), torch.empty((B, pb), dtype=torch.uint8).pin_memory(),
+           torch.zeros(B, dtype=torch.int64).pin_memory(), torch.zeros(B, dtype=torch.int32).pin_memory()]
+          for _ in range(NS - 1)]
 
-    def step_host2():
-        prover2.prove_batch_ptr(B, h2[0].data_ptr(), h2[1].data_ptr(), rstride, h2[2].data_ptr(), pb,
-                                h2[3].data_ptr(), h2[4].data_ptr(), device=False)
-    step_host2()
+    def step_host_x(k):
+        h = hx[k]
+        xprover[k].prove_batch_ptr(B, h[0].data_ptr(), h[1].data_ptr(), rstride, h[2].data_ptr(), pb,
+                                   h[3].data_ptr(), h[4].data_ptr(), device=False)
+    for k in range(NS - 1):
+        step_host_x(k)
 
-    def both():
-        th = threading.Thread(target=lambda: [step_host2() for _ in range(e2e_steps)])
-        th.start()
+    def all_threads():
+        ths = [threading.Thread(target=lambda k=k: [step_host_x(k) for _ in range(e2e_steps)]) for k in range(NS - 1)]
+        for th in ths:
+            th.start()
         for _ in range(e2e_steps):
             step_host()
-        th.join()
-    ms_pipe = timed(both, 1, use_events=False)
-    e2e_value = world * B * 2 * e2e_steps / (ms_pipe * 1e-3)
-    assert int(h2[4].abs().sum().item()) == 0 and int(h2[3][0].item()) == int(h_len[0].item())
-    ms_e2e_step = ms_pipe / (2 * e2e_steps)
+        for th in ths:
+            th.join()
+    ms_pipe = timed(all_threads, 1, use_events=False)
+    e2e_value = world * B * NS * e2e_steps / (ms_pipe * 1e-3)
+    for h in hx:
+        assert int(h[4].abs().sum().item()) == 0 and int(h[3][0].item()) == int(h_len[0].item())
+    ms_e2e_step = ms_pipe / (NS * e2e_steps)
     # the proofs that came back through the host path equal the device-resident ones
     torch.cuda.synchronize()
     n0 = int(h_len[0].item())
@@ -471,14 +485,14 @@ def run_ours(args):
                             ninputs=info["ninputs"], nterms=info["nterms"], tableau=[info["nrow"], info["block_enc"]],
                             proof_bytes=int(lens[0])),
                 clocks=clocks,
-                streams=dict(n=2, note="steps alternate between two contexts/streams; the interval is one "
-                                       "CUDA-event pair on the first stream enclosing all launches of both",
+                streams=dict(n=NS, note="steps go round robin over NS contexts/streams; the interval is one "
+                                        "CUDA-event pair on the first stream enclosing all launches of all",
                              one_stream=dict(value=world * B * args.steps / (ms_one_stream * 1e-3),
                                              ms_per_step=ms_one_stream / args.steps)),
                 e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=B * (wb + rb),
                          d2h_bytes_per_step=B * (((int(lens.max()) + 15) & ~15) + 12), ms_per_step=ms_e2e_step,
-                         how="lf_zk_prove_batch with pinned host buffers; two batches in flight (two host "
-                             "threads, two contexts/streams) so PCIe copies overlap the other batch's kernels",
+                         how="lf_zk_prove_batch with pinned host buffers; NS batches in flight (one host "
+                             "thread, context and stream each) so PCIe copies overlap the other batches' kernels",
                          one_batch_at_a_time=dict(value=e2e_serial, ms_per_step=ms_e2e / e2e_steps)),
                 gpu_launches=launches, roofline=roofline, cpu_baseline=cpu,
                 latency_ms_per_proof_batch1=lat_ms,
