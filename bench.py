@@ -445,8 +445,22 @@ def run_ours(args):
     alg_bytes = info["sumcheck_alg_bytes"] * B
     achieved = alg_bytes / (sc_ms * 1e-3) / 1e9
     gmul_peak = ctx.microbench(2)  # measured GF(2^128) multiply rate of this formulation (Gmul/s)
+    # DRAM bytes of one launch of that kernel from the committed `ncu --set full` capture (same batch size)
+    traffic, traffic_src = None, None
+    try:
+        cap = open(os.path.join(ROOT, "profiles", "r1_sumcheck_occ8_full.txt")).read()
+        import re
+        grid = int(re.search(r"launch__grid_size\s+(\d+)", cap).group(1))
+        rd = float(re.search(r"dram__bytes_read.sum\s+([\d.]+)\s+Gbyte", cap).group(1))
+        wr = float(re.search(r"dram__bytes_write.sum\s+([\d.]+)\s+Gbyte", cap).group(1))
+        traffic = (rd + wr) * 1e9 * B / grid
+        traffic_src = "profiles/r1_sumcheck_occ8_full.txt: dram__bytes_read.sum + dram__bytes_write.sum of one " \
+                      "launch of %d proofs, scaled to %d (bytes)" % (grid, B)
+    except Exception:
+        pass
     roofline = dict(bound="hbm", kernel="k_zk_sumcheck", achieved=achieved, peak=hbm_peak, unit="GB/s",
-                    frac=achieved / hbm_peak, traffic=None, peak_source=peak_src,
+                    frac=achieved / hbm_peak, traffic=traffic, traffic_source=traffic_src,
+                    algorithmic_bytes_per_launch=alg_bytes, peak_source=peak_src,
                     kernel_ms_per_launch=sc_ms, share_of_step=sc_ms / sum(stage_acc.values()),
                     algorithmic_bytes_per_proof=info["sumcheck_alg_bytes"],
                     integer_pipe=dict(

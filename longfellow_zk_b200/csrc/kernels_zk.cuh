@@ -59,7 +59,7 @@ __global__ void k_zk_witness(ZkDims d, ZkBufs<typename F::Elt> b, const LayerDes
   if (i < d.n_witness) {
     const uint8_t* w = b.witness_in + p * b.witness_stride + (size_t)(i + d.npub) * F::kBytes;
     wit[i] = F::from_bytes(w, &ok);
-    if (!ok) b.status[p] = -3;  // non-canonical input element
+    if (!ok) atomicCAS(&b.status[p], 0, -3);  // (the first error of a proof sticks) non-canonical input element
     return;
   }
   uint32_t q = i - d.n_witness;  // index inside the pad block
@@ -78,7 +78,7 @@ __global__ void k_zk_witness(ZkDims d, ZkBufs<typename F::Elt> b, const LayerDes
     Elt c = F::sample_bytes(rng + (size_t)(layers[ly].sc_off + cnt - 1) * F::kBytes, &rok);
     wit[i] = F::mul(a, c);
   }
-  if (!rok) b.status[p] = -6;  // a sample needs a re-draw (prime fields, probability 2^-32 each)
+  if (!rok) atomicCAS(&b.status[p], 0, -6);  // (the first error of a proof sticks) a sample needs a re-draw (prime fields, probability 2^-32 each)
 }
 
 // ----------------------------------------------------------------------------
@@ -159,7 +159,7 @@ k_zk_layout(ZkDims d, ZkBufs<typename F::Elt> b, const uint32_t* __restrict__ ro
       T[j] = e;
     }
   }
-  if (!rok) b.status[p] = -6;
+  if (!rok) atomicCAS(&b.status[p], 0, -6);
 }
 
 // ----------------------------------------------------------------------------
@@ -280,7 +280,7 @@ k_zk_eval_layer(ZkDims d, ZkBufs<typename F::Elt> b, const uint32_t* __restrict_
   } else {
     b.wl[p * d.wl_elts + L.out_off + g] = out;
   }
-  if (bad) b.status[p] = -5;
+  if (bad) atomicCAS(&b.status[p], 0, -5);
 }
 
 // ----------------------------------------------------------------------------
@@ -781,7 +781,7 @@ __device__ __forceinline__ void sumcheck_body(const ZkDims& d, const ZkBufs<type
   }
   if (leader) {
     *reinterpret_cast<Transcript*>(b.ts + p * sizeof(Transcript)) = sh.ts;
-    if (sh.fail) b.status[p] = -100;  // internal inconsistency: never expected
+    if (sh.fail) atomicCAS(&b.status[p], 0, -100);  // (the first error of a proof sticks) internal inconsistency: never expected
     sh.prof[2] = clock64() - sh.prof[3];
     long long* dbg = reinterpret_cast<long long*>(hqbuf);  // free after the last layer
     for (int i = 0; i < 8; ++i) dbg[i] = sh.prof[i];

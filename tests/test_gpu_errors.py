@@ -1,0 +1,67 @@
+"""Error behaviour of the C ABI: the reference aborts on invariant violations (lib/util/panic.h:27-36)
+and returns false for an unsatisfied witness; here every such case is a status code, never a crash and
+never a silently wrong proof."""
+import numpy as np
+import pytest
+
+from fixtures import load, rng_bytes
+
+pytestmark = pytest.mark.gpu
+
+
+def test_malformed_circuits_are_rejected(ctx):
+    import longfellow_zk_b200 as lf
+    circ, _ = load("sha1_gf128")
+    for bad in (b"", circ[:100], b"\x02" + circ[1:], circ[:-1], bytes(len(circ))):
+        with pytest.raises(lf.LongfellowError) as e:
+            lf.Circuit(ctx, 4, bad)
+        assert e.value.code == -3, (len(bad), e.value)            # LF_ERR_FORMAT
+    # like CircuitReader::from_bytes (proto/circuit_reader.h:83-140) the parser consumes one circuit and
+    # leaves what follows alone (the mdoc file holds two circuits back to back)
+    assert lf.Circuit(ctx, 4, circ + b"\x00" * 7).info["nterms"] == 155197
+    with pytest.raises(lf.LongfellowError) as e:
+        lf.Circuit(ctx, 1, circ)                                  # field id in the file is 4, not 1
+    assert e.value.code == -3
+    with pytest.raises(lf.LongfellowError) as e:
+        lf.Circuit(ctx, 101, circ)                                # no ZK path over Fp128
+    assert e.value.code == -4                                     # LF_ERR_UNSUPPORTED
+
+
+def test_short_buffers_are_rejected(ctx):
+    import ctypes as C
+    import longfellow_zk_b200 as lf
+    from longfellow_zk_b200 import _native
+    circ, wit = load("sha1_gf128")
+    c = lf.Circuit(ctx, 4, circ)
+    info = c.info
+    W = np.frombuffer(wit, np.uint8).copy()
+    out = np.zeros(info["max_proof_bytes"], np.uint8)
+    lens, st = np.zeros(1, np.uint64), np.zeros(1, np.int32)
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    rng = rng_bytes(3, info["rng_bytes"])
+    call = lambda rstride, ostride: _native.lib().lf_zk_prove_batch(c._h, 1, p(W), p(rng), rstride, b"test", 4, p(out),
+                                                                    ostride, p(lens), p(st))
+    assert call(info["rng_bytes"] - 1, info["max_proof_bytes"]) == -6      # LF_ERR_RNG
+    assert call(info["rng_bytes"], info["max_proof_bytes"] - 16) == -7     # LF_ERR_CAPACITY
+    assert call(info["rng_bytes"], info["max_proof_bytes"]) == 0 and st[0] == 0 and lens[0] > 100000
+
+
+def test_non_canonical_witness_and_coins_are_flagged_per_proof(ctx, oracle):
+    """Fp256: a witness element >= p is LF_ERR_FORMAT for that proof (the reference's of_bytes_field
+    fails); a caller-random element >= p is LF_ERR_RNG (documented deviation: the reference re-samples);
+    the other proofs of the batch are unaffected and still equal the oracle's."""
+    import longfellow_zk_b200 as lf
+    circ, wit = load("ecdsa1_p256")
+    c = lf.Circuit(ctx, 1, circ)
+    n = c.info["rng_bytes"]
+    good = rng_bytes(50, 1 << 19)[:n].copy()
+    good[31::32] &= 0x7F
+    want = oracle.Circuit(1, circ).prove(wit, good)["proof"]
+    W = np.repeat(np.frombuffer(wit, np.uint8)[None, :], 3, axis=0).copy()
+    W[1, 32 * 10:32 * 11] = 0xFF                         # input 10 of proof 1 = 2^256 - 1 >= p
+    rng = np.stack([good, good, good]).copy()
+    rng[2, 0:32] = 0xFF                                   # first sampled element of proof 2 >= p
+    proofs, status = lf.ZkProver(c).prove_batch(W, rng)
+    assert status[0] == 0 and proofs[0] == want
+    assert status[1] == -3 and proofs[1] == b""
+    assert status[2] == -6 and proofs[2] == b""
