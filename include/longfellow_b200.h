@@ -43,7 +43,8 @@ enum lf_status {
   LF_ERR_FORMAT = -3,       /* malformed circuit bytes / non-canonical element */
   LF_ERR_UNSUPPORTED = -4,  /* field or shape not built yet */
   LF_ERR_WITNESS = -5,      /* witness does not satisfy the circuit (ZkProver::prove == false) */
-  LF_ERR_RNG = -6,          /* caller-supplied randomness exhausted */
+  LF_ERR_RNG = -6,          /* caller-supplied randomness too short, or (prime fields) a caller-random
+                               element was >= p: retry that proof with fresh coins */
   LF_ERR_CAPACITY = -7      /* output buffer too small */
 };
 
