@@ -130,6 +130,9 @@ typedef struct lf_circuit_info {
   /* the same total split by stage (SURVEY.md 8(d) formulas): RS row encodes of commit,
    * eval_circuit, Ligero prove (incl. its RS rows); Merkle commit compressions */
   size_t rs_mults, eval_mults, ligero_mults, merkle_compressions;
+  /* bytes of the LFC1 input this circuit occupied; the mdoc circuit file holds the signature
+   * circuit and the hash circuit back to back (lib/circuits/mdoc/mdoc_zk.cc:440-456) */
+  size_t lfc1_bytes;
 } lf_circuit_info;
 int lf_circuit_get_info(const lf_circuit* c, lf_circuit_info* info);
 

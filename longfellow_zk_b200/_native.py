@@ -20,7 +20,7 @@ class CircuitInfo(C.Structure):
         "ninputs", "npub_in", "nl", "nterms", "kbytes", "witness_bytes", "rng_bytes",
         "max_proof_bytes", "block_enc", "block", "dblock", "block_ext", "nrow", "r", "w", "nwrow",
         "nqtriples", "nreq", "nw", "sumcheck_alg_bytes", "sumcheck_mults", "total_mults", "sha_compressions",
-        "rs_mults", "eval_mults", "ligero_mults", "merkle_compressions")]
+        "rs_mults", "eval_mults", "ligero_mults", "merkle_compressions", "lfc1_bytes")]
 
 
 class Transcript(C.Structure):

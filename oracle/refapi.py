@@ -275,6 +275,81 @@ def prove_pair(circ_a, circ_b, wit_a, wit_b, rng, tinit=b"test", rate=7, nreq=13
                 rng_used_a=ua.value, rng_used_total=ut.value)
 
 
+# ---- the reference's mdoc prover split at its ZkProver calls (oracle/_ref/libref_mdoc.so) ----
+LIBREF_MDOC = os.path.join(_HERE, "_ref", "libref_mdoc.so")
+_mdoc_lib = None
+
+
+def mdoc_available():
+    return os.path.exists(LIBREF_MDOC)
+
+
+def zstd_decompress(data):
+    z = C.CDLL("libzstd.so.1")
+    z.ZSTD_decompress.restype = C.c_size_t
+    z.ZSTD_getFrameContentSize.restype = C.c_ulonglong
+    cap = z.ZSTD_getFrameContentSize(data, len(data))
+    buf = C.create_string_buffer(cap)
+    n = z.ZSTD_decompress(buf, cap, data, len(data))
+    assert not z.ZSTD_isError(n)
+    return buf.raw[:n]
+
+
+class MdocCase:
+    """mdoc_tests[0] + age_over_18 on kZkSpecs[0] (the reference's benchmark claim,
+    circuits/mdoc/mdoc_zk_test.cc:652-656): filled witnesses, and run_mdoc_prover from
+    "Run prover" on with replayed commit coins."""
+
+    def __init__(self, circuit_raw):
+        global _mdoc_lib
+        if _mdoc_lib is None:
+            _mdoc_lib = C.CDLL(LIBREF_MDOC)
+            _mdoc_lib.ref_mdoc_prepare.restype = C.c_void_p
+        self.lib = _mdoc_lib
+        self.h = self.lib.ref_mdoc_prepare(C.c_char_p(circuit_raw), C.c_size_t(len(circuit_raw)))
+        if not self.h:
+            raise RuntimeError("ref_mdoc_prepare failed")
+        out = (C.c_size_t * 8)()
+        self.lib.ref_mdoc_info(C.c_void_p(self.h), out)
+        (self.sig_ninputs, self.sig_npub, self.hash_ninputs, self.hash_npub, self.block_enc_sig,
+         self.block_enc_hash, tr_len, self.version) = [int(x) for x in out]
+        tr = np.zeros(tr_len, np.uint8)
+        self.lib.ref_mdoc_transcript(C.c_void_p(self.h), _p(tr))
+        self.transcript = tr.tobytes()
+        rate, nreq = C.c_size_t(), C.c_size_t()
+        self.lib.ref_mdoc_ligero_params(C.byref(rate), C.byref(nreq))
+        self.rate, self.nreq = rate.value, nreq.value
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.lib.ref_mdoc_free(C.c_void_p(self.h))
+            self.h = None
+
+    def witnesses(self):
+        ws, wh = np.zeros(self.sig_ninputs * 32, np.uint8), np.zeros(self.hash_ninputs * 16, np.uint8)
+        self.lib.ref_mdoc_witness(C.c_void_p(self.h), _p(ws), _p(wh))
+        return ws, wh
+
+    def update_macs(self, av):
+        ws, wh = np.zeros(self.sig_ninputs * 32, np.uint8), np.zeros(self.hash_ninputs * 16, np.uint8)
+        macs = np.zeros(96, np.uint8)
+        self.lib.ref_mdoc_update_macs(C.c_void_p(self.h), C.c_char_p(av), _p(ws), _p(wh), _p(macs))
+        return ws, wh, macs.tobytes()
+
+    def prove(self, coins):
+        coins = _u8(coins)
+        out = np.zeros(1 << 22, np.uint8)
+        n, lh, ls, ch, ct = C.c_size_t(), C.c_size_t(), C.c_size_t(), C.c_size_t(), C.c_size_t()
+        av = np.zeros(16, np.uint8)
+        rc = self.lib.ref_mdoc_prove(C.c_void_p(self.h), _p(coins), C.c_size_t(coins.size), _p(out),
+                                     C.c_size_t(out.size), C.byref(n), C.byref(lh), C.byref(ls), C.byref(ch),
+                                     C.byref(ct), _p(av))
+        if rc != 0:
+            raise RuntimeError(f"reference mdoc prover failed rc={rc}")
+        return dict(proof=out[:n.value].tobytes(), len_hash=lh.value, len_sig=ls.value, coins_hash=ch.value,
+                    coins_total=ct.value, av=av.tobytes())
+
+
 class GpuAdapterCircuit:
     """A reference Circuit object inside libref_gpu.so, proved (1) by the reference's own
     ZkProver with GpuReedSolomonFactory injected, (2) by GpuZkProver."""

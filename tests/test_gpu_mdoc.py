@@ -1,0 +1,53 @@
+"""BASELINE config 4: the ISO mdoc proof -- the signature circuit over Fp256 (482 k quad terms) and the
+hash circuit over GF(2^128) (7.76 M quad terms, 266 x 4151 tableau) proved on ONE transcript with the
+MAC patch of the public inputs between commit and prove (lib/circuits/mdoc/mdoc_zk.cc:398-547).
+
+oracle/_ref/libref_mdoc.so is the reference's mdoc prover split at its four ZkProver calls
+(oracle/ref_build/ref_mdoc.cc); the witness comes from the reference's own fill_witness on its benchmark
+claim (mdoc_tests[0], age_over_18, kZkSpecs[0]).  The CUDA back end replaces the four calls; the result
+must be run_mdoc_prover's bytes: [6 MACs][hash proof][signature proof]."""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_mdoc_proof_matches_reference(ctx):
+    import longfellow_zk_b200 as lf
+    from longfellow_zk_b200 import api
+    from oracle import refapi as ref
+    if not ref.mdoc_available():
+        pytest.fail("oracle/_ref/libref_mdoc.so is missing: run __graft_entry__.build() where /root/reference exists")
+    raw = ref.zstd_decompress(open(os.path.join(ROOT, "tests/golden/mdoc/circuit_v7_1attr.zst"), "rb").read())
+    m = ref.MdocCase(raw)
+    coins = np.random.default_rng(2027).integers(0, 256, 4 << 20, dtype=np.uint8)
+    want = m.prove(coins)
+
+    sig = lf.Circuit(ctx, lf.FIELD_P256, raw, rate=m.rate, nreq=m.nreq, block_enc=m.block_enc_sig)
+    hsh = lf.Circuit(ctx, lf.FIELD_GF2_128, raw[sig.info["lfc1_bytes"]:], rate=m.rate, nreq=m.nreq,
+                     block_enc=m.block_enc_hash)
+    assert (sig.info["ninputs"], sig.info["npub_in"]) == (m.sig_ninputs, m.sig_npub)
+    assert (hsh.info["ninputs"], hsh.info["npub_in"]) == (m.hash_ninputs, m.hash_npub)
+    assert hsh.info["nterms"] > 7_000_000 and hsh.info["block_enc"] == 4151
+    nh, ns = hsh.info["rng_bytes"], sig.info["rng_bytes"]
+    assert nh == want["coins_hash"] and nh + ns == want["coins_total"]
+
+    ws, wh = m.witnesses()
+    ph, ps = lf.ZkProver(hsh), lf.ZkProver(sig)
+    ts = api.transcripts(1, m.transcript)
+    _, st = ph.commit_batch(wh[None, :], coins[None, :nh], ts)
+    assert st[0] == 0
+    _, st = ps.commit_batch(ws[None, :], coins[None, nh:nh + ns], ts)
+    assert st[0] == 0
+    av = api.transcript_challenge(ts[0], 16)      # generate_mac_key(tp)
+    assert av == want["av"]
+    ws2, wh2, macs = m.update_macs(av)            # compute_macs + update_macs (public inputs only)
+    proof_h, st = ph.prove_committed_batch(wh2[None, :], ts)
+    assert st[0] == 0 and len(proof_h[0]) == want["len_hash"]
+    proof_s, st = ps.prove_committed_batch(ws2[None, :], ts)
+    assert st[0] == 0 and len(proof_s[0]) == want["len_sig"]
+    got = macs + proof_h[0] + proof_s[0]
+    assert got == want["proof"]
