@@ -15,6 +15,42 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
+def test_mdoc_proof_matches_frozen_reference_output(ctx):
+    """the same sequence on the committed fixtures (tests/golden/make_golden_mdoc.py): needs nothing
+    of the reference at run time"""
+    import hashlib
+    import longfellow_zk_b200 as lf
+    from longfellow_zk_b200 import api
+    from fixtures import load_mdoc
+    f = load_mdoc()
+    e = f["expect"]
+    sig = lf.Circuit(ctx, lf.FIELD_P256, f["raw"], rate=e["rate"], nreq=e["nreq"], block_enc=e["block_enc_sig"])
+    hsh = lf.Circuit(ctx, lf.FIELD_GF2_128, f["raw"][sig.info["lfc1_bytes"]:], rate=e["rate"], nreq=e["nreq"],
+                     block_enc=e["block_enc_hash"])
+    nh, ns = hsh.info["rng_bytes"], sig.info["rng_bytes"]
+    assert nh == e["coins_hash"] and nh + ns == e["coins_total"]
+    assert (hsh.info["nrow"], hsh.info["block_enc"], hsh.info["nterms"]) == (266, 4151, 7757579)
+    ph, ps = lf.ZkProver(hsh), lf.ZkProver(sig)
+    ts = api.transcripts(1, bytes.fromhex(e["transcript"]))
+    coins = f["coins"]
+    _, st = ph.commit_batch(f["w_hash"][None, :], coins[None, :nh], ts)
+    assert st[0] == 0
+    _, st = ps.commit_batch(f["w_sig"][None, :], coins[None, nh:nh + ns], ts)
+    assert st[0] == 0
+    assert api.transcript_challenge(ts[0], 16).hex() == e["av"]
+    proof_h, st = ph.prove_committed_batch(f["w_hash_mac"][None, :], ts)
+    assert st[0] == 0 and hashlib.sha256(proof_h[0]).hexdigest() == e["hash_proof_sha256"]
+    proof_s, st = ps.prove_committed_batch(f["w_sig_mac"][None, :], ts)
+    assert st[0] == 0 and hashlib.sha256(proof_s[0]).hexdigest() == e["sig_proof_sha256"]
+    whole = bytes.fromhex(e["macs"]) + proof_h[0] + proof_s[0]
+    assert len(whole) == e["proof_len"] and hashlib.sha256(whole).hexdigest() == e["proof_sha256"]
+    # proving without the MAC patch must fail: the patched inputs are checked by the circuits
+    ts = api.transcripts(1, bytes.fromhex(e["transcript"]))
+    ph.commit_batch(f["w_hash"][None, :], coins[None, :nh], ts)
+    _, st = ph.prove_committed_batch(f["w_hash"][None, :], ts)
+    assert st[0] == -5
+
+
 def test_mdoc_proof_matches_reference(ctx):
     import longfellow_zk_b200 as lf
     from longfellow_zk_b200 import api

@@ -221,3 +221,19 @@ def test_bad_witness_rejected(oracle):
     import pytest
     with pytest.raises(RuntimeError, match="rc=-3"):
         oracle.Circuit(4, circ).prove(bytes(bad), rng_bytes(1, 1 << 18))
+
+
+def test_mdoc_fixture_is_consistent(oracle):
+    """tests/golden/mdoc: the circuit file holds the signature circuit (Fp256) then the hash circuit
+    (GF(2^128)); the frozen witnesses have the circuits' input counts and differ only in public inputs"""
+    from fixtures import load_mdoc
+    f = load_mdoc()
+    raw = f["raw"]
+    assert raw[0] == 1 and int.from_bytes(raw[1:4], "little") == 1          # version, P256_ID
+    nin_sig, npub_sig = int.from_bytes(raw[16:19], "little"), int.from_bytes(raw[10:13], "little")
+    assert f["w_sig"].size == nin_sig * 32 and f["w_sig_mac"].size == nin_sig * 32
+    d = np.nonzero((f["w_sig"] != f["w_sig_mac"]).reshape(nin_sig, 32).any(axis=1))[0]
+    assert d.size > 0 and d.max() < npub_sig                                 # the MAC patch touches public inputs only
+    assert oracle.Circuit(oracle.P256_ID, raw) is not None
+    e = f["expect"]
+    assert e["proof_len"] == 96 + e["len_hash"] + e["len_sig"] and f["coins"].size == e["coins_total"]

@@ -1,0 +1,53 @@
+"""mdoc proof (BASELINE config 4) on the GPU: commit(hash) + commit(sig) + prove(hash) + prove(sig) through
+the host-pointer C ABI on the frozen instance of tests/golden/mdoc, for a batch of B identical instances."""
+import json, os, sys, time
+import numpy as np
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+import longfellow_zk_b200 as lf
+from longfellow_zk_b200 import api
+from fixtures import load_mdoc
+
+
+def measure(batches=(1, 8, 32), reps=3):
+    f = load_mdoc(); e = f["expect"]
+    ctx = lf.Context(0)
+    t0 = time.perf_counter()
+    sig = lf.Circuit(ctx, lf.FIELD_P256, f["raw"], rate=e["rate"], nreq=e["nreq"], block_enc=e["block_enc_sig"])
+    hsh = lf.Circuit(ctx, lf.FIELD_GF2_128, f["raw"][sig.info["lfc1_bytes"]:], rate=e["rate"], nreq=e["nreq"],
+                     block_enc=e["block_enc_hash"])
+    upload_s = time.perf_counter() - t0
+    nh, ns = hsh.info["rng_bytes"], sig.info["rng_bytes"]
+    ph, ps = lf.ZkProver(hsh), lf.ZkProver(sig)
+    res = dict(upload_s=upload_s, hash_terms=hsh.info["nterms"], sig_terms=sig.info["nterms"],
+               hash_tableau=[hsh.info["nrow"], hsh.info["block_enc"]], sig_tableau=[sig.info["nrow"], sig.info["block_enc"]],
+               hash_total_mults=hsh.info["total_mults"], sig_total_mults=sig.info["total_mults"], batches=[])
+    for B in batches:
+        rep = lambda a: np.repeat(a[None, :], B, axis=0)
+        wh, ws, whm, wsm = rep(f["w_hash"]), rep(f["w_sig"]), rep(f["w_hash_mac"]), rep(f["w_sig_mac"])
+        ch, cs = rep(f["coins"][:nh]), rep(f["coins"][nh:nh + ns])
+        best = None
+        for r in range(reps + 1):
+            ts = api.transcripts(B, bytes.fromhex(e["transcript"]))
+            t = [time.perf_counter()]
+            ph.commit_batch(wh, ch, ts); t.append(time.perf_counter())
+            ps.commit_batch(ws, cs, ts); t.append(time.perf_counter())
+            for i in range(B):
+                api.transcript_challenge(ts[i], 16)
+            a, st1 = ph.prove_committed_batch(whm, ts); t.append(time.perf_counter())
+            b, st2 = ps.prove_committed_batch(wsm, ts); t.append(time.perf_counter())
+            assert (st1 == 0).all() and (st2 == 0).all()
+            d = [1e3 * (t[i + 1] - t[i]) for i in range(4)]
+            if r > 0 and (best is None or sum(d) < sum(best)):
+                best = d
+        res["batches"].append(dict(batch=B, ms_commit_hash=best[0], ms_commit_sig=best[1], ms_prove_hash=best[2],
+                                   ms_prove_sig=best[3], ms_total=sum(best), ms_per_proof=sum(best) / B,
+                                   proofs_per_s=B / sum(best) * 1e3))
+    return res
+
+
+if __name__ == "__main__":
+    r = measure()
+    print(json.dumps(r, indent=1))
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    json.dump(r, open(os.path.join(ROOT, "gpurun_out", "mdoc_bench.json"), "w"), indent=1)
