@@ -490,6 +490,46 @@ def run_ours(args):
     except Exception as ex:  # the headline line must not depend on the extra workload
         other["ecdsa_p256"] = dict(error=str(ex))
 
+    # ---- third workload (BASELINE.json configs[3]): the ISO mdoc proof, two circuits over two fields on one
+    # transcript (tests/golden/mdoc: the reference's benchmark claim frozen; tools/mdoc_bench.py)
+    try:
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        import mdoc_bench
+        md = mdoc_bench.measure(batches=(1, 32), reps=2)
+        other["mdoc"] = dict(workload="BM_MdocProver: kZkSpecs[0], mdoc_tests[0] + age_over_18; hash circuit GF(2^128) "
+                                      "7.76 M terms 266x4151, signature circuit Fp256 482 k terms 19x4096; "
+                                      "commit+commit+prove+prove through the host-pointer C ABI (H2D/D2H included)",
+                             latency_ms_per_proof_batch1=md["batches"][0]["ms_total"],
+                             value=md["batches"][1]["proofs_per_s"], unit=UNIT, proofs_per_step=32,
+                             ms_per_proof=md["batches"][1]["ms_per_proof"], detail=md)
+        from oracle import refapi
+        if refapi.mdoc_available():
+            from fixtures import load_mdoc
+            mc = refapi.MdocCase(load_mdoc()["raw"])
+            coins = np.random.default_rng(1).integers(0, 256, 1 << 20, dtype=np.uint8)
+            mc.prove(coins)
+            t0 = time.perf_counter()
+            for _ in range(3):
+                mc.prove(coins)
+            one = (time.perf_counter() - t0) / 3
+
+            def many():
+                for _ in range(2):
+                    mc.prove(coins)
+            ths = [threading.Thread(target=many) for _ in range(nthreads)]
+            t0 = time.perf_counter()
+            for th in ths:
+                th.start()
+            for th in ths:
+                th.join()
+            wall = time.perf_counter() - t0
+            other["mdoc"]["cpu_baseline"] = dict(value=2 * nthreads / wall, unit=UNIT, cores=nthreads, kind="reference",
+                                                 sample="%d threads x 2 proofs (run_mdoc_prover from 'Run prover' on, "
+                                                        "oracle/ref_build/ref_mdoc.cc)" % nthreads,
+                                                 single_thread_ms_per_proof=1e3 * one)
+    except Exception as ex:
+        other["mdoc"] = dict(error=str(ex))
+
     line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3),
                 ms_per_step=ms_total / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None,
                 dtype="gf2^128 (u32 limbs)", data="synthetic",
