@@ -15,7 +15,11 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
 from oracle import refapi as ref  # noqa: E402
 
 D = os.path.join(HERE, "mdoc")
-raw = ref.zstd_decompress(open(os.path.join(D, "circuit_v7_1attr.zst"), "rb").read())
+# the reference's circuit file of kZkSpecs[0] (zstd) -> LFC1 bytes -> xz fixture
+import lzma  # noqa: E402
+SRC = "/root/reference/lib/circuits/mdoc/circuits/8d079211715200ff06c5109639245502bfe94aa869908d31176aae4016182121"
+raw = ref.zstd_decompress(open(SRC, "rb").read())
+open(os.path.join(D, "circuits_v7_1attr.lfc1.xz"), "wb").write(lzma.compress(raw, preset=6))
 m = ref.MdocCase(raw)
 coins = np.random.default_rng(20261018).integers(0, 256, 1 << 20, dtype=np.uint8)
 want = m.prove(coins)

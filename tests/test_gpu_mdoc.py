@@ -57,7 +57,8 @@ def test_mdoc_proof_matches_reference(ctx):
     from oracle import refapi as ref
     if not ref.mdoc_available():
         pytest.skip("oracle/_ref/libref_mdoc.so not built (the fixture-based test above covers the same bytes)")
-    raw = ref.zstd_decompress(open(os.path.join(ROOT, "tests/golden/mdoc/circuit_v7_1attr.zst"), "rb").read())
+    from fixtures import load_mdoc
+    raw = load_mdoc()["raw"]
     m = ref.MdocCase(raw)
     coins = np.random.default_rng(2027).integers(0, 256, 4 << 20, dtype=np.uint8)
     want = m.prove(coins)
