@@ -496,12 +496,17 @@ def run_ours(args):
         sys.path.insert(0, os.path.join(ROOT, "tools"))
         import mdoc_bench
         md = mdoc_bench.measure(batches=(1, 128), reps=2)
+        md2 = mdoc_bench.measure_two_in_flight(B=128, rounds=2)
         other["mdoc"] = dict(workload="BM_MdocProver: kZkSpecs[0], mdoc_tests[0] + age_over_18; hash circuit GF(2^128) "
                                       "7.76 M terms 266x4151, signature circuit Fp256 482 k terms 19x4096; "
                                       "commit+commit+prove+prove through the host-pointer C ABI (H2D/D2H included)",
                              latency_ms_per_proof_batch1=md["batches"][0]["ms_total"],
-                             value=md["batches"][1]["proofs_per_s"], unit=UNIT, proofs_per_step=128,
-                             ms_per_proof=md["batches"][1]["ms_per_proof"], detail=md)
+                             value=md2["proofs_per_s"], unit=UNIT, proofs_per_step=128,
+                             ms_per_proof=md2["ms_per_proof"],
+                             how="two batches of 128 in flight (two host threads, contexts and circuit objects)",
+                             one_batch_at_a_time=dict(value=md["batches"][1]["proofs_per_s"],
+                                                      ms_per_proof=md["batches"][1]["ms_per_proof"]),
+                             detail=md)
         from oracle import refapi
         if refapi.mdoc_available():
             from fixtures import load_mdoc
