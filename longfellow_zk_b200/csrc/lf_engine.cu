@@ -596,7 +596,10 @@ static int launch_rs_p256(lf_ctx* ctx, fpw<8>* d_rows, size_t row_stride, size_t
   const size_t fft_smem = ((size_t)64) << t->logM;
   // the direct Toeplitz sum costs n*(m-n) multiplications, the FFT ~ 10 N log N
   if (!force_direct && n * (m - n) > 4096 && fft_smem <= 200 * 1024) {
-    k_rs_fp_fft_rows<FFp256><<<grid, 512, fft_smem, ctx->stream>>>(d_rows, row_stride, batch_stride, (uint32_t)n,
+    // one radix-4 group per thread and pass: M/4 threads (the 455 -> 909 rows of the Ligero
+    // prove have M = 512: 128 threads and four CTAs per SM instead of 512 mostly idle threads)
+    const unsigned fft_threads = (unsigned)std::min<size_t>(512, std::max<size_t>(64, ((size_t)1 << t->logM) / 4));
+    k_rs_fp_fft_rows<FFp256><<<grid, fft_threads, fft_smem, ctx->stream>>>(d_rows, row_stride, batch_stride, (uint32_t)n,
                                                                 (uint32_t)m, t->logM, t->d_wk, t->d_yh, t->d_lead,
                                                                 t->d_binom);
   } else {
