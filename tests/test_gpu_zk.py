@@ -119,14 +119,15 @@ def test_sha_proof_other_ligero_parameters(ctx, oracle, rate, nreq, block_enc, t
 
 @pytest.mark.parametrize("name,fid,B", [("sha1_gf128", 4, 10), ("sha1_gf128", 4, 20), ("sha1_gf128", 4, 40),
                                         ("sha1_gf128", 4, 100), ("sha1_gf128", 4, 160), ("sha1_gf128", 4, 300),
-                                        ("sha1_gf128", 4, 600), ("ecdsa1_p256", 1, 10), ("ecdsa1_p256", 1, 20),
+                                        ("sha1_gf128", 4, 600), ("sha1_gf128", 4, 1040), ("ecdsa1_p256", 1, 10),
+                                        ("ecdsa1_p256", 1, 20),
                                         ("ecdsa1_p256", 1, 40), ("ecdsa1_p256", 1, 100), ("ecdsa1_p256", 1, 160),
                                         ("ecdsa1_p256", 1, 300), ("ecdsa1_p256", 1, 600)])
 def test_every_sumcheck_shape_matches_oracle(ctx, oracle, name, fid, B):
     """The batch size selects the sumcheck launch shape: a cluster of 16 CTAs per proof up to 8 proofs
     (covered by the small-batch tests), of 8 up to 12, of 4 up to 32, of 2 up to 64, one 1024-thread CTA
-    per proof below 148, then 512-thread x 2, 256-thread x 4 and from 592 proofs on 128-thread x 8 CTAs
-    per SM.  Every proof of a
+    per proof below 148, then 512-thread x 2, 256-thread x 4, from 592 proofs on 128-thread x 7 and above
+    1036 proofs 128-thread x 8 CTAs per SM.  Every proof of a
     batch that mixes four coin streams must equal the oracle's proof for its stream, wherever it sits."""
     import longfellow_zk_b200 as lf
     circ, wit = load(name)
