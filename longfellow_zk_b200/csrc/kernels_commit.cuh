@@ -63,11 +63,14 @@ __device__ __forceinline__ void rs_butterfly(typename F::Elt* B, uint32_t q, uin
   B[q + s] = b1;
 }
 
+#ifndef LF_RS_GF_MIN_CTAS
+#define LF_RS_GF_MIN_CTAS 4  // 64 registers: 4 CTAs (32 warps) per SM instead of 3 at 66
+#endif
 // One CTA extends one row: y[0..n) given, y[n..m) produced.  rows are
 // `row_stride` elements apart; blockIdx.y selects the batch instance
 // (batch_stride elements apart).  Dynamic shared memory: 2 * fftn elements.
 template <class F>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, LF_RS_GF_MIN_CTAS)
 k_rs_gf_rows(typename F::Elt* __restrict__ data, size_t row_stride, size_t batch_stride, RsPlan plan,
              const typename F::Elt* __restrict__ d_tw) {
   typedef typename F::Elt Elt;
@@ -99,17 +102,30 @@ k_rs_gf_rows(typename F::Elt* __restrict__ data, size_t row_stride, size_t batch
   __syncthreads();
 
   // remaining cosets: forward FFT of the coefficients at offset b (lch14.h:106-123)
-  for (uint32_t b = fftn; b < m; b += fftn) {
-    for (uint32_t i = threadIdx.x; i < fftn; i += blockDim.x) D[i] = C[i];
+  // The 32 butterflies a warp owns in one pass of a stage st <= 5 lie in the warp's
+  // own 64-element block (t is warp-aligned), for this stage and every later one:
+  // those stages are separated by __syncwarp() instead of a CTA barrier.  The top
+  // stage reads the coefficients C and writes D, so no copy pass is needed.
+  const bool warp_private = fftn >= 64;
+  if (l == 0) {  // n == 1: the constant polynomial
+    if (threadIdx.x == 0) D[0] = C[0];
     __syncthreads();
+  }
+  for (uint32_t b = fftn; b < m; b += fftn) {
     for (uint32_t st = l; st-- > 0;) {
       const uint32_t half = 1u << st;
+      const Elt* src = (st + 1 == l) ? C : D;
       for (uint32_t t = threadIdx.x; t < fftn / 2; t += blockDim.x) {
         uint32_t q = ((t >> st) << (st + 1)) + (t & (half - 1));
         Elt tw = d_tw[tw_offset(st) + ((b + q) >> (st + 1))];
-        rs_butterfly<F>(D, q, half, 0, tw);
+        Elt b0 = src[q], b1 = src[q + half];
+        b0 = F::add(b0, F::mul(tw, b1));
+        b1 = F::add(b1, b0);
+        D[q] = b0;
+        D[q + half] = b1;
       }
-      __syncthreads();
+      if (warp_private && st >= 1 && st <= 5) __syncwarp();
+      else __syncthreads();
     }
     for (uint32_t i = threadIdx.x; i < fftn && b + i < m; i += blockDim.x) y[b + i] = D[i];
     __syncthreads();
