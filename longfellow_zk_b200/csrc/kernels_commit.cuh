@@ -64,7 +64,7 @@ __device__ __forceinline__ void rs_butterfly(typename F::Elt* B, uint32_t q, uin
 }
 
 #ifndef LF_RS_GF_MIN_CTAS
-#define LF_RS_GF_MIN_CTAS 4  // 64 registers: 4 CTAs (32 warps) per SM instead of 3 at 66
+#define LF_RS_GF_MIN_CTAS 4  // 64 registers (66 uncapped): 32 warps per SM, i.e. 8 CTAs of the default 128 threads
 #endif
 // One CTA extends one row: y[0..n) given, y[n..m) produced.  rows are
 // `row_stride` elements apart; blockIdx.y selects the batch instance

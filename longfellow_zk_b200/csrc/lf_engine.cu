@@ -355,6 +355,8 @@ struct lf_ctx {
 
 namespace lf {
 
+static const int kRsGfThreads = 128;  // measured: 64 / 128 / 192 / 256 threads -> 11.77 / 11.11 / 11.84 / 11.76 ms per 1024 SHA proofs
+
 static int ctx_rs_plan(lf_ctx* ctx, size_t n, size_t m, RsPlanHost** out) {
   auto key = std::make_pair(n, m);
   auto it = ctx->rs_plans.find(key);
@@ -463,8 +465,15 @@ static int launch_rs_gf(lf_ctx* ctx, gf128* d_rows, size_t row_stride, size_t nr
     attr_set = true;
   }
   dim3 grid((unsigned)nrows, (unsigned)nbatch);
-  k_rs_gf_rows<FGf128><<<grid, 256, smem, ctx->stream>>>(d_rows, row_stride, batch_stride, ph->plan,
-                                                         ctx->d_tw);
+  // CTA size: LF_RS_GF_THREADS (32..256, multiple of 32) is a tuning knob; the kernel strides by blockDim.x
+  static int rs_threads = 0;
+  if (!rs_threads) {
+    const char* e = getenv("LF_RS_GF_THREADS");
+    int v = e ? atoi(e) : 0;
+    rs_threads = (v >= 32 && v <= 256 && v % 32 == 0) ? v : kRsGfThreads;
+  }
+  k_rs_gf_rows<FGf128><<<grid, rs_threads, smem, ctx->stream>>>(d_rows, row_stride, batch_stride, ph->plan,
+                                                                ctx->d_tw);
   ctx->launches++;
   LF_CUDA(cudaGetLastError());
   return 0;
