@@ -36,6 +36,7 @@ struct RsStep {
   uint32_t stage;
   uint32_t base;
   uint32_t t0, t1;
+  uint32_t wsync;  // in-CTA kernel: the barrier after this step may be __syncwarp() (set by rs_mark_wsync)
 };
 
 struct RsPlan {
@@ -94,7 +95,8 @@ k_rs_gf_rows(typename F::Elt* __restrict__ data, size_t row_stride, size_t batch
       Elt tw = d_tw[tw_offset(st.stage) + (q >> (st.stage + 1))];
       rs_butterfly<F>(C, q, half, st.kind, tw);
     }
-    __syncthreads();
+    if (st.wsync) __syncwarp();
+    else __syncthreads();
   }
   for (uint32_t i = n + threadIdx.x; i < fftn && i < m; i += blockDim.x) y[i] = C[i];
   __syncthreads();

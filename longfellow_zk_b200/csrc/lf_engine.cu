@@ -156,6 +156,16 @@ static void gen_bidir(std::vector<RsStep>& out, uint32_t i, uint32_t base, uint3
   }
 }
 
+// Consecutive steps that both start at t0 == 0 on the same base with stages <= 5: a warp's 32
+// aligned butterflies touch only its own 64-element block in both, so the barrier between them
+// can be a __syncwarp() (k_rs_gf_rows; CTA sizes are multiples of 32).
+static void rs_mark_wsync(std::vector<RsStep>& steps) {
+  for (size_t k = 0; k + 1 < steps.size(); ++k) {
+    const RsStep &a = steps[k], &b = steps[k + 1];
+    steps[k].wsync = (a.t0 == 0 && b.t0 == 0 && a.base == b.base && a.stage <= 5 && b.stage <= 5) ? 1u : 0u;
+  }
+}
+
 struct RsPlanHost {
   RsPlan plan;
   RsStep* d_steps = nullptr;
@@ -369,6 +379,7 @@ static int ctx_rs_plan(lf_ctx* ctx, size_t n, size_t m, RsPlanHost** out) {
     }
     std::vector<RsStep> steps;
     gen_bidir(steps, l, 0, (uint32_t)n);
+    rs_mark_wsync(steps);
     ph.plan.n = (uint32_t)n;
     ph.plan.m = (uint32_t)m;
     ph.plan.l = l;
