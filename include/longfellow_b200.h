@@ -43,9 +43,10 @@ enum lf_status {
   LF_ERR_FORMAT = -3,       /* malformed circuit bytes / non-canonical element */
   LF_ERR_UNSUPPORTED = -4,  /* field or shape not built yet */
   LF_ERR_WITNESS = -5,      /* witness does not satisfy the circuit (ZkProver::prove == false) */
-  LF_ERR_RNG = -6,          /* caller-supplied randomness too short, or (prime fields) a caller-random
-                               element was >= p: retry that proof with fresh coins */
-  LF_ERR_CAPACITY = -7      /* output buffer too small */
+  LF_ERR_RNG = -6,          /* caller-supplied randomness too short (prime fields: including the draws
+                               the reference's Field::sample repeats, see lf_zk_prove_batch) */
+  LF_ERR_CAPACITY = -7,     /* output buffer too small */
+  LF_ERR_INTERNAL = -100    /* the sumcheck prover's own consistency check failed: never expected */
 };
 
 typedef struct lf_ctx lf_ctx;
@@ -110,6 +111,11 @@ int lf_merkle_commit(lf_ctx* ctx, int field_id, size_t nrow, size_t block_enc, s
 int lf_circuit_upload(lf_ctx* ctx, int field_id, const uint8_t* lfc1, size_t len, size_t rate,
                       size_t nreq, size_t block_enc, lf_circuit** out);
 void lf_circuit_free(lf_circuit* c);
+/* CircuitReader::from_bytes(buf, enforce_circuit_id = true) (lib/proto/circuit_reader.h:55-77):
+ * recomputes circuit_id (lib/sumcheck/circuit_id.h:30-67) from the parsed circuit and compares it
+ * with the 32 bytes stored in the file; LF_ERR_FORMAT if they differ.  computed_out (optional)
+ * receives the recomputed id.  Host-side, one SHA-256 pass over all quad terms. */
+int lf_circuit_verify_id(const lf_circuit* c, uint8_t computed_out[32]);
 
 typedef struct lf_circuit_info {
   size_t ninputs, npub_in, nl, nterms, kbytes;
@@ -133,6 +139,16 @@ typedef struct lf_circuit_info {
   /* bytes of the LFC1 input this circuit occupied; the mdoc circuit file holds the signature
    * circuit and the hash circuit back to back (lib/circuits/mdoc/mdoc_zk.cc:440-456) */
   size_t lfc1_bytes;
+  /* Caller randomness of one proof: rng_sample_bytes of field samples (pad,
+   * ILDT, IDOT, IQUAD, blinding of the witness and quadratic rows), then block_ext 32-byte Merkle
+   * nonces; rng_bytes is their sum.  Over a prime field every sample is one slot of
+   * rng_redraw_bytes (= kbytes) and the reference's Field::sample (lib/algebra/fp_generic.h:360-371)
+   * draws the slot again while its value is >= p: each redraw moves everything behind it, nonces
+   * included, one slot further down the stream, exactly as with the reference's RandomEngine.  So
+   * rng_bytes is what a proof consumes when no draw is rejected (2^-32 per sample for P-256) and a
+   * lower bound otherwise; up to rng_redraw_cap redraws per proof are followed.  rng_redraw_bytes
+   * == 0: the field's samples never fail (GF(2^128)) and rng_bytes is exact. */
+  size_t rng_sample_bytes, rng_redraw_bytes, rng_redraw_cap;
 } lf_circuit_info;
 int lf_circuit_get_info(const lf_circuit* c, lf_circuit_info* info);
 
@@ -145,9 +161,17 @@ int lf_circuit_get_info(const lf_circuit* c, lf_circuit_info* info);
  *     zkp.write(bytes_i, F);
  * witnesses: nproofs x ninputs elements (wire encoding).
  * rng: nproofs x rng_stride bytes; proof i consumes rng + i*rng_stride exactly
- *      as the reference consumes RandomEngine::bytes.
+ *      as the reference consumes RandomEngine::bytes,
+ *      rejected draws of Field::sample included (lf_circuit_info.rng_redraw_bytes):
+ *      rng_stride >= rng_bytes is required, and a proof whose redraws need more
+ *      than rng_stride bytes (or more than rng_redraw_cap redraws) is LF_ERR_RNG.
+ *      lf_zk_rng_consumed() tells how many bytes a proof took.
  * proofs_out: nproofs x proof_stride bytes; proof_lens[i] = serialized length.
- * status[i]: LF_OK or LF_ERR_WITNESS / LF_ERR_RNG / LF_ERR_CAPACITY.
+ * status[i]: LF_OK, or the first failure of that proof:
+ *      LF_ERR_FORMAT   a witness element is not canonical (>= p),
+ *      LF_ERR_RNG      the proof's random stream is too short (see above),
+ *      LF_ERR_WITNESS  the witness does not satisfy the circuit (ZkProver::prove == false),
+ *      LF_ERR_INTERNAL never expected.  A failed proof has proof_lens[i] == 0.
  * Host pointers; the call copies in, proves on the GPU and copies out. */
 int lf_zk_prove_batch(lf_circuit* c, size_t nproofs, const uint8_t* witnesses, const uint8_t* rng,
                       size_t rng_stride, const uint8_t* tinit, size_t tinit_len,
@@ -190,6 +214,10 @@ int lf_zk_commit_batch(lf_circuit* c, size_t nproofs, const uint8_t* witnesses, 
  * the transcript as the prover left it. */
 int lf_zk_prove_committed_batch(lf_circuit* c, size_t nproofs, const uint8_t* witnesses, lf_transcript* ts,
                                 uint8_t* proofs_out, size_t proof_stride, size_t* proof_lens, int* status);
+
+/* bytes of proof `index`'s random stream that the most recent batch on `c` consumed
+ * (= rng_bytes + redraws * rng_redraw_bytes) */
+int lf_zk_rng_consumed(lf_circuit* c, size_t index, size_t* bytes);
 
 /* ---- stage read-back for parity tests ---------------------------------- */
 enum lf_stage {

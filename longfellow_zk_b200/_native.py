@@ -20,7 +20,8 @@ class CircuitInfo(C.Structure):
         "ninputs", "npub_in", "nl", "nterms", "kbytes", "witness_bytes", "rng_bytes",
         "max_proof_bytes", "block_enc", "block", "dblock", "block_ext", "nrow", "r", "w", "nwrow",
         "nqtriples", "nreq", "nw", "sumcheck_alg_bytes", "sumcheck_mults", "total_mults", "sha_compressions",
-        "rs_mults", "eval_mults", "ligero_mults", "merkle_compressions", "lfc1_bytes")]
+        "rs_mults", "eval_mults", "ligero_mults", "merkle_compressions", "lfc1_bytes",
+        "rng_sample_bytes", "rng_redraw_bytes", "rng_redraw_cap")]
 
 
 class Transcript(C.Structure):
@@ -36,7 +37,7 @@ EXPORTS = [
     "lf_zk_prove_batch_dev", "lf_zk_debug_fetch", "lf_ctx_launch_count", "lf_microbench",
     "lf_circuit_set_profiling", "lf_circuit_get_stage_ms", "lf_fft", "lf_fft_time",
     "lf_zk_commit_batch", "lf_zk_prove_committed_batch", "lf_transcript_init", "lf_transcript_write_bytes",
-    "lf_transcript_challenge_bytes",
+    "lf_transcript_challenge_bytes", "lf_zk_rng_consumed", "lf_circuit_verify_id",
 ]
 
 
@@ -79,6 +80,18 @@ def lib():
         L.lf_fft.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.c_int]
         L.lf_fft_time.argtypes = [C.c_void_p, C.c_int, C.c_size_t, C.c_int, C.POINTER(C.c_double)]
         L.lf_microbench.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_double)]
+        L.lf_zk_commit_batch.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_size_t,
+                                         C.POINTER(Transcript), C.c_void_p, C.c_void_p]
+        L.lf_zk_prove_committed_batch.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.POINTER(Transcript),
+                                                  C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]
+        L.lf_transcript_init.argtypes = [C.POINTER(Transcript), C.c_char_p, C.c_size_t]
+        L.lf_transcript_init.restype = None
+        L.lf_transcript_write_bytes.argtypes = [C.POINTER(Transcript), C.c_char_p, C.c_size_t]
+        L.lf_transcript_write_bytes.restype = None
+        L.lf_transcript_challenge_bytes.argtypes = [C.POINTER(Transcript), C.c_void_p, C.c_size_t]
+        L.lf_transcript_challenge_bytes.restype = None
+        L.lf_circuit_verify_id.argtypes = [C.c_void_p, C.c_void_p]
+        L.lf_zk_rng_consumed.argtypes = [C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
         _lib = L
     return _lib
 

@@ -162,6 +162,13 @@ class Circuit:
         check(_native.lib().lf_circuit_get_info(self._h, C.byref(info)))
         self.info = {n: int(getattr(info, n)) for n, _ in info._fields_}
 
+    def verify_id(self):
+        """CircuitReader's enforce_circuit_id: recompute circuit_id and compare with the stored one;
+        raises LongfellowError(LF_ERR_FORMAT) on mismatch, returns the id."""
+        out = np.zeros(32, np.uint8)
+        check(_native.lib().lf_circuit_verify_id(self._h, _p(out)))
+        return out.tobytes()
+
     def close(self):
         if self._h:
             _native.lib().lf_circuit_free(self._h)
@@ -242,6 +249,12 @@ class ZkProver:
         if n < 0:
             check(n)
         return dict(zip(self.STAGES, [float(x) for x in ms[:n]]))
+
+    def rng_consumed(self, index):
+        """bytes of proof `index`'s random stream the most recent batch consumed (redraws included)"""
+        n = C.c_size_t()
+        check(_native.lib().lf_zk_rng_consumed(self.c._h, index, C.byref(n)))
+        return n.value
 
     def debug_fetch(self, index, stage, cap=1 << 26):
         buf = np.zeros(cap, np.uint8)

@@ -5,7 +5,7 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "liblongfellow_b200.so")
-SOURCES = ["lf_engine.cu"]
+SOURCES = ["lf_engine.cu", "host_hash.cc"]
 NVCC_FLAGS = ["--split-compile", "0", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
 

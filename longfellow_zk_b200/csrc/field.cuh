@@ -95,6 +95,7 @@ struct FGf128 {
   }
   // Field::sample on a fixed-size slot of the caller's random stream
   __device__ static __forceinline__ Elt sample_bytes(const uint8_t* p, bool* ok) { return from_bytes(p, ok); }
+  __device__ static __forceinline__ bool sample_ok(const uint8_t*) { return true; }
   // RandomEngine::elt on the transcript (random.h:37-41, gf2_128.h:182-190)
   __device__ static __forceinline__ Elt ts_elt(Transcript* ts) {
     Elt e;
@@ -306,6 +307,16 @@ struct FFp {
     mask_bits(in);
     if (fp_geq<W>(in, T::C().m)) *ok = false;
     return from_wire(in);
+  }
+  // would Field::sample accept this slot of the stream, or draw again?
+  __device__ static __forceinline__ bool sample_ok(const uint8_t* p) {
+    uint32_t in[W];
+#pragma unroll
+    for (int k = 0; k < W; ++k)
+      in[k] = (uint32_t)p[4 * k] | ((uint32_t)p[4 * k + 1] << 8) | ((uint32_t)p[4 * k + 2] << 16) |
+              ((uint32_t)p[4 * k + 3] << 24);
+    mask_bits(in);
+    return !fp_geq<W>(in, T::C().m);
   }
   __device__ static __forceinline__ Elt ts_elt(Transcript* ts) {
     uint32_t in[W];

@@ -407,11 +407,15 @@ k_merkle_leaves(const typename F::Elt* __restrict__ tableau, size_t tab_batch_st
                 uint32_t block_enc, uint32_t dblock, uint32_t block_ext,
                 const uint8_t* __restrict__ nonces, size_t nonce_batch_stride,
                 uint32_t* __restrict__ nodes /* [batch][2*block_ext][8] big-endian digest words */,
-                size_t nodes_batch_stride) {
+                size_t nodes_batch_stride,
+                const uint32_t* __restrict__ rej /* or null: per-instance count of redrawn sample slots */,
+                size_t rej_stride) {
   uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= block_ext) return;
   const typename F::Elt* T = tableau + (size_t)blockIdx.y * tab_batch_stride + dblock + j;
-  const uint8_t* nzb = nonces + (size_t)blockIdx.y * nonce_batch_stride + 32ull * j;
+  // prime fields: every redrawn sample (k_zk_rng_scan) pushes the nonces one slot back in the caller's stream
+  const size_t shift = rej ? (size_t)rej[(size_t)blockIdx.y * rej_stride] * F::kBytes : 0;
+  const uint8_t* nzb = nonces + (size_t)blockIdx.y * nonce_batch_stride + shift + 32ull * j;
   uint32_t h[8], w[16];
   sha256_iv(h);
   if ((reinterpret_cast<uintptr_t>(nzb) & 3) == 0) {

@@ -43,6 +43,86 @@ __device__ __noinline__ typename F::Elt ts_challenge(Transcript* ts) {
 }
 
 // ----------------------------------------------------------------------------
+// Caller randomness of a prime field.  Field::sample (algebra/fp_generic.h:360-371)
+// draws kBytes at a time from the RandomEngine and draws AGAIN while the value is
+// >= p, so the position of sample k in the caller's stream depends on how many
+// earlier draws were rejected.  Every caller-random element of the prover comes
+// before the Merkle nonces (pad, ILDT, IDOT, IQUAD, witness
+// rows, quadratic rows), so the stream up to there is a sequence of kBytes slots
+// and the samples are the slots that pass, in order.  k_zk_rng_scan finds the
+// rejected slots of each proof once (almost always none: 2^-32 per slot for
+// P-256); every reader maps sample index -> slot through that short sorted list.
+// rej[0] = number of rejected slots, rej[1 + j] = index of the sample whose draw
+// the j-th rejected slot was (= accepted slots before it), non-decreasing in j.
+// ----------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t rng_slot(const uint32_t* __restrict__ rej, uint32_t k) {
+  if (rej == nullptr) return k;
+  const uint32_t n = rej[0];
+  if (n == 0) return k;
+  uint32_t lo = 0, hi = n;  // number of rejected slots that precede the slot of sample k
+  while (lo < hi) {
+    uint32_t mid = (lo + hi) >> 1;
+    if (rej[1 + mid] <= k) lo = mid + 1;
+    else hi = mid;
+  }
+  return k + lo;
+}
+// pointer to sample k of proof p (prime fields: through the reject list)
+template <class F>
+__device__ __forceinline__ const uint8_t* rng_sample_ptr(const uint8_t* rng, const uint32_t* rej, uint32_t k) {
+  if constexpr (F::kChar2) return rng + (size_t)k * F::kBytes;
+  else return rng + (size_t)rng_slot(rej, k) * F::kBytes;
+}
+
+// One CTA per proof (prime fields only).  Slots are scanned in stream order, never
+// further than the samples still missing, so a slot is tested only if the reference
+// would have drawn it as a sample.  The stream must hold the nonces behind the last
+// sample: otherwise the proof is LF_ERR_RNG (stream too short).
+template <class F>
+__global__ void __launch_bounds__(256)
+k_zk_rng_scan(ZkDims d, ZkBufs<typename F::Elt> b) {
+  const size_t p = blockIdx.x;
+  const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  uint32_t* rej = b.rej + p * (size_t)(1 + d.rej_cap);
+  const uint8_t* rng = b.rng + p * b.rng_stride;
+  __shared__ uint32_t s_wcnt[8];
+  const size_t max_slots = (b.rng_avail - (size_t)d.block_ext * 32) / F::kBytes;
+  uint32_t acc = 0, pos = 0, nrej = 0;
+  bool too_short = false;
+  while (acc < d.rng_nsamples) {
+    const uint32_t nc = min(256u, d.rng_nsamples - acc);
+    if ((size_t)pos + nc > max_slots) {
+      too_short = true;
+      break;
+    }
+    const bool r = tid < nc && !F::sample_ok(rng + (size_t)(pos + tid) * F::kBytes);
+    const unsigned bal = __ballot_sync(0xffffffffu, r);
+    if (lane == 0) s_wcnt[warp] = __popc(bal);
+    __syncthreads();
+    uint32_t before = 0, total = 0;
+#pragma unroll
+    for (uint32_t w = 0; w < 8; ++w) {
+      const uint32_t c = s_wcnt[w];
+      if (w < warp) before += c;
+      total += c;
+    }
+    if (r) {
+      const uint32_t j = nrej + before + __popc(bal & ((1u << lane) - 1u));
+      if (j < d.rej_cap) rej[1 + j] = (pos + tid) - j;
+    }
+    __syncthreads();
+    nrej += total;
+    acc += nc - total;
+    pos += nc;
+  }
+  if (tid == 0) {
+    const bool bad = too_short || nrej > d.rej_cap;
+    rej[0] = bad ? 0u : nrej;  // a failed proof reads the un-shifted slots: always inside the buffer
+    if (bad) atomicCAS(&b.status[p], 0, -6);
+  }
+}
+
+// ----------------------------------------------------------------------------
 // k_zk_witness: Ligero witness = private inputs || pad (zk_prover.h:78-96,152-188)
 // pad of layer i: 4*logw+2 random elements in order (round, hand, k in {0,2}),
 // then wc[0], wc[1]; then the product wc[0]*wc[1].
@@ -55,6 +135,7 @@ __global__ void k_zk_witness(ZkDims d, ZkBufs<typename F::Elt> b, const LayerDes
   if (i >= d.nw) return;
   Elt* wit = b.wit + p * d.nw;
   const uint8_t* rng = b.rng + p * b.rng_stride;
+  const uint32_t* rej = b.rej ? b.rej + p * (size_t)(1 + d.rej_cap) : nullptr;
   bool ok = true, rok = true;
   if (i < d.n_witness) {
     const uint8_t* w = b.witness_in + p * b.witness_stride + (size_t)(i + d.npub) * F::kBytes;
@@ -72,13 +153,14 @@ __global__ void k_zk_witness(ZkDims d, ZkBufs<typename F::Elt> b, const LayerDes
   while (ly + 1 < d.nl && layers[ly + 1].pad_off <= q) ++ly;
   uint32_t j = q - layers[ly].pad_off, cnt = 4 * layers[ly].logw + 2;
   if (j < cnt) {
-    wit[i] = F::sample_bytes(rng + (size_t)(layers[ly].sc_off + j) * F::kBytes, &rok);
+    wit[i] = F::sample_bytes(rng_sample_ptr<F>(rng, rej, layers[ly].sc_off + j), &rok);
   } else {
-    Elt a = F::sample_bytes(rng + (size_t)(layers[ly].sc_off + cnt - 2) * F::kBytes, &rok);
-    Elt c = F::sample_bytes(rng + (size_t)(layers[ly].sc_off + cnt - 1) * F::kBytes, &rok);
+    Elt a = F::sample_bytes(rng_sample_ptr<F>(rng, rej, layers[ly].sc_off + cnt - 2), &rok);
+    Elt c = F::sample_bytes(rng_sample_ptr<F>(rng, rej, layers[ly].sc_off + cnt - 1), &rok);
     wit[i] = F::mul(a, c);
   }
-  if (!rok) atomicCAS(&b.status[p], 0, -6);  // (the first error of a proof sticks) a sample needs a re-draw (prime fields, probability 2^-32 each)
+  // (the first error of a proof sticks) never expected once k_zk_rng_scan accepted the stream
+  if (!rok) atomicCAS(&b.status[p], 0, -6);
 }
 
 // ----------------------------------------------------------------------------
@@ -95,15 +177,23 @@ k_zk_layout(ZkDims d, ZkBufs<typename F::Elt> b, const uint32_t* __restrict__ ro
   const uint32_t row = blockIdx.x;
   Elt* T = b.tableau + (p * d.nrow + row) * (size_t)d.block_enc;
   const Elt* wit = b.wit + p * d.nw;
-  const uint8_t* rng = b.rng + p * b.rng_stride + row_rng[row];
+  const uint8_t* rng0 = b.rng + p * b.rng_stride;
+  const uint8_t* rng = rng0 + row_rng[row];
+  const uint32_t* rej = b.rej ? b.rej + p * (size_t)(1 + d.rej_cap) : nullptr;
+  const uint32_t k0 = row_rng[row] / F::kBytes;  // prime fields: index of the row's first sample
+  // j-th full-size sample of this row
+  auto samp = [&](uint32_t j, bool* okp) {
+    if constexpr (F::kChar2) return F::sample_bytes(rng + (size_t)j * F::kBytes, okp);
+    else return F::sample_bytes(rng_sample_ptr<F>(rng0, rej, k0 + j), okp);
+  };
   __shared__ Elt red[8];
   bool rok = true;
   if (row == 0) {  // ILDT: block random elements
-    for (uint32_t j = threadIdx.x; j < d.block; j += blockDim.x) T[j] = F::sample_bytes(rng + (size_t)j * F::kBytes, &rok);
+    for (uint32_t j = threadIdx.x; j < d.block; j += blockDim.x) T[j] = samp(j, &rok);
   } else if (row == 1) {  // IDOT: dblock random, then T[r] -= sum of the W part
     Elt s = F::zero();
     for (uint32_t j = threadIdx.x; j < d.dblock; j += blockDim.x) {
-      Elt e = F::sample_bytes(rng + (size_t)j * F::kBytes, &rok);
+      Elt e = samp(j, &rok);
       T[j] = e;
       if (j >= d.r && j < d.r + d.w) s = F::add(s, e);
     }
@@ -120,11 +210,11 @@ k_zk_layout(ZkDims d, ZkBufs<typename F::Elt> b, const uint32_t* __restrict__ ro
     if (threadIdx.x == 0) {
       Elt tot = red[0];
       for (uint32_t k = 1; k < blockDim.x / 32; ++k) tot = F::add(tot, red[k]);
-      T[d.r] = F::sub(F::sample_bytes(rng + (size_t)d.r * F::kBytes, &rok), tot);
+      T[d.r] = F::sub(samp(d.r, &rok), tot);
     }
   } else if (row == 2) {  // IQUAD: dblock random with the W part cleared
     for (uint32_t j = threadIdx.x; j < d.dblock; j += blockDim.x) {
-      Elt e = F::sample_bytes(rng + (size_t)j * F::kBytes, &rok);
+      Elt e = samp(j, &rok);
       T[j] = (j >= d.r && j < d.r + d.w) ? F::zero() : e;
     }
   } else if (row < d.iq) {  // witness rows
@@ -137,7 +227,7 @@ k_zk_layout(ZkDims d, ZkBufs<typename F::Elt> b, const uint32_t* __restrict__ ro
           const uint8_t* q = rng + 2 * (size_t)j;
           e = F::of_sub16((uint32_t)q[0] | ((uint32_t)q[1] << 8));
         } else {
-          e = F::sample_bytes(rng + (size_t)j * F::kBytes, &rok);
+          e = samp(j, &rok);
         }
       } else {
         uint32_t k = i * d.w + (j - d.r);
@@ -151,7 +241,7 @@ k_zk_layout(ZkDims d, ZkBufs<typename F::Elt> b, const uint32_t* __restrict__ ro
     for (uint32_t j = threadIdx.x; j < d.block; j += blockDim.x) {
       Elt e;
       if (j < d.r) {
-        e = F::sample_bytes(rng + (size_t)j * F::kBytes, &rok);
+        e = samp(j, &rok);
       } else {
         uint32_t k = i * d.w + (j - d.r);
         e = (k < d.nq) ? wit[lqc[3 * k + which]] : F::zero();
@@ -1130,7 +1220,9 @@ k_lig_finish(ZkDims d, ZkBufs<typename F::Elt> b, const LayerDesc* __restrict__ 
   const Elt* y = b.y + p * (size_t)(d.block + 2 * d.dblock);
   const Elt* sc = b.sc + p * d.sc_elts;
   const uint32_t* nodes = b.nodes + p * (size_t)(2 * d.block_ext * 8);
-  const uint8_t* nonces = b.rng + p * b.rng_stride + d.rng_nonce_off;
+  // the nonces follow the last sample: redrawn slots push them back (k_zk_rng_scan)
+  const uint8_t* nonces = b.rng + p * b.rng_stride + d.rng_nonce_off +
+                          (b.rej ? (size_t)b.rej[p * (size_t)(1 + d.rej_cap)] * F::kBytes : 0);
   uint32_t* idx = b.idx + p * d.nreq;
   uint8_t* out = b.out + p * b.out_stride;
   uint32_t* sw = b.scratch + p * b.scratch_words;

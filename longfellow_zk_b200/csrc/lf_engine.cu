@@ -9,6 +9,7 @@
 
 #include <algorithm>
 #include <map>
+#include <set>
 #include <memory>
 #include <string>
 #include <utility>
@@ -361,7 +362,12 @@ struct lf_ctx {
   std::map<std::pair<int, std::pair<size_t, size_t>>, void*> rs_conv;  // (field,(n,m)) -> RsConvTables*
   uint64_t launches = 0;
   int sm_count = 0;
+  // cudaFuncSetAttribute acts on the CURRENT device: which kernels already have their attributes on
+  // this context's device (a process may hold contexts on several GPUs)
+  uint32_t attr_mask = 0;
+  std::set<const void*> fft_attr;
 };
+enum { kAttrRsGf = 1, kAttrRsFp = 2, kAttrScCluster = 4 };
 
 namespace lf {
 
@@ -469,11 +475,10 @@ static int launch_rs_gf(lf_ctx* ctx, gf128* d_rows, size_t row_stride, size_t nr
   if (rc) return rc;
   size_t smem = 2 * (size_t)ph->plan.fftn * sizeof(gf128);
   if (smem > 200 * 1024) return launch_rs_gf_global(ctx, d_rows, row_stride, nrows, batch_stride, nbatch, *ph);
-  static bool attr_set = false;
-  if (!attr_set) {
+  if (!(ctx->attr_mask & kAttrRsGf)) {
     LF_CUDA(cudaFuncSetAttribute(k_rs_gf_rows<FGf128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  200 * 1024));
-    attr_set = true;
+    ctx->attr_mask |= kAttrRsGf;
   }
   dim3 grid((unsigned)nrows, (unsigned)nbatch);
   // CTA size: LF_RS_GF_THREADS (32..256, multiple of 32) is a tuning knob; the kernel strides by blockDim.x
@@ -605,11 +610,10 @@ static int launch_rs_p256(lf_ctx* ctx, fpw<8>* d_rows, size_t row_stride, size_t
   RsFpTables* t;
   int rc = ctx_rs_fp_tables(ctx, n, m, &t);
   if (rc) return rc;
-  static bool attr_set = false;
-  if (!attr_set) {
+  if (!(ctx->attr_mask & kAttrRsFp)) {
     LF_CUDA(cudaFuncSetAttribute(k_rs_fp_rows<FFp256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     LF_CUDA(cudaFuncSetAttribute(k_rs_fp_fft_rows<FFp256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    attr_set = true;
+    ctx->attr_mask |= kAttrRsFp;
   }
   dim3 grid((unsigned)nrows, (unsigned)nbatch);
   static const bool force_direct = getenv("LF_RS_DIRECT") != nullptr;
@@ -637,10 +641,13 @@ static int fft_run(lf_ctx* ctx, typename A::Elt* d, size_t batch_stride, size_t 
                    const typename A::Elt* d_tw, bool inverse_root, bool dif, bool bitrev) {
   typedef typename A::Elt Elt;
   if (logn == 0 || nbatch == 0) return 0;
-  static bool attr_set = false;
-  if (!attr_set) {
-    LF_CUDA(cudaFuncSetAttribute(k_fft_stages<A>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-    attr_set = true;
+  // one flag per (context, instantiation): set on the context's device, which is current here
+  {
+    static const char kTag = 0;  // address unique per instantiation of fft_run<A>
+    if (!ctx->fft_attr.count(&kTag)) {
+      LF_CUDA(cudaFuncSetAttribute(k_fft_stages<A>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+      ctx->fft_attr.insert(&kTag);
+    }
   }
   uint32_t tile_log = 0;
   while ((sizeof(Elt) << (tile_log + 1)) <= 64 * 1024) ++tile_log;
@@ -885,12 +892,12 @@ template <class F>
 static int launch_merkle(lf_ctx* ctx, const typename F::Elt* d_tab, size_t tab_batch_stride, uint32_t nrow,
                          uint32_t block_enc, uint32_t dblock, const uint8_t* d_nonces,
                          size_t nonce_batch_stride, uint32_t* d_nodes, size_t nodes_batch_stride,
-                         size_t nbatch) {
+                         size_t nbatch, const uint32_t* d_rej = nullptr, size_t rej_stride = 0) {
   uint32_t block_ext = block_enc - dblock;
   dim3 grid((block_ext + 127) / 128, (unsigned)nbatch);
   k_merkle_leaves<F><<<grid, 128, 0, ctx->stream>>>(d_tab, tab_batch_stride, nrow, block_enc, dblock,
                                                          block_ext, d_nonces, nonce_batch_stride, d_nodes,
-                                                         nodes_batch_stride);
+                                                         nodes_batch_stride, d_rej, rej_stride);
   ctx->launches++;
   LF_CUDA(cudaGetLastError());
   k_merkle_tree<<<(unsigned)nbatch, 256, 0, ctx->stream>>>(d_nodes, nodes_batch_stride, block_ext);

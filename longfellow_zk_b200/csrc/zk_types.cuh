@@ -63,6 +63,12 @@ struct ZkDims {
   // caller-supplied randomness layout (bytes from the start of one proof's stream)
   uint32_t rng_nonce_off;
   uint32_t rng_total;
+  // Prime fields: every caller-random element before the nonces is one kBytes slot of the
+  // stream, and a slot whose value is >= p makes the reference draw again
+  // (algebra/fp_generic.h:360-371).  rng_nsamples = number of samples (0 for GF(2^128), whose
+  // samples never fail); rej_cap = redraws per proof that are followed.
+  uint32_t rng_nsamples;
+  uint32_t rej_cap;
   uint32_t max_proof_bytes;
   uint32_t tinit_len;
   uint32_t debug_stop;  // LF_DEBUG_STOP: early exit point inside k_lig_finish (bisecting)
@@ -74,6 +80,9 @@ template <class Elt>
 struct ZkBufs {
   const uint8_t* witness_in;  size_t witness_stride;   // ninputs * kBytes wire bytes
   const uint8_t* rng;         size_t rng_stride;
+  size_t rng_avail;           // valid bytes of each proof's stream (<= rng_stride)
+  uint32_t* rej;   // [1 + rej_cap] prime fields: number of rejected slots, then for each (in stream
+                   // order) the index of the sample that was drawn again (k_zk_rng_scan); else null
   Elt* wit;        // [nw] Ligero witness
   Elt* tableau;    // [nrow * block_enc]
   uint32_t* nodes; // [2 * block_ext * 8] Merkle heap, big-endian digest words

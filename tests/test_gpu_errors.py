@@ -48,14 +48,14 @@ def test_short_buffers_are_rejected(ctx):
 
 def test_non_canonical_witness_and_coins_are_flagged_per_proof(ctx, oracle):
     """Fp256: a witness element >= p is LF_ERR_FORMAT for that proof (the reference's of_bytes_field
-    fails); a caller-random element >= p is LF_ERR_RNG (documented deviation: the reference re-samples);
-    the other proofs of the batch are unaffected and still equal the oracle's."""
+    fails); a caller-random slot >= p is drawn again like the reference's Field::sample does, which this
+    proof's stream of exactly rng_bytes has no room for: LF_ERR_RNG (stream too short); the other proofs
+    of the batch are unaffected and still equal the oracle's."""
     import longfellow_zk_b200 as lf
     circ, wit = load("ecdsa1_p256")
     c = lf.Circuit(ctx, 1, circ)
     n = c.info["rng_bytes"]
     good = rng_bytes(50, 1 << 19)[:n].copy()
-    good[31::32] &= 0x7F
     want = oracle.Circuit(1, circ).prove(wit, good)["proof"]
     W = np.repeat(np.frombuffer(wit, np.uint8)[None, :], 3, axis=0).copy()
     W[1, 32 * 10:32 * 11] = 0xFF                         # input 10 of proof 1 = 2^256 - 1 >= p
@@ -65,3 +65,21 @@ def test_non_canonical_witness_and_coins_are_flagged_per_proof(ctx, oracle):
     assert status[0] == 0 and proofs[0] == want
     assert status[1] == -3 and proofs[1] == b""
     assert status[2] == -6 and proofs[2] == b""
+
+
+def test_circuit_id_is_recomputed(ctx):
+    """CircuitReader::from_bytes(enforce_circuit_id = true): the id the reference's compiler stored in
+    the fixture equals circuit_id (lib/sumcheck/circuit_id.h:30-67) recomputed from the parsed terms,
+    for both fields; a file with another trailing id still parses (the reference's default) but
+    verify_id refuses it"""
+    import longfellow_zk_b200 as lf
+    for name, fid in (("sha1_gf128", 4), ("ecdsa1_p256", 1)):
+        circ, _ = load(name)
+        c = lf.Circuit(ctx, fid, circ)
+        assert c.verify_id() == circ[c.info["lfc1_bytes"] - 32:c.info["lfc1_bytes"]]
+        bad = bytearray(circ)
+        bad[c.info["lfc1_bytes"] - 1] ^= 1
+        cb = lf.Circuit(ctx, fid, bytes(bad))
+        with pytest.raises(lf.LongfellowError) as e:
+            cb.verify_id()
+        assert e.value.code == -3

@@ -134,9 +134,6 @@ def test_every_sumcheck_shape_matches_oracle(ctx, oracle, name, fid, B):
     c = lf.Circuit(ctx, fid, circ)
     n = c.info["rng_bytes"]
     streams = [rng_bytes(40 + s, 1 << 19)[:n].copy() for s in range(4)]
-    if fid == 1:
-        for s in streams:
-            s[31::32] &= 0x7F  # every 32-byte sample below p: no rejection in either implementation
     want = [oracle.Circuit(fid, circ).prove(wit, s)["proof"] for s in streams]
     rng = np.stack([streams[i % 4] for i in range(B)])
     W = np.repeat(np.frombuffer(wit, np.uint8)[None, :], B, axis=0)
@@ -162,19 +159,17 @@ def test_growing_and_shrinking_batches_on_one_circuit(sha, oracle):
 @pytest.mark.parametrize("name,fid", [("sha1_gf128", 4), ("ecdsa1_p256", 1)])
 def test_full_size_batch_is_accepted_by_the_reference_verifier(ctx, ref, name, fid):
     """BASELINE's batch size (1024 independent proofs, every proof its own coins): every status is
-    zero, all proofs differ, and the unmodified reference ZkVerifier accepts a sample of them"""
+    zero, all proofs differ, and the unmodified reference ZkVerifier accepts every one of them"""
     import longfellow_zk_b200 as lf
     circ, wit = load(name)
     c = lf.Circuit(ctx, fid, circ)
     B, n = 1024, c.info["rng_bytes"]
-    rng = np.random.default_rng(2026).integers(0, 256, (B, n), dtype=np.uint8)
-    if fid == 1:
-        rng[:, 31::32] &= 0x7F
+    rng = np.random.default_rng(2026).integers(0, 256, (B, n + 64), dtype=np.uint8)
     W = np.repeat(np.frombuffer(wit, np.uint8)[None, :], B, axis=0)
     proofs, status = lf.ZkProver(c).prove_batch(W, rng)
     assert (status == 0).all()
     assert len({hashlib.sha256(p).digest() for p in proofs}) == B
     rc = ref.Circuit(fid, circ)
     pub = wit[:c.info["npub_in"] * c.info["kbytes"]]
-    for i in list(range(0, B, 37)) + [B - 1]:
+    for i in range(B):
         assert rc.verify(pub, proofs[i]) == 0, i

@@ -16,8 +16,6 @@ for which, fid in (("sha1_gf128", 4), ("ecdsa1_p256", 1)):
     BMAX = 2048
     d_wit = torch.from_numpy(np.frombuffer(wit, np.uint8).copy()).repeat(BMAX, 1).cuda()
     d_rng = torch.randint(0, 256, (BMAX, rstride), dtype=torch.uint8)
-    if fid == 1:
-        d_rng[:, 31::32] &= 0x7F
     d_rng = d_rng.cuda()
     d_out = torch.empty((BMAX, info["max_proof_bytes"]), dtype=torch.uint8, device="cuda")
     d_len = torch.zeros(BMAX, dtype=torch.int64, device="cuda")

@@ -17,8 +17,6 @@ info = provers[0].c.info
 rstride = (info["rng_bytes"] + 15) & ~15
 d_wit = torch.from_numpy(np.frombuffer(wit, np.uint8).copy()).repeat(B, 1).cuda()
 d_rng = torch.randint(0, 256, (B, rstride), dtype=torch.uint8)
-if fid == 1:
-    d_rng[:, 31::32] &= 0x7F
 d_rng = d_rng.cuda()
 outs = [(torch.empty((B, info["max_proof_bytes"]), dtype=torch.uint8, device="cuda"),
          torch.zeros(B, dtype=torch.int64, device="cuda"), torch.zeros(B, dtype=torch.int32, device="cuda"))
