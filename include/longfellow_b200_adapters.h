@@ -23,6 +23,7 @@
 #ifndef LONGFELLOW_B200_ADAPTERS_H_
 #define LONGFELLOW_B200_ADAPTERS_H_
 
+#include <algorithm>
 #include <cstddef>
 #include <cstdint>
 #include <memory>
@@ -103,6 +104,33 @@ class GpuZkProver {
 
   const lf_circuit_info& info() const { return info_; }
 
+  /* Exactly the bytes ZkProver::commit would take from `rng` for one proof, in its order: the field
+   * samples -- over a prime field Field::sample draws a kBytes slot again while its value is >= p
+   * (lib/algebra/fp_generic.h:360-371), and so does this: every rejected slot is followed by one
+   * more drawn slot -- then the Merkle nonces.  A RandomEngine cannot be rewound, so the redraws
+   * are resolved here, on the reference's side of the C ABI, and the back end then finds the same
+   * rejected slots in the stream it is given. */
+  void draw_coins(proofs::RandomEngine& rng, std::vector<uint8_t>& coins) const {
+    coins.resize(info_.rng_sample_bytes);
+    rng.bytes(coins.data(), coins.size());
+    const size_t slot = info_.rng_redraw_bytes;
+    if (slot != 0) {
+      size_t checked = 0;
+      for (;;) {
+        size_t redraw = 0;
+        for (; checked + slot <= coins.size(); checked += slot)
+          if (!f_.of_bytes_field(&coins[checked]).has_value()) ++redraw;
+        if (redraw == 0) break;
+        const size_t at = coins.size();
+        coins.resize(at + redraw * slot);
+        rng.bytes(&coins[at], redraw * slot);
+      }
+    }
+    const size_t at = coins.size(), nonce_bytes = info_.rng_bytes - info_.rng_sample_bytes;
+    coins.resize(at + nonce_bytes);
+    rng.bytes(&coins[at], nonce_bytes);
+  }
+
   /* One proof per witness W[i] (the reference's Dense<Field>(1, ninputs)); every proof
    * starts from Transcript(tinit, tinit_len) and draws its coins from `rng` in the order
    * the reference's ZkProver does.  ok[i] is what ZkProver::prove would return. */
@@ -110,16 +138,21 @@ class GpuZkProver {
                                 size_t tinit_len, proofs::RandomEngine& rng,
                                 std::vector<std::vector<uint8_t>>& proofs_out) {
     const size_t B = W.size();
-    std::vector<uint8_t> wit(B * info_.witness_bytes), coins(B * info_.rng_bytes);
+    std::vector<uint8_t> wit(B * info_.witness_bytes);
+    std::vector<std::vector<uint8_t>> draws(B);
+    size_t stride = info_.rng_bytes;
     for (size_t i = 0; i < B; ++i) {
       for (size_t k = 0; k < info_.ninputs; ++k)
         f_.to_bytes_field(&wit[i * info_.witness_bytes + k * Field::kBytes], W[i]->v_[k]);
-      rng.bytes(&coins[i * info_.rng_bytes], info_.rng_bytes);
+      draw_coins(rng, draws[i]);
+      stride = std::max(stride, draws[i].size());
     }
+    std::vector<uint8_t> coins(B * stride);
+    for (size_t i = 0; i < B; ++i) std::copy(draws[i].begin(), draws[i].end(), coins.begin() + i * stride);
     std::vector<uint8_t> out(B * info_.max_proof_bytes);
     std::vector<size_t> len(B);
     std::vector<int> st(B);
-    lf_check(lf_zk_prove_batch(circ_, B, wit.data(), coins.data(), info_.rng_bytes, tinit, tinit_len, out.data(),
+    lf_check(lf_zk_prove_batch(circ_, B, wit.data(), coins.data(), stride, tinit, tinit_len, out.data(),
                                info_.max_proof_bytes, len.data(), st.data()));
     std::vector<bool> ok(B);
     proofs_out.resize(B);

@@ -57,6 +57,17 @@ struct FGf128 {
   __host__ __device__ static __forceinline__ void mac(Acc& a, const Elt& x, const Elt& y) {
     gf_mac(a.t, x, y);
   }
+  // (first ? a0 : a1) += x * y without a divergent call of the multiplier
+  __host__ __device__ static __forceinline__ void mac_sel(Acc& a0, Acc& a1, bool first, const Elt& x, const Elt& y) {
+    uint32_t t[8];
+    gf_mul_wide(x, y, t);
+    const uint32_t m0 = first ? 0xffffffffu : 0u, m1 = ~m0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      a0.t[i] ^= t[i] & m0;
+      a1.t[i] ^= t[i] & m1;
+    }
+  }
   // a += x (an element, i.e. x * 1)
   __host__ __device__ static __forceinline__ void acc_add_elt(Acc& a, const Elt& x) {
     a.t[0] ^= x.w[0]; a.t[1] ^= x.w[1]; a.t[2] ^= x.w[2]; a.t[3] ^= x.w[3];
@@ -252,6 +263,18 @@ struct FFp {
   // modular accumulator yields the same field element
   __device__ static __forceinline__ void acc_zero(Acc& a) { a.v = zero(); }
   __device__ static __forceinline__ void mac(Acc& a, const Elt& x, const Elt& y) { a.v = add(a.v, mul(x, y)); }
+  __device__ static __forceinline__ void mac_sel(Acc& a0, Acc& a1, bool first, const Elt& x, const Elt& y) {
+    const Elt prod = mul(x, y);
+    Elt s;
+#pragma unroll
+    for (int i = 0; i < W; ++i) s.w[i] = first ? a0.v.w[i] : a1.v.w[i];
+    s = add(s, prod);
+#pragma unroll
+    for (int i = 0; i < W; ++i) {
+      a0.v.w[i] = first ? s.w[i] : a0.v.w[i];
+      a1.v.w[i] = first ? a1.v.w[i] : s.w[i];
+    }
+  }
   __device__ static __forceinline__ void acc_add_elt(Acc& a, const Elt& x) { a.v = add(a.v, x); }
   __device__ static __forceinline__ void acc_add(Acc& a, const Acc& b) { a.v = add(a.v, b.v); }
   __device__ static __forceinline__ Elt reduce(const Acc& a) { return a.v; }

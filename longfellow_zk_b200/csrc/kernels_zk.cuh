@@ -409,6 +409,59 @@ struct ScShared {
   long long prof[8];    // LF_PROF: cycles of thread 0 per phase
 };
 
+// What the sumcheck prover carries from one kernel to the next when a proof's rounds are split
+// over several launches (the flat path, kernels_scflat.cuh): the transcript hash (no live challenge
+// stream ever crosses a launch: every launch ends on a write or starts on one), the bindings, and
+// the running claim.
+template <class F>
+struct ScCore {
+  Sha256 sha;
+  typename F::Elt G[2][40];
+  typename F::Elt r, alpha, beta, sum, wc[2];
+  int fail;
+};
+// which part of the layered sumcheck one launch of the per-proof kernel runs
+struct ScRange {
+  uint32_t ly_begin, ly_end;  // layers [ly_begin, ly_end)
+  uint32_t t_begin;           // first round of layer ly_begin (0: the layer starts here, with its EQ tables and bind_g)
+  uint32_t first;             // != 0: this launch starts the proof (sc_begin on the transcript k_zk_transcript_init left)
+};
+
+template <class F>
+__device__ __noinline__ void sc_save(const ScShared<F>* sh, ScCore<F>* g) {
+  g->sha = sh->ts.sha;
+  for (int i = 0; i < 40; ++i) {
+    g->G[0][i] = sh->G[0][i];
+    g->G[1][i] = sh->G[1][i];
+  }
+  g->r = sh->r;
+  g->alpha = sh->alpha;
+  g->beta = sh->beta;
+  g->sum = sh->sum;
+  g->wc[0] = sh->wc[0];
+  g->wc[1] = sh->wc[1];
+  g->fail = sh->fail;
+}
+template <class F>
+__device__ __noinline__ void sc_load(ScShared<F>* sh, const ScCore<F>* g) {
+  sh->ts.sha = g->sha;
+  sh->ts.have_prf = 0;
+  sh->ts.nblock = 0;
+  sh->ts.rdptr = 16;
+  sh->ts.use_tables(&sh->aes);
+  for (int i = 0; i < 40; ++i) {
+    sh->G[0][i] = g->G[0][i];
+    sh->G[1][i] = g->G[1][i];
+  }
+  sh->r = g->r;
+  sh->alpha = g->alpha;
+  sh->beta = g->beta;
+  sh->sum = g->sum;
+  sh->wc[0] = g->wc[0];
+  sh->wc[1] = g->wc[1];
+  sh->fail = g->fail;
+}
+
 template <class F>
 __device__ __forceinline__ typename F::Elt warp_sum(typename F::Elt s) {
 #pragma unroll
@@ -661,7 +714,8 @@ __device__ __forceinline__ void sumcheck_body(const ZkDims& d, const ZkBufs<type
                                               const uint32_t* __restrict__ arena,
                                               const LayerDesc* __restrict__ layers,
                                               const StepDesc* __restrict__ steps,
-                                              const typename F::Elt* __restrict__ consts, ScShared<F>& sh) {
+                                              const typename F::Elt* __restrict__ consts, ScShared<F>& sh,
+                                              const ScRange R) {
   typedef typename F::Elt Elt;
   typedef typename F::Acc Acc;
   const ScPar<CL> P;
@@ -685,16 +739,21 @@ __device__ __forceinline__ void sumcheck_body(const ZkDims& d, const ZkBufs<type
   Elt* hbs = b.hb + p * d.nhb;
 
   aes_stage_tables(&sh.aes);
+  ScCore<F>* core = reinterpret_cast<ScCore<F>*>(b.scst + p * sizeof(ScCore<F>));
   if (leader) {
     for (int i = 0; i < 8; ++i) sh.prof[i] = 0;
     sh.prof[3] = clock64();
-    sc_begin<F>(&sh, reinterpret_cast<const Transcript*>(b.ts + p * sizeof(Transcript)));
+    if (R.first) sc_begin<F>(&sh, reinterpret_cast<const Transcript*>(b.ts + p * sizeof(Transcript)));
+    else sc_load<F>(&sh, core);
   }
   P.sync();
 
-  uint32_t logv = d.logv;
-  for (uint32_t ly = 0; ly < d.nl; ++ly) {
+  uint32_t logv = R.ly_begin == 0 ? d.logv : layers[R.ly_begin - 1].logw;
+  for (uint32_t ly = R.ly_begin; ly < R.ly_end; ++ly) {
     const LayerDesc L = layers[ly];
+    // a launch may pick a layer up at round t0 > 0: the earlier rounds ran as flat kernels
+    const uint32_t t0 = ly == R.ly_begin ? R.t_begin : 0;
+    if (t0 == 0) {
     if (leader) {
       sc_begin_layer<F>(&sh, &b.alphas[p * d.nl + ly]);
       E0[0] = F::one();
@@ -739,14 +798,19 @@ __device__ __forceinline__ void sumcheck_body(const ZkDims& d, const ZkBufs<type
             else F::mac(acc, o.c, dot);
           });
     }
+    }  // t0 == 0
 
-    const Elt *wcur0 = wl + L.w_off, *wcur1 = wl + L.w_off;  // current array of each hand
-    uint32_t wpar0 = 0, wpar1 = 0;
-    uint32_t hqpar = 0;
+    // current array of each hand: hand 0 has been bound ceil(t0 / 2) times, hand 1 floor(t0 / 2) times;
+    // bind number k (from 0) of hand h writes whbuf[2h + (k & 1)]; the HQuad buffers alternate every round
+    const uint32_t nb0 = (t0 + 1) >> 1, nb1 = t0 >> 1;
+    const Elt* wcur0 = nb0 ? whbuf + (size_t)((nb0 - 1) & 1) * d.max_nw : wl + L.w_off;
+    const Elt* wcur1 = nb1 ? whbuf + (size_t)(2 + ((nb1 - 1) & 1)) * d.max_nw : wl + L.w_off;
+    uint32_t wpar0 = nb0 & 1, wpar1 = nb1 & 1;
+    uint32_t hqpar = t0 & 1;
     const Elt* pad = wit + d.n_witness + L.pad_off;
 
     bool solo = false;
-    for (uint32_t t = 0; t < 2 * L.logw; ++t) {
+    for (uint32_t t = t0; t < 2 * L.logw; ++t) {
       const StepDesc S = steps[L.step0 + t];
       const uint32_t hand = t & 1, round = t >> 1;
       // Cluster mode: once a layer's steps are small, a cluster-wide phase costs
@@ -870,11 +934,15 @@ __device__ __forceinline__ void sumcheck_body(const ZkDims& d, const ZkBufs<type
     logv = L.logw;
   }
   if (leader) {
-    *reinterpret_cast<Transcript*>(b.ts + p * sizeof(Transcript)) = sh.ts;
-    if (sh.fail) atomicCAS(&b.status[p], 0, -100);  // (the first error of a proof sticks) internal inconsistency: never expected
-    sh.prof[2] = clock64() - sh.prof[3];
-    long long* dbg = reinterpret_cast<long long*>(hqbuf);  // free after the last layer
-    for (int i = 0; i < 8; ++i) dbg[i] = sh.prof[i];
+    if (R.ly_end == d.nl) {
+      *reinterpret_cast<Transcript*>(b.ts + p * sizeof(Transcript)) = sh.ts;
+      if (sh.fail) atomicCAS(&b.status[p], 0, -100);  // (the first error of a proof sticks) internal inconsistency: never expected
+      sh.prof[2] = clock64() - sh.prof[3];
+      long long* dbg = reinterpret_cast<long long*>(hqbuf);  // free after the last layer
+      for (int i = 0; i < 8; ++i) dbg[i] = sh.prof[i];
+    } else {
+      sc_save<F>(&sh, core);  // the flat kernels of the next layer continue from here
+    }
   }
 }
 
@@ -889,7 +957,7 @@ template <class F, int NT, int MINB>
 __global__ void __launch_bounds__(NT, MINB)
 k_zk_sumcheck(ZkDims d, ZkBufs<typename F::Elt> b, const uint32_t* __restrict__ arena,
               const LayerDesc* __restrict__ layers, const StepDesc* __restrict__ steps,
-              const typename F::Elt* __restrict__ consts) {
+              const typename F::Elt* __restrict__ consts, const ScRange R) {
   __shared__ ScShared<F> sh;
   __shared__ typename F::Elt hp[NT];
   __shared__ uint32_t hr[NT];
@@ -898,7 +966,7 @@ k_zk_sumcheck(ZkDims d, ZkBufs<typename F::Elt> b, const uint32_t* __restrict__ 
     sh.hr = hr;
   }
   __syncthreads();
-  sumcheck_body<F, false>(d, b, arena, layers, steps, consts, sh);
+  sumcheck_body<F, false>(d, b, arena, layers, steps, consts, sh, R);
 }
 constexpr int kScClThreads = 512;
 template <class F>
@@ -914,7 +982,7 @@ k_zk_sumcheck_cluster(ZkDims d, ZkBufs<typename F::Elt> b, const uint32_t* __res
     sh.hr = hr;
   }
   __syncthreads();
-  sumcheck_body<F, true>(d, b, arena, layers, steps, consts, sh);
+  sumcheck_body<F, true>(d, b, arena, layers, steps, consts, sh, ScRange{0, d.nl, 0, 1});
 }
 
 // ----------------------------------------------------------------------------

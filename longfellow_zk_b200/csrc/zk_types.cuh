@@ -48,6 +48,47 @@ struct StepDesc {
   uint32_t merge;    // [n_out] (src << 2) | kind ; kind 0 pair, 1 lone even, 2 lone odd
 };
 
+// ---- batch-synchronous ("flat") sumcheck rounds ---------------------------------------------
+// With hundreds of proofs in a batch the large rounds of a layer are run as ordinary grid-wide
+// kernels over (work item, proof) instead of inside one CTA per proof: k_sc_eval (QW gather and the
+// two dot products of ProverLayers::evaluations), k_sc_round (the serial Fiat-Shamir step, one
+// THREAD per proof, so a warp runs the SHA-256/AES chains of 32 proofs in lockstep) and k_sc_bind
+// (Dense::bind and HQuad::bind_h).  The work lists are static per circuit:
+//
+// k_sc_eval: one thread per PAIR of rows (2i, 2i+1) of the hand's CSR; pairs are sorted by their
+// number of entries and stored 32 to a warp in column-major (sliced-ELL) order, so index loads are
+// coalesced and the 32 lanes loop about equally often.  Rows with more than kFlatHeavyRow entries
+// (the constant wire 0 feeds tens of thousands of corners) are taken out of their pair and cut
+// into warp-sized chunks whose partial QW enters the two dot products by linearity.
+constexpr uint32_t kFlatHeavyRow = 48;     // entries of one row a pair thread still takes
+constexpr uint32_t kFlatHeavyChunk = 256;  // entries per heavy-row warp chunk
+constexpr uint32_t kFlatEvalWarps = 8;     // warps per CTA of k_sc_eval
+constexpr uint32_t kFlatMaxCta = 8;        // CTAs per proof of k_sc_eval (their partial sums are added by k_sc_round)
+constexpr uint32_t kFlatNone = 0xffffffffu;
+
+struct FlatStepDesc {
+  uint32_t nwarp_pair;   // sliced-ELL warps of row pairs
+  uint32_t nwarp_heavy;  // heavy-row chunks, one warp each
+  uint32_t ncta;         // CTAs per proof
+  uint32_t pw_pair;      // [32 * nwarp_pair] pair index of each lane (kFlatNone: padding)
+  uint32_t pw_cnt;       // [32 * nwarp_pair] entries of row 2i | entries of row 2i+1 << 16
+  uint32_t pw_base;      // [nwarp_pair] entry offset of the warp's column-major block
+  uint32_t e_c, e_p;     // entry arrays: corner index, wire index of the other hand
+  uint32_t hv_row, hv_off, hv_cnt;  // [nwarp_heavy] row, first entry and entry count inside the step's CSR
+};
+// Quad::bind_g of a large layer: one thread per initial HQuad corner, same layout; corners with
+// more than kFlatHeavyRow terms are cut into warp chunks whose partial sums k_sc_bindg_fix adds.
+struct FlatLayerDesc {
+  uint32_t nwarp_c, nwarp_heavy, ncta;
+  uint32_t cw_corner, cw_cnt, cw_base;  // [32 * nwarp_c], [32 * nwarp_c], [nwarp_c]
+  uint32_t t_g, t_v;                    // term arrays in sliced-ELL order: gate index, constant index + flags
+  uint32_t hv_off, hv_cnt;              // [nwarp_heavy] first term / term count in canonical order
+  uint32_t nheavy;                      // heavy corners
+  uint32_t hc_corner, hc_item;          // [nheavy] corner, [nheavy + 1] first chunk of each heavy corner
+  uint32_t nflat;                       // rounds 0 .. nflat-1 of this layer run flat
+  uint32_t fs0;                         // index of the first FlatStepDesc of this layer
+};
+
 struct ZkDims {
   uint32_t nl, ninputs, npub, n_witness, nv, logv, nterms;
   // LigeroParam (lib/ligero/ligero_param.h:116-147)
@@ -94,6 +135,8 @@ struct ZkBufs {
   Elt* bq;         // [nl] bound quads (ProofAux)
   Elt* hb;         // [nhb] hand challenges
   Elt* alphas;     // [nl] per-layer alpha
+  uint8_t* scst;   // [sizeof(ScCore<F>)] sumcheck prover state between the kernels of the flat path
+  Elt* part;       // [2 * kFlatMaxCta] per-CTA partial sums of the two dot products of a round
   Elt* chal;       // [1 + nchal] alpha_in, u_ldt, alphal, alphaq, u_quad
   Elt* avec;       // [nwqrow * w]
   Elt* aext;       // [nwqrow * dblock]
