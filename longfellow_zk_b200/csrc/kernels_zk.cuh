@@ -620,8 +620,9 @@ __device__ __forceinline__ void seg_sum(ScShared<F>* sh, const ScPar<CL>& P, uin
 
 // serial part of one round, thread 0 only (prover_layers.h:244-251,320-329,
 // transcript_sumcheck.h:63-79, poly.h:59-98)
-template <class F>
-__device__ __noinline__ void sc_round_serial(ScShared<F>* sh, typename F::Elt a0, typename F::Elt a2,
+// (S: ScShared<F> in the per-proof kernel, ScLane<F> -- a thread's own copy -- in k_sc_round)
+template <class F, class S>
+__device__ __noinline__ void sc_round_serial(S* sh, typename F::Elt a0, typename F::Elt a2,
                                             const typename F::Elt* pad /* hp[hand][round] k=0,2 */,
                                             typename F::Elt* proof0, typename F::Elt* proof2,
                                             typename F::Elt* hb_out) {
@@ -655,8 +656,8 @@ __device__ __noinline__ void sc_round_serial(ScShared<F>* sh, typename F::Elt a0
 // new claim = p(rnd).  The reference evaluates the Lagrange form through
 // Newton differences (poly.h:59-98); it is the same polynomial, so Horner on
 // the monomial coefficients gives the same field element with two multiplies.
-template <class F>
-__device__ __forceinline__ void sc_new_claim(ScShared<F>* sh) {
+template <class F, class S>
+__device__ __forceinline__ void sc_new_claim(S* sh) {
   const typename F::Elt rnd = sh->r;
   sh->sum = F::add(F::mul(F::add(F::mul(sh->pc[2], rnd), sh->pc[1]), rnd), sh->pc[0]);
 }

@@ -21,6 +21,7 @@
 #include "kernels_commit.cuh"
 #include "kernels_fft.cuh"
 #include "kernels_zk.cuh"
+#include "kernels_scflat.cuh"
 #include "zk_types.cuh"
 
 namespace lf {
