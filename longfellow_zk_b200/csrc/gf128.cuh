@@ -51,9 +51,15 @@ __host__ __device__ __forceinline__ uint64_t clmul32(uint32_t x, uint32_t y) {
   uint32_t x0 = x & m0, x1 = x & m1, x2 = x & m2, x3 = x & m3;
   uint32_t y0 = y & m0, y1 = y & m1, y2 = y & m2, y3 = y & m3;
 #define LF_WM(a, b) ((uint64_t)(a) * (uint64_t)(b))
-  uint64_t z0 = LF_WM(x0, y0) ^ LF_WM(x1, y3) ^ LF_WM(x2, y2) ^ LF_WM(x3, y1);
-  uint64_t z1 = LF_WM(x0, y1) ^ LF_WM(x1, y0) ^ LF_WM(x2, y3) ^ LF_WM(x3, y2);
-  uint64_t z2 = LF_WM(x0, y2) ^ LF_WM(x1, y1) ^ LF_WM(x2, y0) ^ LF_WM(x3, y3);
+  // x_i * y_j puts its partial products into the holes at bit 4h + (i + j): hole h holds at most
+  // min(h + 1, 15 - h) <= 8 of them when i + j < 4, and the same profile one hole later when
+  // i + j >= 4 (its hole h is the other's h - 1).  So a product of each kind can be ADDED: no hole
+  // ever sums more than 8 + 7 = 15 terms and none carries into its neighbour -- and the add is the
+  // multiplier's free accumulate input (IMAD.WIDE a * b + c), where an XOR is two LOP3.  Products
+  // of the same kind could reach 16 in hole 7 (or 8) and still take the XOR.
+  uint64_t z0 = (LF_WM(x0, y0) + LF_WM(x1, y3)) ^ LF_WM(x2, y2) ^ LF_WM(x3, y1);
+  uint64_t z1 = (LF_WM(x0, y1) + LF_WM(x2, y3)) ^ (LF_WM(x1, y0) + LF_WM(x3, y2));
+  uint64_t z2 = (LF_WM(x0, y2) + LF_WM(x3, y3)) ^ LF_WM(x1, y1) ^ LF_WM(x2, y0);
   uint64_t z3 = LF_WM(x0, y3) ^ LF_WM(x1, y2) ^ LF_WM(x2, y1) ^ LF_WM(x3, y0);
 #undef LF_WM
   const uint64_t M0 = 0x1111111111111111ull, M1 = 0x2222222222222222ull,

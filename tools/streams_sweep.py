@@ -14,7 +14,7 @@ streams = [torch.cuda.Stream() for _ in range(S_MAX)]
 ctxs = [lf.Context(0, stream=s.cuda_stream) for s in streams]
 provers = [lf.ZkProver(lf.Circuit(c, fid, circ)) for c in ctxs]
 info = provers[0].c.info
-rstride = (info["rng_bytes"] + 15) & ~15
+rstride = (info["rng_bytes"] + 8 * info["rng_redraw_bytes"] + 15) & ~15
 d_wit = torch.from_numpy(np.frombuffer(wit, np.uint8).copy()).repeat(B, 1).cuda()
 d_rng = torch.randint(0, 256, (B, rstride), dtype=torch.uint8)
 d_rng = d_rng.cuda()
@@ -34,4 +34,7 @@ for S in (1, 2, 3, 4):
     for k in range(K):
         step(k % S)
     torch.cuda.synchronize(); dt = time.perf_counter() - t0
-    print(which, "streams", S, "proofs/s %.0f" % (K * B / dt), "ms/step %.2f" % (1e3 * dt / K))
+    print(which, {k: v for k, v in os.environ.items() if k.startswith("LF_")}, "streams", S,
+          "proofs/s %.0f" % (K * B / dt), "ms/step %.2f" % (1e3 * dt / K))
+for o in outs:
+    assert int(o[2].abs().sum().item()) == 0
