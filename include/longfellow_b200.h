@@ -46,6 +46,7 @@ enum lf_status {
   LF_ERR_RNG = -6,          /* caller-supplied randomness too short (prime fields: including the draws
                                the reference's Field::sample repeats, see lf_zk_prove_batch) */
   LF_ERR_CAPACITY = -7,     /* output buffer too small */
+  LF_ERR_VERIFY = -8,       /* the verifier rejected the proof (ZkVerifier::verify == false) */
   LF_ERR_INTERNAL = -100    /* the sumcheck prover's own consistency check failed: never expected */
 };
 
@@ -149,6 +150,9 @@ typedef struct lf_circuit_info {
    * lower bound otherwise; up to rng_redraw_cap redraws per proof are followed.  rng_redraw_bytes
    * == 0: the field's samples never fail (GF(2^128)) and rng_bytes is exact. */
   size_t rng_sample_bytes, rng_redraw_bytes, rng_redraw_cap;
+  /* elements of the serialized sumcheck proof (ZkProof::write: root[32] | these | y_ldt[block] y_dot[dblock]
+   * y_quad_0[r] y_quad_2[dblock-block] | nreq nonces | run-length coded columns | Merkle proof) */
+  size_t sumcheck_proof_elts;
 } lf_circuit_info;
 int lf_circuit_get_info(const lf_circuit* c, lf_circuit_info* info);
 
@@ -215,6 +219,23 @@ int lf_zk_commit_batch(lf_circuit* c, size_t nproofs, const uint8_t* witnesses, 
 int lf_zk_prove_committed_batch(lf_circuit* c, size_t nproofs, const uint8_t* witnesses, lf_transcript* ts,
                                 uint8_t* proofs_out, size_t proof_stride, size_t* proof_lens, int* status);
 
+/* ---- verifier, batch of independent proofs -------------------------------------- */
+/* replaces, per proof i (lib/zk/zk_verifier.h:69-106, lib/zk/zk_proof.h:107-112):
+ *     ZkProof zkp(circuit, rate, nreq[, block_enc]);  ok = zkp.read(bytes_i, F);
+ *     Transcript tv(tinit, tinit_len);
+ *     ZkVerifier verifier(circuit, rs_factory, rate, nreq[, block_enc], F);
+ *     verifier.recv_commitment(zkp, tv);  ok = verifier.verify(zkp, pub_i, tv);
+ * pub_inputs: nproofs x npub_in elements (wire encoding; may be NULL when npub_in == 0).
+ * proofs: nproofs x proof_stride bytes, proof i is proof_lens[i] bytes long.
+ * status[i]: LF_OK accepted; LF_ERR_FORMAT the bytes are not a proof of this circuit's shape
+ * (ZkProof::read == false) or a public input is not canonical; LF_ERR_VERIFY rejected.
+ * why[i] (optional): the first check that failed, in the order of LigeroVerifier::verify
+ * (lib/ligero/ligero_verifier.h:92-134): 1 merkle_check, 2 low_degree_check, 3 dot_check,
+ * 4 wrong dot product, 5 quadratic_check; 0 otherwise.  Host pointers. */
+int lf_zk_verify_batch(lf_circuit* c, size_t nproofs, const uint8_t* pub_inputs, const uint8_t* proofs,
+                       size_t proof_stride, const size_t* proof_lens, const uint8_t* tinit, size_t tinit_len,
+                       int* status, int* why);
+
 /* bytes of proof `index`'s random stream that the most recent batch on `c` consumed
  * (= rng_bytes + redraws * rng_redraw_bytes) */
 int lf_zk_rng_consumed(lf_circuit* c, size_t index, size_t* bytes);
@@ -246,7 +267,8 @@ uint64_t lf_ctx_launch_count(const lf_ctx* ctx);
  *          3: SHA-256 compressions (G/s)  4: P-256 Montgomery multiply (Gmul/s)
  *   what = 100..105: single-thread latency of the transcript primitives, in
  *          CYCLES per call: compression, digest snapshot, AES-256 key
- *          schedule, AES block, 16-byte element write, write + challenge */
+ *          schedule, AES block, 16-byte element write, write + challenge;
+ *          107: the first write + challenge of the launch (cold instruction cache) */
 int lf_microbench(lf_ctx* ctx, int what, double* gops);
 
 #ifdef __cplusplus

@@ -21,7 +21,7 @@ class CircuitInfo(C.Structure):
         "max_proof_bytes", "block_enc", "block", "dblock", "block_ext", "nrow", "r", "w", "nwrow",
         "nqtriples", "nreq", "nw", "sumcheck_alg_bytes", "sumcheck_mults", "total_mults", "sha_compressions",
         "rs_mults", "eval_mults", "ligero_mults", "merkle_compressions", "lfc1_bytes",
-        "rng_sample_bytes", "rng_redraw_bytes", "rng_redraw_cap")]
+        "rng_sample_bytes", "rng_redraw_bytes", "rng_redraw_cap", "sumcheck_proof_elts")]
 
 
 class Transcript(C.Structure):
@@ -37,7 +37,7 @@ EXPORTS = [
     "lf_zk_prove_batch_dev", "lf_zk_debug_fetch", "lf_ctx_launch_count", "lf_microbench",
     "lf_circuit_set_profiling", "lf_circuit_get_stage_ms", "lf_fft", "lf_fft_time",
     "lf_zk_commit_batch", "lf_zk_prove_committed_batch", "lf_transcript_init", "lf_transcript_write_bytes",
-    "lf_transcript_challenge_bytes", "lf_zk_rng_consumed", "lf_circuit_verify_id",
+    "lf_transcript_challenge_bytes", "lf_zk_rng_consumed", "lf_circuit_verify_id", "lf_zk_verify_batch",
 ]
 
 
@@ -92,6 +92,8 @@ def lib():
         L.lf_transcript_challenge_bytes.restype = None
         L.lf_circuit_verify_id.argtypes = [C.c_void_p, C.c_void_p]
         L.lf_zk_rng_consumed.argtypes = [C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
+        L.lf_zk_verify_batch.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p,
+                                         C.c_char_p, C.c_size_t, C.c_void_p, C.c_void_p]
         _lib = L
     return _lib
 

@@ -261,3 +261,36 @@ class ZkProver:
         n = C.c_size_t()
         check(_native.lib().lf_zk_debug_fetch(self.c._h, index, stage, _p(buf), cap, C.byref(n)))
         return buf[:n.value].copy()
+
+
+class ZkVerifier:
+    """zk/zk_verifier.h:39-111 + ZkProof::read (zk/zk_proof.h:107-112): recv_commitment + verify for a batch
+    of independent proofs of one circuit (lf_zk_verify_batch)."""
+
+    WHY = ["", "merkle_check", "low_degree_check", "dot_check", "wrong dot product", "quadratic_check"]
+
+    def __init__(self, circuit):
+        self.c = circuit
+
+    def verify_batch(self, pub_inputs, proofs, tinit=b"test"):
+        """pub_inputs: (B, npub_in*kBytes) uint8 (or None when the circuit has no public inputs); proofs: a list
+        of B byte strings.  Returns (status, why) int32 arrays: status 0 accepted, LF_ERR_FORMAT (-3) not a
+        proof of this shape, LF_ERR_VERIFY (-8) rejected with why = index into WHY."""
+        info = self.c.info
+        B = len(proofs)
+        stride = max(16, max(len(p) for p in proofs))
+        buf = np.zeros((B, stride), np.uint8)
+        lens = np.zeros(B, np.uint64)
+        for i, pr in enumerate(proofs):
+            buf[i, :len(pr)] = np.frombuffer(pr, np.uint8)
+            lens[i] = len(pr)
+        pubb = info["npub_in"] * info["kbytes"]
+        pub = None
+        if pubb:
+            pub = _u8(pub_inputs).reshape(B, -1)
+            assert pub.shape[1] == pubb, pub.shape
+        status = np.zeros(B, np.int32)
+        why = np.zeros(B, np.int32)
+        check(_native.lib().lf_zk_verify_batch(self.c._h, B, _p(pub) if pub is not None else None, _p(buf), stride,
+                                               _p(lens), tinit, len(tinit), _p(status), _p(why)))
+        return status, why

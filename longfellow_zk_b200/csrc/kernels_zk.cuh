@@ -1272,39 +1272,19 @@ __device__ __forceinline__ void put_digest(uint8_t* dst, const uint32_t* be_word
   }
 }
 
-// 128 threads, 8 CTAs per SM: the kernel is bound by one thread per proof running the
-// SHA-256 rounds, so a whole batch of 1024 proofs should be resident at once (at 256
-// threads and 124 registers only 2 CTAs fitted an SM: 3.5 waves).
+// The part of LigeroProver::prove that the prover and the verifier share (ligero_prover.h:127-145,
+// ligero_verifier.h:83-90): the four response arrays y_ldt | y_dot | y_quad_0 | y_quad_2 enter the
+// transcript and the opened columns are drawn (RandomEngine::choose, random.h:92-105).  Called by
+// all threads of a CTA; y in the layout of ZkBufs::y; msg: scratch for the message bytes
+// (>= 64 + 36 + (block + 2 dblock + r - block) kBytes ... i.e. what the arrays serialise to);
+// perm [n], mark [2n bytes] scratch; on return idx[0..nreq) and mark[n + idx] = 1, *gts updated.
 template <class F>
-__global__ void __launch_bounds__(128, 8)
-k_lig_finish(ZkDims d, ZkBufs<typename F::Elt> b, const LayerDesc* __restrict__ layers) {
-  typedef typename F::Elt Elt;
-  const size_t p = blockIdx.x;
-  if (b.status[p] != 0) {
-    if (threadIdx.x == 0) b.out_len[p] = 0;
-    return;
-  }
+__device__ __forceinline__ void lig_absorb_and_choose(const ZkDims& d, const typename F::Elt* __restrict__ y,
+                                                      Transcript* gts, uint8_t* msg, uint32_t* perm, uint8_t* mark,
+                                                      uint32_t* idx, const AesTables* aes) {
   const uint32_t tid = threadIdx.x, nth = blockDim.x;
-  const Elt* T = b.tableau + p * (size_t)d.nrow * d.block_enc;
-  const Elt* y = b.y + p * (size_t)(d.block + 2 * d.dblock);
-  const Elt* sc = b.sc + p * d.sc_elts;
-  const uint32_t* nodes = b.nodes + p * (size_t)(2 * d.block_ext * 8);
-  // the nonces follow the last sample: redrawn slots push them back (k_zk_rng_scan)
-  const uint8_t* nonces = b.rng + p * b.rng_stride + d.rng_nonce_off +
-                          (b.rej ? (size_t)b.rej[p * (size_t)(1 + d.rej_cap)] * F::kBytes : 0);
-  uint32_t* idx = b.idx + p * d.nreq;
-  uint8_t* out = b.out + p * b.out_stride;
-  uint32_t* sw = b.scratch + p * b.scratch_words;
-  const uint32_t n = d.block_ext, total = d.nreq * d.nrow;
-  uint32_t* perm = sw;
-  uint8_t* mark = reinterpret_cast<uint8_t*>(sw + n);
-  uint8_t* flag = mark + 2 * (size_t)((n + 3) & ~3u);
-  uint32_t* eoff = reinterpret_cast<uint32_t*>(flag + ((total + 3) & ~3u));
-  uint32_t* path_idx = eoff + total;
-  __shared__ uint32_t s_npath, s_req_end;
-  __shared__ AesTables s_aes;
-  aes_stage_tables(&s_aes);
-
+  const uint32_t n = d.block_ext;
+  const AesTables& s_aes = *aes;
   for (uint32_t i = tid; i < n; i += nth) perm[i] = i;
   for (uint32_t i = tid; i < 2 * n; i += nth) mark[i] = 0;
   // ---- the four response arrays enter the transcript (ligero_prover.h:84-146) ----
@@ -1319,8 +1299,6 @@ k_lig_finish(ZkDims d, ZkBufs<typename F::Elt> b, const LayerDesc* __restrict__ 
   __shared__ uint64_t s_len0;
   const uint32_t lens[4] = {d.block, d.dblock, d.r, d.dblock - d.block};
   const uint32_t offs[4] = {0, d.block, d.block + d.dblock, d.block + d.dblock + d.block};
-  Transcript* gts = reinterpret_cast<Transcript*>(b.ts + p * sizeof(Transcript));
-  uint8_t* msg = out;
   if (tid == 0) {
     const Sha256& sh0 = gts->sha;
     const uint32_t pos0 = (uint32_t)(sh0.len & 63);
@@ -1392,6 +1370,43 @@ k_lig_finish(ZkDims d, ZkBufs<typename F::Elt> b, const LayerDesc* __restrict__ 
     *gts = ts;
   }
   __syncthreads();
+}
+
+// 128 threads, 8 CTAs per SM: the kernel is bound by one thread per proof running the
+// SHA-256 rounds, so a whole batch of 1024 proofs should be resident at once (at 256
+// threads and 124 registers only 2 CTAs fitted an SM: 3.5 waves).
+template <class F>
+__global__ void __launch_bounds__(128, 8)
+k_lig_finish(ZkDims d, ZkBufs<typename F::Elt> b, const LayerDesc* __restrict__ layers) {
+  typedef typename F::Elt Elt;
+  const size_t p = blockIdx.x;
+  if (b.status[p] != 0) {
+    if (threadIdx.x == 0) b.out_len[p] = 0;
+    return;
+  }
+  const uint32_t tid = threadIdx.x, nth = blockDim.x;
+  const Elt* T = b.tableau + p * (size_t)d.nrow * d.block_enc;
+  const Elt* y = b.y + p * (size_t)(d.block + 2 * d.dblock);
+  const Elt* sc = b.sc + p * d.sc_elts;
+  const uint32_t* nodes = b.nodes + p * (size_t)(2 * d.block_ext * 8);
+  // the nonces follow the last sample: redrawn slots push them back (k_zk_rng_scan)
+  const uint8_t* nonces = b.rng + p * b.rng_stride + d.rng_nonce_off +
+                          (b.rej ? (size_t)b.rej[p * (size_t)(1 + d.rej_cap)] * F::kBytes : 0);
+  uint32_t* idx = b.idx + p * d.nreq;
+  uint8_t* out = b.out + p * b.out_stride;
+  uint32_t* sw = b.scratch + p * b.scratch_words;
+  const uint32_t n = d.block_ext, total = d.nreq * d.nrow;
+  uint32_t* perm = sw;
+  uint8_t* mark = reinterpret_cast<uint8_t*>(sw + n);
+  uint8_t* flag = mark + 2 * (size_t)((n + 3) & ~3u);
+  uint32_t* eoff = reinterpret_cast<uint32_t*>(flag + ((total + 3) & ~3u));
+  uint32_t* path_idx = eoff + total;
+  __shared__ uint32_t s_npath, s_req_end;
+  __shared__ AesTables s_aes;
+  aes_stage_tables(&s_aes);
+
+  lig_absorb_and_choose<F>(d, y, reinterpret_cast<Transcript*>(b.ts + p * sizeof(Transcript)), out, perm, mark, idx,
+                           &s_aes);
   // compressed_merkle_proof_tree (merkle_tree.h:75-98), level by level
   if (n >= 2) {
     int top = 31 - __clz(n - 1);

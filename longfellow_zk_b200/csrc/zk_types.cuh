@@ -29,6 +29,7 @@ struct LayerDesc {
   uint32_t ev_perm;              // [nout] gates sorted by decreasing term count
   uint32_t bg_seg;   // [nterms] initial HQuad corner of each term (canonical order, non-decreasing)
   uint32_t bg_g, bg_vi;          // [nterms]
+  uint32_t vq_h0, vq_h1;         // [nhq0] the two hand indices of each initial corner (verifier: bind_gh_all)
   uint32_t step0;    // first StepDesc of this layer (2*logw of them)
   uint32_t w_off;    // element offset of this layer's input wires in the per-proof wire store
   uint32_t out_off;  // element offset of this layer's output wires
