@@ -236,6 +236,13 @@ int lf_zk_verify_batch(lf_circuit* c, size_t nproofs, const uint8_t* pub_inputs,
                        size_t proof_stride, const size_t* proof_lens, const uint8_t* tinit, size_t tinit_len,
                        int* status, int* why);
 
+/* Test hook, the analogue of BadReedSolomonFactory in lib/ligero/ligero_test.cc:114-160: make exactly one of the
+ * verifier's own computations wrong so that each check of LigeroVerifier::verify can be seen to fire on an
+ * otherwise valid proof.  fault: 0 none; 1 the interpolation of y_ldt (low_degree_check); 2 of y_dot
+ * (dot_check); 3 of y_quad (quadratic_check); 4 of the first row of A (dot_check); 5 the value of b . alphal
+ * plus one ("wrong dot product").  Stays set on `c` until reset. */
+int lf_zk_verify_set_fault(lf_circuit* c, int fault);
+
 /* bytes of proof `index`'s random stream that the most recent batch on `c` consumed
  * (= rng_bytes + redraws * rng_redraw_bytes) */
 int lf_zk_rng_consumed(lf_circuit* c, size_t index, size_t* bytes);

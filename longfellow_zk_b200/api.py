@@ -272,6 +272,10 @@ class ZkVerifier:
     def __init__(self, circuit):
         self.c = circuit
 
+    def set_fault(self, fault):
+        """test hook (lf_zk_verify_set_fault): break one of the verifier's interpolations"""
+        check(_native.lib().lf_zk_verify_set_fault(self.c._h, int(fault)))
+
     def verify_batch(self, pub_inputs, proofs, tinit=b"test"):
         """pub_inputs: (B, npub_in*kBytes) uint8 (or None when the circuit has no public inputs); proofs: a list
         of B byte strings.  Returns (status, why) int32 arrays: status 0 accepted, LF_ERR_FORMAT (-3) not a

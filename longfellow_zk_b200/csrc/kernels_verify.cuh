@@ -405,6 +405,25 @@ __global__ void k_zkv_rows(ZkDims d, ZkBufs<typename F::Elt> b) {
   }
 }
 
+// Fault injection for tests, the analogue of BadInterpolator (ligero/ligero_test.cc:114-160): the extension
+// part [n, block_enc) of one extended row is rotated left by one, so that exactly one of the verifier's
+// interpolations is wrong.  One thread per proof (test-only, tiny).
+template <class F>
+__global__ void k_zkv_fault(ZkDims d, ZkBufs<typename F::Elt> b, ZkVBufs<typename F::Elt> v, uint32_t row, uint32_t n,
+                            int bump_dot, size_t nproofs) {
+  typedef typename F::Elt Elt;
+  const size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= nproofs) return;
+  if (bump_dot) {
+    v.dots[2 * p] = F::add(v.dots[2 * p], F::one());
+    return;
+  }
+  Elt* T = b.tableau + (p * d.nrow + row) * (size_t)d.block_enc;
+  const Elt first = T[n];
+  for (uint32_t i = n; i + 1 < d.block_enc; ++i) T[i] = T[i + 1];
+  T[d.block_enc - 1] = first;
+}
+
 // the responses enter the transcript, the opened columns are drawn (shared with the prover)
 template <class F>
 __global__ void __launch_bounds__(128, 8)

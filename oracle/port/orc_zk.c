@@ -4,6 +4,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <stdio.h>
 #include "orc.h"
 
 #define KMAXB 40 /* sumcheck/circuit.h:77 kMaxBindings */
@@ -795,6 +796,13 @@ int zk_prove(const circuit* c, const uint8_t* wbytes, rng* rg, const uint8_t* ti
     }
     if (!eval_quad(c, &c->l[l], V, nvout, in[l])) rc = -3;
   }
+  if (getenv("ORC_WIRE_STATS"))
+    for (size_t l = 0; l < nl; ++l) {
+      size_t nb = 0, nwl = c->l[l].nw;
+      for (size_t i = 0; i < nwl; ++i)
+        if (f_is_zero(F, in[l][i]) || memcmp(&in[l][i], &F->one, sizeof(elt)) == 0) ++nb;
+      fprintf(stderr, "layer %zu nw %zu bits %zu nterms %zu\n", l, nwl, nb, (size_t)c->l[l].nterms);
+    }
   for (size_t i = 0; i < c->nv; ++i)
     if (!f_is_zero(F, finalV[i])) rc = -3;
 

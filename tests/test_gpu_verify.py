@@ -159,6 +159,23 @@ def test_malformed_proofs_are_format_errors(case, ref):
     assert st[0] == 0
 
 
+def test_each_ligero_check_fires(case):
+    """ligero_test.cc:160-268 (test_ligero_verifier_failures): with one of the verifier's interpolations
+    broken (BadReedSolomonFactory), or b changed, a valid proof fails at exactly that check"""
+    v = case["v"]
+    proofs = case["proofs"][:3]
+    want = {1: 2, 2: 3, 3: 5, 4: 3, 5: 4}
+    try:
+        for fault, why_code in want.items():
+            v.set_fault(fault)
+            st, why = v.verify_batch(_pubs(case, 3), proofs)
+            assert (st == -8).all() and (why == why_code).all(), (fault, st, why)
+    finally:
+        v.set_fault(0)
+    st, why = v.verify_batch(_pubs(case, 3), proofs)
+    assert (st == 0).all()
+
+
 def test_prover_still_works_after_a_verify(case, oracle):
     """the verifier reuses the prover's per-proof buffers"""
     import longfellow_zk_b200 as lf
