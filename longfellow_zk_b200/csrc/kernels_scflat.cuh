@@ -192,74 +192,72 @@ __global__ void k_sc_bindg_fix(ZkDims d, ZkBufs<typename F::Elt> b, const uint32
 // k_sc_eval: the two sums of one round (prover_layers.h:357-402),
 //   a0 = sum_i QW[2i] W[2i],   a2 = sum_i (QW[2i+1] - QW[2i]) (W[2i+1] - W[2i]),
 // with QW[l] = sum_r Q[l, r] W'[r] (prover_layers.h:230-243) computed on the fly per row pair and
-// never stored.  grid = (ncta, proofs); the CTA's partial (a0, a2) goes to part[2 * cta ..].
+// never stored.  grid = (ceil(nbin / warps per CTA), proofs); every warp owns one BIN of work items and leaves
+// its partial (a0, a2) in part[2 * bin ..]; k_sc_round adds the nbin partials of a proof.
 // ----------------------------------------------------------------------------
 template <class F>
-__global__ void __launch_bounds__(32 * kFlatEvalWarps)
+__global__ void __launch_bounds__(32 * kFlatEvalWarps, kFlatEvalMinCta)
 k_sc_eval(ZkDims d, ZkBufs<typename F::Elt> b, const uint32_t* __restrict__ arena, LayerDesc L, StepDesc S,
           FlatStepDesc FS, uint32_t t) {
   typedef typename F::Elt Elt;
   typedef typename F::Acc Acc;
   const size_t p = blockIdx.y;
   if (b.status[p] != 0) return;
-  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31, cta = blockIdx.x;
+  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t bin = blockIdx.x * kFlatEvalWarps + warp;
+  if (bin >= FS.nbin) return;
   const FlatPtrs<F> P(d, b, L, p, t);
   const Elt *Wh = P.Wh, *Wo = P.Wo, *HQ = P.HQ;
   Acc c0, c2;
   F::acc_zero(c0);
   F::acc_zero(c2);
-  for (uint32_t wb = cta + FS.ncta * warp; wb < FS.nwarp_pair; wb += FS.ncta * kFlatEvalWarps) {
-    const uint32_t slot = wb * 32 + lane;
-    const uint32_t pair = arena[FS.pw_pair + slot];
-    if (pair == kFlatNone) continue;
-    const uint32_t cnt = arena[FS.pw_cnt + slot], n0c = cnt & 0xffffu, tot = n0c + (cnt >> 16);
-    const uint32_t base = arena[FS.pw_base + wb];
-    Acc q0, q1;
-    F::acc_zero(q0);
-    F::acc_zero(q1);
-    for (uint32_t k = 0; k < tot; ++k) {
-      const uint32_t e = base + k * 32 + lane;
-      F::mac_sel(q0, q1, k < n0c, HQ[arena[FS.e_c + e]], Wo[arena[FS.e_p + e]]);
-    }
-    const Elt qw0 = F::reduce(q0), qw1 = F::reduce(q1);
-    const Elt w0 = Wh[2 * pair], w1 = (2 * pair + 1 < S.n0) ? Wh[2 * pair + 1] : F::zero();
-    F::mac(c0, qw0, w0);
-    F::mac(c2, F::sub(qw1, qw0), F::sub(w1, w0));
-  }
-  // heavy rows: the chunk's partial QW enters both sums by linearity
-  for (uint32_t hw = cta + FS.ncta * warp; hw < FS.nwarp_heavy; hw += FS.ncta * kFlatEvalWarps) {
-    const uint32_t row = arena[FS.hv_row + hw], off = arena[FS.hv_off + hw], cnt = arena[FS.hv_cnt + hw];
-    const uint32_t *rc = arena + S.row_c, *rp = arena + S.row_p1;
-    Acc q;
-    F::acc_zero(q);
-    for (uint32_t e = off + lane; e < off + cnt; e += 32) F::mac(q, HQ[rc[e]], Wo[rp[e]]);
-    const Elt v = warp_sum<F>(F::reduce(q));
-    if (lane == 0) {
-      if ((row & 1) == 0) {
-        const Elt w0 = Wh[row], w1 = (row + 1 < S.n0) ? Wh[row + 1] : F::zero();
-        F::mac(c0, v, w0);
-        F::mac(c2, F::neg(v), F::sub(w1, w0));
-      } else {
-        F::mac(c2, v, F::sub(Wh[row], Wh[row - 1]));
+  // the bin's items (balanced on the host by their entry counts): sliced-ELL warps of row pairs, then heavy-row chunks
+  const uint32_t i0 = arena[FS.bin_off + bin], i1 = arena[FS.bin_off + bin + 1];
+  for (uint32_t ii = i0; ii < i1; ++ii) {
+    const uint32_t item = arena[FS.bin_item + ii];
+    if (item < FS.nwarp_pair) {
+      const uint32_t wb = item, slot = wb * 32 + lane;
+      const uint32_t pair = arena[FS.pw_pair + slot];
+      if (pair == kFlatNone) continue;
+      const uint32_t cnt = arena[FS.pw_cnt + slot], n0c = cnt & 0xffffu, tot = n0c + (cnt >> 16);
+      const uint32_t base = arena[FS.pw_base + wb];
+      Acc q0, q1;
+      F::acc_zero(q0);
+      F::acc_zero(q1);
+      for (uint32_t k = 0; k < tot; ++k) {
+        const uint32_t e = base + k * 32 + lane;
+        F::mac_sel(q0, q1, k < n0c, HQ[arena[FS.e_c + e]], Wo[arena[FS.e_p + e]]);
+      }
+      const Elt qw0 = F::reduce(q0), qw1 = F::reduce(q1);
+      const Elt w0 = Wh[2 * pair], w1 = (2 * pair + 1 < S.n0) ? Wh[2 * pair + 1] : F::zero();
+      F::mac(c0, qw0, w0);
+      F::mac(c2, F::sub(qw1, qw0), F::sub(w1, w0));
+    } else {
+      // heavy row: the chunk's partial QW enters both sums by linearity
+      const uint32_t hw = item - FS.nwarp_pair;
+      const uint32_t row = arena[FS.hv_row + hw], off = arena[FS.hv_off + hw], cnt = arena[FS.hv_cnt + hw];
+      const uint32_t *rc = arena + S.row_c, *rp = arena + S.row_p1;
+      Acc q;
+      F::acc_zero(q);
+      for (uint32_t e = off + lane; e < off + cnt; e += 32) F::mac(q, HQ[rc[e]], Wo[rp[e]]);
+      const Elt v = warp_sum<F>(F::reduce(q));
+      if (lane == 0) {
+        if ((row & 1) == 0) {
+          const Elt w0 = Wh[row], w1 = (row + 1 < S.n0) ? Wh[row + 1] : F::zero();
+          F::mac(c0, v, w0);
+          F::mac(c2, F::neg(v), F::sub(w1, w0));
+        } else {
+          F::mac(c2, v, F::sub(Wh[row], Wh[row - 1]));
+        }
       }
     }
   }
-  __shared__ Elt red[2][kFlatEvalWarps];
+  // no CTA-level reduction (a barrier here made every warp wait for the CTA's slowest): one partial per warp
   const Elt s0 = warp_sum<F>(F::reduce(c0)), s2 = warp_sum<F>(F::reduce(c2));
   if (lane == 0) {
-    red[0][warp] = s0;
-    red[1][warp] = s2;
-  }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    Elt r0 = red[0][0], r2 = red[1][0];
-    for (uint32_t w = 1; w < kFlatEvalWarps; ++w) {
-      r0 = F::add(r0, red[0][w]);
-      r2 = F::add(r2, red[1][w]);
-    }
-    Elt* part = b.part + p * 2 * (size_t)kFlatMaxCta;
-    part[2 * cta] = r0;
-    part[2 * cta + 1] = r2;
+    Elt* part = b.part + p * 2 * (size_t)kFlatMaxBins;
+    part[2 * bin] = s0;
+    part[2 * bin + 1] = s2;
   }
 }
 
@@ -278,16 +276,16 @@ struct ScLane {  // the members sc_round_serial / sc_new_claim touch, in a threa
 
 template <class F>
 __global__ void __launch_bounds__(32)
-k_sc_round(ZkDims d, ZkBufs<typename F::Elt> b, LayerDesc L, uint32_t t, uint32_t ncta, size_t nproofs) {
+k_sc_round(ZkDims d, ZkBufs<typename F::Elt> b, LayerDesc L, uint32_t t, uint32_t nbin, size_t nproofs) {
   typedef typename F::Elt Elt;
   __shared__ AesTables s_aes;
   aes_stage_tables(&s_aes);
   const size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= nproofs || b.status[p] != 0) return;
   ScCore<F>* core = reinterpret_cast<ScCore<F>*>(b.scst + p * sizeof(ScCore<F>));
-  const Elt* part = b.part + p * 2 * (size_t)kFlatMaxCta;
+  const Elt* part = b.part + p * 2 * (size_t)kFlatMaxBins;
   Elt s0 = part[0], s2 = part[1];
-  for (uint32_t c = 1; c < ncta; ++c) {
+  for (uint32_t c = 1; c < nbin; ++c) {
     s0 = F::add(s0, part[2 * c]);
     s2 = F::add(s2, part[2 * c + 1]);
   }

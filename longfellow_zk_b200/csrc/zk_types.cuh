@@ -56,21 +56,25 @@ struct StepDesc {
 // THREAD per proof, so a warp runs the SHA-256/AES chains of 32 proofs in lockstep) and k_sc_bind
 // (Dense::bind and HQuad::bind_h).  The work lists are static per circuit:
 //
-// k_sc_eval: one thread per PAIR of rows (2i, 2i+1) of the hand's CSR; pairs are sorted by their
+// k_sc_eval: one lane per PAIR of rows (2i, 2i+1) of the hand's CSR; pairs are sorted by their
 // number of entries and stored 32 to a warp in column-major (sliced-ELL) order, so index loads are
 // coalesced and the 32 lanes loop about equally often.  Rows with more than kFlatHeavyRow entries
 // (the constant wire 0 feeds tens of thousands of corners) are taken out of their pair and cut
 // into warp-sized chunks whose partial QW enters the two dot products by linearity.
 constexpr uint32_t kFlatHeavyRow = 48;     // entries of one row a pair thread still takes
 constexpr uint32_t kFlatHeavyChunk = 256;  // entries per heavy-row warp chunk
-constexpr uint32_t kFlatEvalWarps = 8;     // warps per CTA of k_sc_eval
-constexpr uint32_t kFlatMaxCta = 8;        // CTAs per proof of k_sc_eval (their partial sums are added by k_sc_round)
+constexpr uint32_t kFlatEvalWarps = 4;     // warps per CTA of k_sc_eval
+constexpr uint32_t kFlatEvalMinCta = 5;    // resident CTAs per SM the kernel is compiled for (register cap)
+constexpr uint32_t kFlatMaxBins = 32;      // warps (bins of work) per proof of k_sc_eval; k_sc_round adds their partials
+constexpr uint32_t kFlatBinCost = 8;       // smallest bin worth a warp, in multiplications per lane
 constexpr uint32_t kFlatNone = 0xffffffffu;
 
 struct FlatStepDesc {
   uint32_t nwarp_pair;   // sliced-ELL warps of row pairs
   uint32_t nwarp_heavy;  // heavy-row chunks, one warp each
-  uint32_t ncta;         // CTAs per proof
+  uint32_t nbin;         // warps per proof: each takes the items bin_item[bin_off[w] .. bin_off[w+1])
+  uint32_t bin_off;      // [nbin + 1]
+  uint32_t bin_item;     // [nwarp_pair + nwarp_heavy] item < nwarp_pair: sliced-ELL warp; else heavy chunk + nwarp_pair
   uint32_t pw_pair;      // [32 * nwarp_pair] pair index of each lane (kFlatNone: padding)
   uint32_t pw_cnt;       // [32 * nwarp_pair] entries of row 2i | entries of row 2i+1 << 16
   uint32_t pw_base;      // [nwarp_pair] entry offset of the warp's column-major block
@@ -137,7 +141,7 @@ struct ZkBufs {
   Elt* hb;         // [nhb] hand challenges
   Elt* alphas;     // [nl] per-layer alpha
   uint8_t* scst;   // [sizeof(ScCore<F>)] sumcheck prover state between the kernels of the flat path
-  Elt* part;       // [2 * kFlatMaxCta] per-CTA partial sums of the two dot products of a round
+  Elt* part;       // [2 * kFlatMaxBins] per-warp partial sums of the two dot products of a round
   Elt* chal;       // [1 + nchal] alpha_in, u_ldt, alphal, alphaq, u_quad
   Elt* avec;       // [nwqrow * w]
   Elt* aext;       // [nwqrow * dblock]
