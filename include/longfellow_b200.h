@@ -81,6 +81,8 @@ int lf_elt_mul(lf_ctx* ctx, int field_id, const void* a, const void* b, void* ou
 int lf_fft(lf_ctx* ctx, int field_id, void* elts, size_t n, int forward);
 /* device-resident timing of fftb at size n (CUDA events on the context stream) */
 int lf_fft_time(lf_ctx* ctx, int field_id, size_t n, int reps, double* ms_per_fft);
+/* the same for nrows independent transforms of size n side by side (one call = all rows) */
+int lf_fft_time_rows(lf_ctx* ctx, int field_id, size_t n, size_t nrows, int reps, double* ms_per_call);
 
 /* ---- (a7,a9) Reed-Solomon row extension -------------------------------- */
 /* replaces InterpolatorFactory::make(n, m)->interpolate(y) batched over rows
@@ -92,6 +94,10 @@ int lf_rs_interpolate(lf_ctx* ctx, int field_id, size_t n, size_t m, void* rows,
  * context stream */
 int lf_rs_interpolate_dev(lf_ctx* ctx, int field_id, size_t n, size_t m, void* d_rows,
                           size_t row_stride, size_t nrows);
+
+/* device-resident timing of one lf_rs_interpolate_dev call on nrows rows (CUDA events on the context
+ * stream; row contents are arbitrary limbs, the arithmetic does not depend on them) */
+int lf_rs_time(lf_ctx* ctx, int field_id, size_t n, size_t m, size_t nrows, int reps, double* ms_per_call);
 
 /* ---- (a11) Merkle column commitment ------------------------------------ */
 /* replaces LigeroProver::commit's MerkleCommitment::commit(updhash, rng)
@@ -153,8 +159,18 @@ typedef struct lf_circuit_info {
   /* elements of the serialized sumcheck proof (ZkProof::write: root[32] | these | y_ldt[block] y_dot[dblock]
    * y_quad_0[r] y_quad_2[dblock-block] | nreq nonces | run-length coded columns | Merkle proof) */
   size_t sumcheck_proof_elts;
+  /* Large batches run the big sumcheck rounds as grid-wide kernels (k_sc_eval / k_sc_round / k_sc_bind, one
+   * launch each per round): number of such rounds, and per proof the algorithmic bytes and field
+   * multiplications of all k_sc_eval launches (per CSR entry two indices, an HQuad value, a wire and one
+   * product; per wire pair two wires and two products) and of all k_sc_bind launches. */
+  size_t flat_rounds, flat_eval_alg_bytes, flat_eval_mults, flat_bind_alg_bytes, flat_bind_mults;
 } lf_circuit_info;
 int lf_circuit_get_info(const lf_circuit* c, lf_circuit_info* info);
+
+/* With profiling on (lf_circuit_set_profiling), the most recent batch's device time of one kernel class of
+ * the flat sumcheck, summed over its launches (CUDA events around every launch on the context stream):
+ * cls 0 k_sc_eval, 1 k_sc_bind, 2 k_sc_round, 3 k_zk_sumcheck over the small rounds. */
+int lf_circuit_get_kernel_ms(lf_circuit* c, int cls, float* ms_total, size_t* launches);
 
 /* ---- whole prover, batch of independent proofs -------------------------- */
 /* replaces, per proof i (lib/zk/zk_prover.h:72-149, lib/zk/zk_proof.h:90-112):

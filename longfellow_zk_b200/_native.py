@@ -21,7 +21,8 @@ class CircuitInfo(C.Structure):
         "max_proof_bytes", "block_enc", "block", "dblock", "block_ext", "nrow", "r", "w", "nwrow",
         "nqtriples", "nreq", "nw", "sumcheck_alg_bytes", "sumcheck_mults", "total_mults", "sha_compressions",
         "rs_mults", "eval_mults", "ligero_mults", "merkle_compressions", "lfc1_bytes",
-        "rng_sample_bytes", "rng_redraw_bytes", "rng_redraw_cap", "sumcheck_proof_elts")]
+        "rng_sample_bytes", "rng_redraw_bytes", "rng_redraw_cap", "sumcheck_proof_elts",
+        "flat_rounds", "flat_eval_alg_bytes", "flat_eval_mults", "flat_bind_alg_bytes", "flat_bind_mults")]
 
 
 class Transcript(C.Structure):
@@ -37,7 +38,7 @@ EXPORTS = [
     "lf_zk_prove_batch_dev", "lf_zk_debug_fetch", "lf_ctx_launch_count", "lf_microbench",
     "lf_circuit_set_profiling", "lf_circuit_get_stage_ms", "lf_fft", "lf_fft_time",
     "lf_zk_commit_batch", "lf_zk_prove_committed_batch", "lf_transcript_init", "lf_transcript_write_bytes",
-    "lf_transcript_challenge_bytes", "lf_zk_rng_consumed", "lf_circuit_verify_id", "lf_zk_verify_batch", "lf_zk_verify_set_fault",
+    "lf_transcript_challenge_bytes", "lf_zk_rng_consumed", "lf_circuit_verify_id", "lf_zk_verify_batch", "lf_zk_verify_set_fault", "lf_fft_time_rows", "lf_rs_time", "lf_circuit_get_kernel_ms",
 ]
 
 
@@ -79,6 +80,10 @@ def lib():
         L.lf_circuit_get_stage_ms.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.c_size_t]
         L.lf_fft.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.c_int]
         L.lf_fft_time.argtypes = [C.c_void_p, C.c_int, C.c_size_t, C.c_int, C.POINTER(C.c_double)]
+        L.lf_fft_time_rows.argtypes = [C.c_void_p, C.c_int, C.c_size_t, C.c_size_t, C.c_int, C.POINTER(C.c_double)]
+        L.lf_rs_time.argtypes = [C.c_void_p, C.c_int, C.c_size_t, C.c_size_t, C.c_size_t, C.c_int,
+                                 C.POINTER(C.c_double)]
+        L.lf_circuit_get_kernel_ms.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_size_t)]
         L.lf_microbench.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_double)]
         L.lf_zk_commit_batch.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_size_t,
                                          C.POINTER(Transcript), C.c_void_p, C.c_void_p]

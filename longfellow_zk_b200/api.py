@@ -74,6 +74,17 @@ class Context:
         check(_native.lib().lf_fft_time(self._h, field_id, n, reps, C.byref(ms)))
         return ms.value
 
+    def fft_time_rows_ms(self, field_id, n, nrows, reps=5):
+        ms = C.c_double()
+        check(_native.lib().lf_fft_time_rows(self._h, field_id, n, nrows, reps, C.byref(ms)))
+        return ms.value
+
+    def rs_time_ms(self, field_id, n, m, nrows, reps=5):
+        """device-resident time of one ReedSolomon(n, m) extension of nrows rows (lf_rs_time)"""
+        ms = C.c_double()
+        check(_native.lib().lf_rs_time(self._h, field_id, n, m, nrows, reps, C.byref(ms)))
+        return ms.value
+
     def microbench(self, what):
         g = C.c_double()
         check(_native.lib().lf_microbench(self._h, int(what), C.byref(g)))
@@ -249,6 +260,17 @@ class ZkProver:
         if n < 0:
             check(n)
         return dict(zip(self.STAGES, [float(x) for x in ms[:n]]))
+
+    KERNEL_CLASSES = ["k_sc_eval", "k_sc_bind", "k_sc_round", "k_zk_sumcheck_tail"]
+
+    def kernel_ms(self):
+        """per kernel class of the flat sumcheck: (total ms, launches) of the most recent profiled batch"""
+        out = {}
+        for i, name in enumerate(self.KERNEL_CLASSES):
+            ms, n = C.c_float(), C.c_size_t()
+            check(_native.lib().lf_circuit_get_kernel_ms(self.c._h, i, C.byref(ms), C.byref(n)))
+            out[name] = (float(ms.value), int(n.value))
+        return out
 
     def rng_consumed(self, index):
         """bytes of proof `index`'s random stream the most recent batch consumed (redraws included)"""

@@ -117,41 +117,50 @@ __global__ void k_fft_pointwise(typename A::Elt* __restrict__ a, const typename 
 }
 
 // RS through FFTConvolution (lib/algebra/convolution.h:55-106) for fields with
-// 2-power roots: x = binom * y zero-padded to N (one row per blockIdx.y)
+// 2-power roots: x = binom * y zero-padded to N.  Work row blockIdx.y is row (row0 + blockIdx.y) of the
+// caller's rows: row r of batch b sits at rows + b * batch_stride + r * row_stride (rpb rows per batch).
+struct RsRows {
+  size_t row_stride, batch_stride;
+  uint32_t rpb, row0;
+  __device__ __forceinline__ size_t at(uint32_t y) const {
+    const uint32_t g = row0 + y;
+    return (size_t)(g / rpb) * batch_stride + (size_t)(g % rpb) * row_stride;
+  }
+};
 template <class F>
-__global__ void k_rs_pad(const typename F::Elt* __restrict__ rows, size_t row_stride, typename F::Elt* __restrict__ x,
+__global__ void k_rs_pad(const typename F::Elt* __restrict__ rows, RsRows R, typename F::Elt* __restrict__ x,
                          uint32_t n, uint32_t N, const typename F::Elt* __restrict__ binom) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= N) return;
-  const typename F::Elt* y = rows + (size_t)blockIdx.y * row_stride;
+  const typename F::Elt* y = rows + R.at(blockIdx.y);
   x[(size_t)blockIdx.y * N + i] = i < n ? F::mul(binom[i], y[i]) : F::zero();
 }
 // y[k] = lead[k-d] * conv[k], k in [n, m); conv is stored bit-reversed or natural
 template <class F>
-__global__ void k_rs_finish(typename F::Elt* __restrict__ rows, size_t row_stride, const typename F::Elt* __restrict__ x,
+__global__ void k_rs_finish(typename F::Elt* __restrict__ rows, RsRows R, const typename F::Elt* __restrict__ x,
                             uint32_t n, uint32_t m, uint32_t N, const typename F::Elt* __restrict__ lead) {
   uint32_t k = n + blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= m) return;
-  typename F::Elt* y = rows + (size_t)blockIdx.y * row_stride;
+  typename F::Elt* y = rows + R.at(blockIdx.y);
   y[k] = F::mul(lead[k - (n - 1)], x[(size_t)blockIdx.y * N + k]);
 }
 
 // the same pad / finish steps for a real row carried in the real parts of Fp2
 // elements (P-256 rows too long for the shared-memory real-FFT kernel)
 template <class F>
-__global__ void k_rs_pad_cx(const typename F::Elt* __restrict__ rows, size_t row_stride, Cx<F>* __restrict__ x,
+__global__ void k_rs_pad_cx(const typename F::Elt* __restrict__ rows, RsRows R, Cx<F>* __restrict__ x,
                             uint32_t n, uint32_t N, const typename F::Elt* __restrict__ binom) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= N) return;
-  const typename F::Elt* y = rows + (size_t)blockIdx.y * row_stride;
+  const typename F::Elt* y = rows + R.at(blockIdx.y);
   x[(size_t)blockIdx.y * N + i] = Cx<F>{i < n ? F::mul(binom[i], y[i]) : F::zero(), F::zero()};
 }
 template <class F>
-__global__ void k_rs_finish_cx(typename F::Elt* __restrict__ rows, size_t row_stride, const Cx<F>* __restrict__ x,
+__global__ void k_rs_finish_cx(typename F::Elt* __restrict__ rows, RsRows R, const Cx<F>* __restrict__ x,
                                uint32_t n, uint32_t m, uint32_t N, const typename F::Elt* __restrict__ lead) {
   uint32_t k = n + blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= m) return;
-  typename F::Elt* y = rows + (size_t)blockIdx.y * row_stride;
+  typename F::Elt* y = rows + R.at(blockIdx.y);
   y[k] = F::mul(lead[k - (n - 1)], x[(size_t)blockIdx.y * N + k].re);
 }
 

@@ -369,10 +369,28 @@ struct lf_ctx {
   // this context's device (a process may hold contexts on several GPUs)
   uint32_t attr_mask = 0;
   std::set<const void*> fft_attr;
+  // grow-only work arrays of the large-row RS / convolution paths (stream ordered: a later call on this
+  // context's stream reuses them only after the earlier kernels are done)
+  void* work[2] = {nullptr, nullptr};
+  size_t work_cap[2] = {0, 0};
 };
 enum { kAttrRsGf = 1, kAttrRsFp = 2, kAttrScCluster = 4 };
 
 namespace lf {
+
+static const size_t kWorkChunkBytes = (size_t)2 << 30;  // rows are taken in chunks whose work array stays below this
+static int ctx_work(lf_ctx* ctx, int slot, size_t bytes, void** out) {
+  if (bytes > ctx->work_cap[slot]) {
+    LF_CUDA(cudaStreamSynchronize(ctx->stream));  // kernels of an earlier call may still use the old array
+    cudaFree(ctx->work[slot]);
+    ctx->work[slot] = nullptr;
+    ctx->work_cap[slot] = 0;
+    LF_CUDA(cudaMalloc(&ctx->work[slot], bytes));
+    ctx->work_cap[slot] = bytes;
+  }
+  *out = ctx->work[slot];
+  return 0;
+}
 
 static const int kRsGfThreads = 128;  // measured: 64 / 128 / 192 / 256 threads -> 11.77 / 11.11 / 11.84 / 11.76 ms per 1024 SHA proofs
 
@@ -422,47 +440,46 @@ static int launch_rs_gf_global(lf_ctx* ctx, gf128* d_rows, size_t row_stride, si
                                size_t nbatch, const RsPlanHost& ph) {
   const uint32_t n = ph.plan.n, m = ph.plan.m, l = ph.plan.l, fftn = ph.plan.fftn;
   gf128 *C = nullptr, *D = nullptr;
-  LF_CUDA(cudaMalloc(&C, nrows * (size_t)fftn * sizeof(gf128)));
-  if (m > fftn && cudaMalloc(&D, nrows * (size_t)fftn * sizeof(gf128)) != cudaSuccess) {
-    cudaFree(C);
-    return fail(LF_ERR_CUDA, "rs: out of device memory for the coset work array");
-  }
-  const dim3 cgrid((fftn + 255) / 256, (unsigned)nrows);
-  for (size_t bi = 0; bi < nbatch; ++bi) {
-    gf128* y = d_rows + bi * batch_stride;
-    // C = y[0..n) zero-extended; truncated transform on the first coset
-    k_rs_gf_copy<FGf128><<<cgrid, 256, 0, ctx->stream>>>(C, fftn, y, row_stride, fftn, 0, n);
-    ctx->launches++;
-    for (const RsStep& st : ph.steps) gf_gstep(ctx, C, fftn, nrows, st, 0);
-    // evaluations n..fftn of the first coset go out; C keeps the n coefficients
-    if (fftn > n) {
-      const uint32_t hi = std::min(fftn, m);
-      LF_CUDA(cudaMemcpy2DAsync(y + n, row_stride * sizeof(gf128), C + n, (size_t)fftn * sizeof(gf128),
-                                (size_t)(hi - n) * sizeof(gf128), nrows, cudaMemcpyDeviceToDevice, ctx->stream));
-    }
-    for (uint32_t b = fftn; b < m; b += fftn) {
-      k_rs_gf_copy<FGf128><<<cgrid, 256, 0, ctx->stream>>>(D, fftn, C, fftn, fftn, 0, n);
+  // rows of one batch in chunks that keep the two work arrays bounded
+  const size_t chunk = std::max<size_t>(1, std::min(nrows, kWorkChunkBytes / ((size_t)fftn * sizeof(gf128))));
+  int rc = ctx_work(ctx, 0, chunk * (size_t)fftn * sizeof(gf128), (void**)&C);
+  if (rc) return rc;
+  if (m > fftn && (rc = ctx_work(ctx, 1, chunk * (size_t)fftn * sizeof(gf128), (void**)&D))) return rc;
+  for (size_t bi = 0; bi < nbatch; ++bi)
+    for (size_t r0 = 0; r0 < nrows; r0 += chunk) {
+      const size_t nr = std::min(chunk, nrows - r0);
+      const dim3 cgrid((fftn + 255) / 256, (unsigned)nr);
+      gf128* y = d_rows + bi * batch_stride + r0 * row_stride;
+      // C = y[0..n) zero-extended; truncated transform on the first coset
+      k_rs_gf_copy<FGf128><<<cgrid, 256, 0, ctx->stream>>>(C, fftn, y, row_stride, fftn, 0, n);
       ctx->launches++;
-      for (uint32_t st = l; st-- > 0;) gf_gstep(ctx, D, fftn, nrows, RsStep{0, st, 0, 0, fftn / 2}, b);
-      const uint32_t cnt = std::min(fftn, m - b);
-      LF_CUDA(cudaMemcpy2DAsync(y + b, row_stride * sizeof(gf128), D, (size_t)fftn * sizeof(gf128),
-                                (size_t)cnt * sizeof(gf128), nrows, cudaMemcpyDeviceToDevice, ctx->stream));
+      for (const RsStep& st : ph.steps) gf_gstep(ctx, C, fftn, nr, st, 0);
+      // evaluations n..fftn of the first coset go out; C keeps the n coefficients
+      if (fftn > n) {
+        const uint32_t hi = std::min(fftn, m);
+        LF_CUDA(cudaMemcpy2DAsync(y + n, row_stride * sizeof(gf128), C + n, (size_t)fftn * sizeof(gf128),
+                                  (size_t)(hi - n) * sizeof(gf128), nr, cudaMemcpyDeviceToDevice, ctx->stream));
+      }
+      for (uint32_t b = fftn; b < m; b += fftn) {
+        k_rs_gf_copy<FGf128><<<cgrid, 256, 0, ctx->stream>>>(D, fftn, C, fftn, fftn, 0, n);
+        ctx->launches++;
+        for (uint32_t st = l; st-- > 0;) gf_gstep(ctx, D, fftn, nr, RsStep{0, st, 0, 0, fftn / 2}, b);
+        const uint32_t cnt = std::min(fftn, m - b);
+        LF_CUDA(cudaMemcpy2DAsync(y + b, row_stride * sizeof(gf128), D, (size_t)fftn * sizeof(gf128),
+                                  (size_t)cnt * sizeof(gf128), nr, cudaMemcpyDeviceToDevice, ctx->stream));
+      }
     }
-  }
   LF_CUDA(cudaGetLastError());
-  LF_CUDA(cudaStreamSynchronize(ctx->stream));
-  cudaFree(C);
-  if (D) cudaFree(D);
   return 0;
 }
 
 // LCH14::FFT(l, coset, B) / IFFT (lch14.h:106-146) on one device array of 2^l elements
-static int launch_lch14_fft(lf_ctx* ctx, gf128* d, uint32_t l, uint32_t coset, bool forward) {
+static int launch_lch14_fft(lf_ctx* ctx, gf128* d, uint32_t l, uint32_t coset, bool forward, size_t nrows = 1) {
   const uint32_t n = 1u << l;
   if (forward) {
-    for (uint32_t st = l; st-- > 0;) gf_gstep(ctx, d, n, 1, RsStep{0, st, 0, 0, n / 2}, coset);
+    for (uint32_t st = l; st-- > 0;) gf_gstep(ctx, d, n, nrows, RsStep{0, st, 0, 0, n / 2}, coset);
   } else {
-    for (uint32_t st = 0; st < l; ++st) gf_gstep(ctx, d, n, 1, RsStep{1, st, 0, 0, n / 2}, coset);
+    for (uint32_t st = 0; st < l; ++st) gf_gstep(ctx, d, n, nrows, RsStep{1, st, 0, 0, n / 2}, coset);
   }
   LF_CUDA(cudaGetLastError());
   return 0;
@@ -598,18 +615,13 @@ static int ctx_rs_fp_tables(lf_ctx* ctx, size_t n, size_t m, RsFpTables** out) {
   return 0;
 }
 
-static int rs_conv_run_p256(lf_ctx* ctx, fpw<8>* d_rows, size_t row_stride, size_t nrows, size_t n, size_t m);
+static int rs_conv_run_p256(lf_ctx* ctx, fpw<8>* d_rows, size_t row_stride, size_t nrows, size_t batch_stride,
+                            size_t nbatch, size_t n, size_t m);
 static int launch_rs_p256(lf_ctx* ctx, fpw<8>* d_rows, size_t row_stride, size_t nrows, size_t batch_stride,
                           size_t nbatch, size_t n, size_t m) {
   if (n == 0 || m < n || m > (1u << 24)) return fail(LF_ERR_ARG, "rs: need 0 < n <= m <= 2^24");
   if (nrows == 0 || nbatch == 0 || m == n) return 0;
-  if (m > 6400) {
-    for (size_t bi = 0; bi < nbatch; ++bi) {
-      int rc2 = rs_conv_run_p256(ctx, d_rows + bi * batch_stride, row_stride, nrows, n, m);
-      if (rc2) return rc2;
-    }
-    return 0;
-  }
+  if (m > 6400) return rs_conv_run_p256(ctx, d_rows, row_stride, nrows, batch_stride, nbatch, n, m);
   RsFpTables* t;
   int rc = ctx_rs_fp_tables(ctx, n, m, &t);
   if (rc) return rc;
@@ -732,12 +744,12 @@ struct RsConvTables {
   void *d_yh = nullptr, *d_lead = nullptr, *d_binom = nullptr;
 };
 template <class F, class H>
-static int rs_conv_run(lf_ctx* ctx, const H& Hf, typename F::Elt* d_rows, size_t row_stride, size_t nrows, size_t n,
-                       size_t m) {
+static int rs_conv_run(lf_ctx* ctx, const H& Hf, typename F::Elt* d_rows, size_t row_stride, size_t nrows,
+                       size_t batch_stride, size_t nbatch, size_t n, size_t m) {
   typedef typename F::Elt Elt;
   typedef AlgF<F> A;
   if (n == 0 || m < n) return fail(LF_ERR_ARG, "rs: need 0 < n <= m");
-  if (nrows == 0 || m == n) return 0;
+  if (nrows == 0 || nbatch == 0 || m == n) return 0;
   uint32_t logN = 0;
   while (((size_t)1 << logN) < m) ++logN;
   const size_t N = (size_t)1 << logN;
@@ -774,25 +786,31 @@ static int rs_conv_run(lf_ctx* ctx, const H& Hf, typename F::Elt* d_rows, size_t
     it = ctx->rs_conv.emplace(key, (void*)t).first;
   }
   auto* t = (RsConvTables*)it->second;
+  // all rows of all batches, in chunks whose work array stays bounded; asynchronous on the context's stream
+  const size_t total = nrows * nbatch;
+  const size_t chunk = std::max<size_t>(1, std::min(total, kWorkChunkBytes / (N * sizeof(Elt))));
   Elt* x;
-  LF_CUDA(cudaMalloc(&x, nrows * N * sizeof(Elt)));
-  k_rs_pad<F><<<dim3((unsigned)((N + 255) / 256), (unsigned)nrows), 256, 0, ctx->stream>>>(
-      d_rows, row_stride, x, (uint32_t)n, (uint32_t)N, (const Elt*)t->d_binom);
-  ctx->launches++;
-  if ((rc = fft_run<A>(ctx, x, N, nrows, logN, d_tw, true, true, false)) == 0) {
-    k_fft_pointwise<A><<<dim3((unsigned)((N + 255) / 256), (unsigned)nrows), 256, 0, ctx->stream>>>(
-        x, (const Elt*)t->d_yh, N);
+  if ((rc = ctx_work(ctx, 0, chunk * N * sizeof(Elt), (void**)&x))) return rc;
+  for (size_t r0 = 0; r0 < total && rc == 0; r0 += chunk) {
+    const size_t nr = std::min(chunk, total - r0);
+    const RsRows R{row_stride, batch_stride, (uint32_t)nrows, (uint32_t)r0};
+    k_rs_pad<F><<<dim3((unsigned)((N + 255) / 256), (unsigned)nr), 256, 0, ctx->stream>>>(
+        d_rows, R, x, (uint32_t)n, (uint32_t)N, (const Elt*)t->d_binom);
     ctx->launches++;
-    rc = fft_run<A>(ctx, x, N, nrows, logN, d_tw, false, false, false);
+    if ((rc = fft_run<A>(ctx, x, N, nr, logN, d_tw, true, true, false)) == 0) {
+      k_fft_pointwise<A><<<dim3((unsigned)((N + 255) / 256), (unsigned)nr), 256, 0, ctx->stream>>>(
+          x, (const Elt*)t->d_yh, N);
+      ctx->launches++;
+      rc = fft_run<A>(ctx, x, N, nr, logN, d_tw, false, false, false);
+    }
+    if (rc == 0) {
+      k_rs_finish<F><<<dim3((unsigned)((m - n + 255) / 256), (unsigned)nr), 256, 0, ctx->stream>>>(
+          d_rows, R, x, (uint32_t)n, (uint32_t)m, (uint32_t)N, (const Elt*)t->d_lead);
+      ctx->launches++;
+      cudaError_t ce = cudaGetLastError();
+      if (ce != cudaSuccess) rc = fail(LF_ERR_CUDA, cudaGetErrorString(ce));
+    }
   }
-  if (rc == 0) {
-    k_rs_finish<F><<<dim3((unsigned)((m - n + 255) / 256), (unsigned)nrows), 256, 0, ctx->stream>>>(
-        d_rows, row_stride, x, (uint32_t)n, (uint32_t)m, (uint32_t)N, (const Elt*)t->d_lead);
-    ctx->launches++;
-    cudaError_t ce = cudaStreamSynchronize(ctx->stream);
-    if (ce != cudaSuccess) rc = fail(LF_ERR_CUDA, cudaGetErrorString(ce));
-  }
-  cudaFree(x);
   return rc;
 }
 
@@ -800,7 +818,8 @@ static int rs_conv_run(lf_ctx* ctx, const H& Hf, typename F::Elt* d_rows, size_t
 // row embedded in Fp2 (imaginary parts zero) and global-memory stage-group FFTs
 // over Fp2 (FFTExtConvolution, lib/algebra/convolution.h:128-191; exact, so the
 // real part of the result is the convolution).
-static int rs_conv_run_p256(lf_ctx* ctx, fpw<8>* d_rows, size_t row_stride, size_t nrows, size_t n, size_t m) {
+static int rs_conv_run_p256(lf_ctx* ctx, fpw<8>* d_rows, size_t row_stride, size_t nrows, size_t batch_stride,
+                            size_t nbatch, size_t n, size_t m) {
   typedef FFp256 F;
   typedef AlgCx<F> A;
   typedef Cx<F> CxE;
@@ -835,25 +854,30 @@ static int rs_conv_run_p256(lf_ctx* ctx, fpw<8>* d_rows, size_t row_stride, size
     it = ctx->rs_conv.emplace(key, (void*)t).first;
   }
   auto* t = (RsConvTables*)it->second;
+  const size_t total = nrows * nbatch;
+  const size_t chunk = std::max<size_t>(1, std::min(total, kWorkChunkBytes / (N * sizeof(CxE))));
   CxE* x;
-  LF_CUDA(cudaMalloc(&x, nrows * N * sizeof(CxE)));
-  k_rs_pad_cx<F><<<dim3((unsigned)((N + 255) / 256), (unsigned)nrows), 256, 0, ctx->stream>>>(
-      d_rows, row_stride, x, (uint32_t)n, (uint32_t)N, (const fpw<8>*)t->d_binom);
-  ctx->launches++;
-  if ((rc = fft_run<A>(ctx, x, N, nrows, logN, d_tw, true, true, false)) == 0) {
-    k_fft_pointwise<A><<<dim3((unsigned)((N + 255) / 256), (unsigned)nrows), 256, 0, ctx->stream>>>(
-        x, (const CxE*)t->d_yh, N);
+  if ((rc = ctx_work(ctx, 0, chunk * N * sizeof(CxE), (void**)&x))) return rc;
+  for (size_t r0 = 0; r0 < total && rc == 0; r0 += chunk) {
+    const size_t nr = std::min(chunk, total - r0);
+    const RsRows R{row_stride, batch_stride, (uint32_t)nrows, (uint32_t)r0};
+    k_rs_pad_cx<F><<<dim3((unsigned)((N + 255) / 256), (unsigned)nr), 256, 0, ctx->stream>>>(
+        d_rows, R, x, (uint32_t)n, (uint32_t)N, (const fpw<8>*)t->d_binom);
     ctx->launches++;
-    rc = fft_run<A>(ctx, x, N, nrows, logN, d_tw, false, false, false);
+    if ((rc = fft_run<A>(ctx, x, N, nr, logN, d_tw, true, true, false)) == 0) {
+      k_fft_pointwise<A><<<dim3((unsigned)((N + 255) / 256), (unsigned)nr), 256, 0, ctx->stream>>>(
+          x, (const CxE*)t->d_yh, N);
+      ctx->launches++;
+      rc = fft_run<A>(ctx, x, N, nr, logN, d_tw, false, false, false);
+    }
+    if (rc == 0) {
+      k_rs_finish_cx<F><<<dim3((unsigned)((m - n + 255) / 256), (unsigned)nr), 256, 0, ctx->stream>>>(
+          d_rows, R, x, (uint32_t)n, (uint32_t)m, (uint32_t)N, (const fpw<8>*)t->d_lead);
+      ctx->launches++;
+      cudaError_t ce = cudaGetLastError();
+      if (ce != cudaSuccess) rc = fail(LF_ERR_CUDA, cudaGetErrorString(ce));
+    }
   }
-  if (rc == 0) {
-    k_rs_finish_cx<F><<<dim3((unsigned)((m - n + 255) / 256), (unsigned)nrows), 256, 0, ctx->stream>>>(
-        d_rows, row_stride, x, (uint32_t)n, (uint32_t)m, (uint32_t)N, (const fpw<8>*)t->d_lead);
-    ctx->launches++;
-    cudaError_t ce = cudaStreamSynchronize(ctx->stream);
-    if (ce != cudaSuccess) rc = fail(LF_ERR_CUDA, cudaGetErrorString(ce));
-  }
-  cudaFree(x);
   return rc;
 }
 
@@ -875,20 +899,17 @@ int launch_rs<FFp256>(lf_ctx* ctx, fpw<8>* d_rows, size_t row_stride, size_t nro
 template <>
 int launch_rs<FFpBn254>(lf_ctx* ctx, fpw<8>* d_rows, size_t row_stride, size_t nrows, size_t batch_stride,
                         size_t nbatch, size_t n, size_t m) {
-  if (nbatch != 1) return fail(LF_ERR_UNSUPPORTED, "rs: batches over this field are not built");
-  return rs_conv_run<FFpBn254>(ctx, bn254_host(), d_rows, row_stride, nrows, n, m);
+  return rs_conv_run<FFpBn254>(ctx, bn254_host(), d_rows, row_stride, nrows, batch_stride, nbatch, n, m);
 }
 template <>
 int launch_rs<FFp128>(lf_ctx* ctx, fpw<4>* d_rows, size_t row_stride, size_t nrows, size_t batch_stride,
                       size_t nbatch, size_t n, size_t m) {
-  if (nbatch != 1) return fail(LF_ERR_UNSUPPORTED, "rs: batches over this field are not built");
-  return rs_conv_run<FFp128>(ctx, fp128_host(), d_rows, row_stride, nrows, n, m);
+  return rs_conv_run<FFp128>(ctx, fp128_host(), d_rows, row_stride, nrows, batch_stride, nbatch, n, m);
 }
 template <>
 int launch_rs<FFpGold>(lf_ctx* ctx, fpw<2>* d_rows, size_t row_stride, size_t nrows, size_t batch_stride,
                        size_t nbatch, size_t n, size_t m) {
-  if (nbatch != 1) return fail(LF_ERR_UNSUPPORTED, "rs: batches over this field are not built");
-  return rs_conv_run<FFpGold>(ctx, gold_host(), d_rows, row_stride, nrows, n, m);
+  return rs_conv_run<FFpGold>(ctx, gold_host(), d_rows, row_stride, nrows, batch_stride, nbatch, n, m);
 }
 
 template <class F>
@@ -1041,6 +1062,8 @@ void lf_ctx_destroy(lf_ctx* ctx) {
     cudaFree(kv.second.d_yh);
   }
   cudaFree(ctx->d_tw);
+  cudaFree(ctx->work[0]);
+  cudaFree(ctx->work[1]);
   if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -1226,7 +1249,8 @@ int lf_merkle_commit(lf_ctx* ctx, int field_id, size_t nrow, size_t block_enc, s
 
 namespace {
 template <class F, class H>
-int fft_scalar_t(lf_ctx* ctx, const H& Hf, void* elts, size_t n, uint32_t logn, int forward, int reps, double* ms) {
+int fft_scalar_t(lf_ctx* ctx, const H& Hf, void* elts, size_t n, uint32_t logn, int forward, int reps, double* ms,
+                 size_t nrows = 1) {
   typedef typename F::Elt Elt;
   Elt* d = nullptr;
   Elt* d_tw;
@@ -1235,15 +1259,15 @@ int fft_scalar_t(lf_ctx* ctx, const H& Hf, void* elts, size_t n, uint32_t logn, 
   if (elts) {
     rc = upload_elts<F>(ctx, elts, n, &d);
   } else {
-    LF_CUDA(cudaMalloc(&d, n * sizeof(Elt)));
-    LF_CUDA(cudaMemsetAsync(d, 0x5a, n * sizeof(Elt), ctx->stream));  // timing only: any limbs do
+    LF_CUDA(cudaMalloc(&d, nrows * n * sizeof(Elt)));
+    LF_CUDA(cudaMemsetAsync(d, 0x11, nrows * n * sizeof(Elt), ctx->stream));  // timing only: any limbs do
   }
   if (rc) return rc;
   cudaEvent_t e0, e1;
   LF_CUDA(cudaEventCreate(&e0));
   LF_CUDA(cudaEventCreate(&e1));
   LF_CUDA(cudaEventRecord(e0, ctx->stream));
-  for (int r = 0; r < reps && !rc; ++r) rc = fft_run<AlgF<F>>(ctx, d, 0, 1, logn, d_tw, forward != 0, false, true);
+  for (int r = 0; r < reps && !rc; ++r) rc = fft_run<AlgF<F>>(ctx, d, n, nrows, logn, d_tw, forward != 0, false, true);
   LF_CUDA(cudaEventRecord(e1, ctx->stream));
   LF_CUDA(cudaEventSynchronize(e1));
   if (ms) {
@@ -1257,7 +1281,7 @@ int fft_scalar_t(lf_ctx* ctx, const H& Hf, void* elts, size_t n, uint32_t logn, 
   cudaFree(d);
   return rc;
 }
-int fft_p256_t(lf_ctx* ctx, void* elts, size_t n, uint32_t logn, int forward, int reps, double* ms) {
+int fft_p256_t(lf_ctx* ctx, void* elts, size_t n, uint32_t logn, int forward, int reps, double* ms, size_t nrows = 1) {
   typedef FFp256 F;
   fpw<8>* d = nullptr;
   Cx<F>* d_tw;
@@ -1266,8 +1290,8 @@ int fft_p256_t(lf_ctx* ctx, void* elts, size_t n, uint32_t logn, int forward, in
   if (elts) {
     rc = upload_elts<F>(ctx, elts, 2 * n, &d);  // (re, im) pairs
   } else {
-    LF_CUDA(cudaMalloc(&d, 2 * n * sizeof(fpw<8>)));
-    LF_CUDA(cudaMemsetAsync(d, 0x5a, 2 * n * sizeof(fpw<8>), ctx->stream));
+    LF_CUDA(cudaMalloc(&d, nrows * 2 * n * sizeof(fpw<8>)));
+    LF_CUDA(cudaMemsetAsync(d, 0x5a, nrows * 2 * n * sizeof(fpw<8>), ctx->stream));
   }
   if (rc) return rc;
   cudaEvent_t e0, e1;
@@ -1275,7 +1299,7 @@ int fft_p256_t(lf_ctx* ctx, void* elts, size_t n, uint32_t logn, int forward, in
   LF_CUDA(cudaEventCreate(&e1));
   LF_CUDA(cudaEventRecord(e0, ctx->stream));
   for (int r = 0; r < reps && !rc; ++r)
-    rc = fft_run<AlgCx<F>>(ctx, (Cx<F>*)d, 0, 1, logn, d_tw, forward != 0, false, true);
+    rc = fft_run<AlgCx<F>>(ctx, (Cx<F>*)d, n, nrows, logn, d_tw, forward != 0, false, true);
   LF_CUDA(cudaEventRecord(e1, ctx->stream));
   LF_CUDA(cudaEventSynchronize(e1));
   if (ms) {
@@ -1291,21 +1315,21 @@ int fft_p256_t(lf_ctx* ctx, void* elts, size_t n, uint32_t logn, int forward, in
 }
 // GF(2^128): the additive FFT of LCH14 on the span of beta_0..beta_{l-1}, coset 0
 // (lch14.h:106-146): forward = evaluate the novel-basis coefficients, else IFFT
-int fft_gf_t(lf_ctx* ctx, void* elts, size_t n, uint32_t logn, int forward, int reps, double* ms) {
+int fft_gf_t(lf_ctx* ctx, void* elts, size_t n, uint32_t logn, int forward, int reps, double* ms, size_t nrows = 1) {
   if (logn > 16) return fail(LF_ERR_ARG, "fft: the LCH14 subspace has dimension 16 (lch14.h:45-47), n <= 65536");
   gf128* d = nullptr;
-  LF_CUDA(cudaMalloc(&d, n * sizeof(gf128)));
+  LF_CUDA(cudaMalloc(&d, nrows * n * sizeof(gf128)));
   if (elts) {
     LF_CUDA(cudaMemcpyAsync(d, elts, n * sizeof(gf128), cudaMemcpyHostToDevice, ctx->stream));
   } else {
-    LF_CUDA(cudaMemsetAsync(d, 0x5a, n * sizeof(gf128), ctx->stream));
+    LF_CUDA(cudaMemsetAsync(d, 0x5a, nrows * n * sizeof(gf128), ctx->stream));
   }
   cudaEvent_t e0, e1;
   LF_CUDA(cudaEventCreate(&e0));
   LF_CUDA(cudaEventCreate(&e1));
   LF_CUDA(cudaEventRecord(e0, ctx->stream));
   int rc = 0;
-  for (int r = 0; r < reps && !rc; ++r) rc = launch_lch14_fft(ctx, d, logn, 0, forward != 0);
+  for (int r = 0; r < reps && !rc; ++r) rc = launch_lch14_fft(ctx, d, logn, 0, forward != 0, nrows);
   LF_CUDA(cudaEventRecord(e1, ctx->stream));
   LF_CUDA(cudaEventSynchronize(e1));
   if (ms) {
@@ -1322,17 +1346,17 @@ int fft_gf_t(lf_ctx* ctx, void* elts, size_t n, uint32_t logn, int forward, int 
   cudaFree(d);
   return rc;
 }
-int fft_dispatch(lf_ctx* ctx, int field_id, void* elts, size_t n, int forward, int reps, double* ms) {
+int fft_dispatch(lf_ctx* ctx, int field_id, void* elts, size_t n, int forward, int reps, double* ms, size_t nrows = 1) {
   if (n == 0 || (n & (n - 1))) return fail(LF_ERR_ARG, "fft: n must be a power of two");
   uint32_t logn = 0;
   while (((size_t)1 << logn) < n) ++logn;
   if (logn > 26) return fail(LF_ERR_ARG, "fft: n too large");
   switch (field_id) {
-    case LF_FIELD_BN254: return fft_scalar_t<FFpBn254>(ctx, bn254_host(), elts, n, logn, forward, reps, ms);
-    case LF_FIELD_FP128: return fft_scalar_t<FFp128>(ctx, fp128_host(), elts, n, logn, forward, reps, ms);
-    case LF_FIELD_GOLDILOCKS: return fft_scalar_t<FFpGold>(ctx, gold_host(), elts, n, logn, forward, reps, ms);
-    case LF_FIELD_P256: return fft_p256_t(ctx, elts, n, logn, forward, reps, ms);
-    case LF_FIELD_GF2_128: return fft_gf_t(ctx, elts, n, logn, forward, reps, ms);
+    case LF_FIELD_BN254: return fft_scalar_t<FFpBn254>(ctx, bn254_host(), elts, n, logn, forward, reps, ms, nrows);
+    case LF_FIELD_FP128: return fft_scalar_t<FFp128>(ctx, fp128_host(), elts, n, logn, forward, reps, ms, nrows);
+    case LF_FIELD_GOLDILOCKS: return fft_scalar_t<FFpGold>(ctx, gold_host(), elts, n, logn, forward, reps, ms, nrows);
+    case LF_FIELD_P256: return fft_p256_t(ctx, elts, n, logn, forward, reps, ms, nrows);
+    case LF_FIELD_GF2_128: return fft_gf_t(ctx, elts, n, logn, forward, reps, ms, nrows);
     default: return fail(LF_ERR_UNSUPPORTED, "fft: unknown field");
   }
 }
@@ -1352,6 +1376,49 @@ int lf_fft_time(lf_ctx* ctx, int field_id, size_t n, int reps, double* ms_per_ff
   int rc = fft_dispatch(ctx, field_id, nullptr, n, 0, 1, nullptr);  // warm-up (tables, attributes)
   if (rc) return rc;
   return fft_dispatch(ctx, field_id, nullptr, n, 0, reps, ms_per_fft);
+}
+
+int lf_fft_time_rows(lf_ctx* ctx, int field_id, size_t n, size_t nrows, int reps, double* ms_per_call) {
+  if (!ctx || !ms_per_call || reps <= 0 || nrows == 0) return fail(LF_ERR_ARG, "lf_fft_time_rows: bad argument");
+  LF_CUDA(cudaSetDevice(ctx->device));
+  int rc = fft_dispatch(ctx, field_id, nullptr, n, 0, 1, nullptr, nrows);
+  if (rc) return rc;
+  return fft_dispatch(ctx, field_id, nullptr, n, 0, reps, ms_per_call, nrows);
+}
+
+}  // extern "C"
+namespace {
+template <class F>
+int rs_time_t(lf_ctx* ctx, size_t n, size_t m, size_t nrows, int reps, double* ms) {
+  typedef typename F::Elt Elt;
+  Elt* d = nullptr;
+  LF_CUDA(cudaMalloc(&d, nrows * m * sizeof(Elt)));
+  LF_CUDA(cudaMemsetAsync(d, 0x11, nrows * m * sizeof(Elt), ctx->stream));  // timing only: any limbs do
+  int rc = launch_rs<F>(ctx, d, m, nrows, 0, 1, n, m);                       // warm-up (tables, attributes)
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  cudaEventRecord(e0, ctx->stream);
+  for (int r = 0; r < reps && !rc; ++r) rc = launch_rs<F>(ctx, d, m, nrows, 0, 1, n, m);
+  cudaEventRecord(e1, ctx->stream);
+  cudaError_t ce = cudaEventSynchronize(e1);
+  if (!rc && ce != cudaSuccess) rc = fail(LF_ERR_CUDA, cudaGetErrorString(ce));
+  float t = 0;
+  cudaEventElapsedTime(&t, e0, e1);
+  *ms = t / reps;
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(d);
+  return rc;
+}
+}  // namespace
+extern "C" {
+
+int lf_rs_time(lf_ctx* ctx, int field_id, size_t n, size_t m, size_t nrows, int reps, double* ms_per_call) {
+  if (!ctx || !ms_per_call || reps <= 0 || nrows == 0 || n == 0 || m < n)
+    return fail(LF_ERR_ARG, "lf_rs_time: bad argument");
+  LF_CUDA(cudaSetDevice(ctx->device));
+  LF_DISPATCH_FIELD(field_id, rs_time_t<F>(ctx, n, m, nrows, reps, ms_per_call));
 }
 
 }  // extern "C"

@@ -65,7 +65,7 @@ constexpr uint32_t kFlatHeavyRow = 48;     // entries of one row a pair thread s
 constexpr uint32_t kFlatHeavyChunk = 256;  // entries per heavy-row warp chunk
 constexpr uint32_t kFlatEvalWarps = 4;     // warps per CTA of k_sc_eval
 constexpr uint32_t kFlatEvalMinCta = 5;    // resident CTAs per SM the kernel is compiled for (register cap)
-constexpr uint32_t kFlatMaxBins = 32;      // warps (bins of work) per proof of k_sc_eval; k_sc_round adds their partials
+constexpr uint32_t kFlatMaxBins = 128;     // warps (bins of work) per proof of k_sc_eval; k_sc_round adds their partials
 constexpr uint32_t kFlatBinCost = 8;       // smallest bin worth a warp, in multiplications per lane
 constexpr uint32_t kFlatNone = 0xffffffffu;
 

@@ -292,6 +292,18 @@ void ref_lch14_interpolate(size_t n, size_t m, uint8_t* rows, size_t nrows) {
   }
 }
 
+// seconds per LCH14ReedSolomon(n, m)::interpolate of one row on one thread (BM_ReedSolomon_gf128)
+double ref_lch14_rs_bench(size_t n, size_t m, int reps) {
+  const GF& F = gf();
+  LCH14ReedSolomon<GF> rs(n, m, F);
+  std::vector<GF::Elt> v(m);
+  for (size_t i = 0; i < n; ++i) v[i] = F.of_scalar(i + 1);
+  rs.interpolate(v.data());
+  auto t0 = std::chrono::steady_clock::now();
+  for (int r = 0; r < reps; ++r) rs.interpolate(v.data());
+  return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() / reps;
+}
+
 // ---------------- Merkle ----------------
 // merkle/merkle_tree.h:100-151 ; leaves: n x 32 ; nodes_out: 2n x 32 (heap)
 void ref_merkle_build(size_t n, const uint8_t* leaves, uint8_t* nodes_out,

@@ -3,6 +3,7 @@
 // (algebra/fft.h:185-201), ReedSolomon::interpolate (algebra/reed_solomon.h:93-110)
 // over the fields of BASELINE config 1 (algebra/fft_test.cc:33-44,168-172,
 // algebra/reed_solomon_test.cc:337-401).
+#include <chrono>
 #include <cstdint>
 #include <cstring>
 #include <vector>
@@ -68,6 +69,33 @@ void rs_t(const Field& F, const StaticString omega_s, uint64_t order, uint8_t* r
     for (size_t i = 0; i < m; ++i) F.to_bytes_field(p + i * Field::kBytes, y[i]);
   }
 }
+// timing of the same two calls on one host thread (the reference's BM_FFT_* / BM_ReedSolomon* bodies,
+// algebra/fft_test.cc:185-251, algebra/reed_solomon_test.cc:337-401): seconds per call, data prepared outside
+template <class Field>
+double fft_bench_t(const Field& F, const StaticString omega_s, uint64_t order, size_t n, int reps) {
+  using Elt = typename Field::Elt;
+  Elt omega = F.of_string(omega_s);
+  std::vector<Elt> A(n);
+  for (size_t i = 0; i < n; ++i) A[i] = F.of_scalar(i * 2654435761u + 1);
+  FFT<Field>::fftb(A.data(), n, omega, order, F);
+  auto t0 = std::chrono::steady_clock::now();
+  for (int r = 0; r < reps; ++r) FFT<Field>::fftb(A.data(), n, omega, order, F);
+  return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() / reps;
+}
+template <class Field>
+double rs_bench_t(const Field& F, const StaticString omega_s, uint64_t order, size_t n, size_t m, int reps) {
+  using Elt = typename Field::Elt;
+  using Conv = FFTConvolutionFactory<Field>;
+  Elt omega = F.of_string(omega_s);
+  Conv conv(F, omega, order);
+  ReedSolomon<Field, Conv> rs(n, m, F, conv);
+  std::vector<Elt> y(m);
+  for (size_t i = 0; i < n; ++i) y[i] = F.of_scalar(i * 2654435761u + 1);
+  rs.interpolate(y.data());
+  auto t0 = std::chrono::steady_clock::now();
+  for (int r = 0; r < reps; ++r) rs.interpolate(y.data());
+  return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() / reps;
+}
 const char kBnOmega[] =
     "1910321906792171394429139282769207003614565195732928631530564200482146216"
     "1904";
@@ -130,6 +158,47 @@ int ref_rs(int fid, uint8_t* rows, size_t n, size_t m, size_t nrows) {
     }
   } else return -1;
   return 0;
+}
+// seconds per FFT<Field>::fftb of n points on one thread (fid 1: Fp2 over P-256, BM_FFT_Fp256_2)
+double ref_fft_bench(int fid, size_t n, int reps) {
+  if (fid == 100) return fft_bench_t(bn(), StaticString(kBnOmega), 1ull << 28, n, reps);
+  if (fid == 101) return fft_bench_t(f128(), StaticString(kF128Omega), 1ull << 32, n, reps);
+  if (fid == 102) return fft_bench_t(gold(), StaticString(kGoldOmega), 1ull << 32, n, reps);
+  if (fid == 1) {
+    using F2 = Fp2<Fp256Base>;
+    static const F2 f2(p256_base);
+    auto omega = f2.of_string(kRootX, kRootY);
+    std::vector<F2::Elt> A(n);
+    for (size_t i = 0; i < n; ++i) {
+      A[i].re = p256_base.of_scalar(i * 2654435761u + 1);
+      A[i].im = p256_base.of_scalar(i + 7);
+    }
+    FFT<F2>::fftb(A.data(), n, omega, 1ull << 31, f2);
+    auto t0 = std::chrono::steady_clock::now();
+    for (int r = 0; r < reps; ++r) FFT<F2>::fftb(A.data(), n, omega, 1ull << 31, f2);
+    return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() / reps;
+  }
+  return -1;
+}
+// seconds per ReedSolomon(n, m)::interpolate of one row on one thread (BM_ReedSolomonFp*)
+double ref_rs_bench(int fid, size_t n, size_t m, int reps) {
+  if (fid == 100) return rs_bench_t(bn(), StaticString(kBnOmega), 1ull << 28, n, m, reps);
+  if (fid == 101) return rs_bench_t(f128(), StaticString(kF128Omega), 1ull << 32, n, m, reps);
+  if (fid == 102) return rs_bench_t(gold(), StaticString(kGoldOmega), 1ull << 32, n, m, reps);
+  if (fid == 1) {
+    using F2 = Fp2<Fp256Base>;
+    using Conv = FFTExtConvolutionFactory<Fp256Base, F2>;
+    static const F2 f2(p256_base);
+    static const Conv conv(p256_base, f2, f2.of_string(kRootX, kRootY), 1ull << 31);
+    ReedSolomon<Fp256Base, Conv> rs(n, m, p256_base, conv);
+    std::vector<Fp256Base::Elt> y(m);
+    for (size_t i = 0; i < n; ++i) y[i] = p256_base.of_scalar(i * 2654435761u + 1);
+    rs.interpolate(y.data());
+    auto t0 = std::chrono::steady_clock::now();
+    for (int r = 0; r < reps; ++r) rs.interpolate(y.data());
+    return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() / reps;
+  }
+  return -1;
 }
 // elementwise Montgomery-domain-free multiply in byte encoding
 int ref_fp_mul(int fid, const uint8_t* a, const uint8_t* b, uint8_t* out, size_t n) {

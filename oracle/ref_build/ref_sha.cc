@@ -33,5 +33,42 @@ int ref_sha_circuit(size_t nblocks, uint8_t** circ, size_t* circ_len,
   for (size_t i = 0; i < c->ninputs; ++i) Fs.to_bytes_field(*wit + i * F::kBytes, W.v_[i]);
   return 0;
 }
+// The witness of the nblocks-block circuit for an arbitrary message (fill_input's steps,
+// flatsha256_circuit_test.cc:415-468, with the message and its SHA-256 supplied by the caller instead
+// of the benchmark's "aaa..." strings).  msg must pad to exactly nblocks blocks; wit = ninputs x 16 bytes.
+int ref_sha_witness(size_t nblocks, const uint8_t* msg, size_t len, const uint8_t hash[32], uint8_t* wit,
+                    size_t wit_cap) {
+  using namespace proofs;
+  using F = GF2_128<>;
+  static const F Fs;
+  if ((len + 9 + 63) / 64 != nblocks) return -1;
+  uint8_t numb;
+  std::vector<uint8_t> inb(64 * nblocks);
+  std::vector<FlatSHA256Witness::BlockWitness> bwb(nblocks);
+  FlatSHA256Witness::transform_and_witness_message(len, msg, nblocks, numb, &inb[0], &bwb[0]);
+  std::vector<F::Elt> W;
+  auto bit = [&](bool b) { W.push_back(b ? Fs.one() : Fs.zero()); };
+  W.push_back(Fs.one());
+  for (size_t i = 0; i < 8; ++i) bit((numb >> i) & 1);
+  for (size_t j = 0; j < nblocks * 64; ++j)
+    for (size_t i = 0; i < 8; ++i) bit((inb[j] >> i) & 1);
+  for (size_t j = 0; j < 256; ++j) bit((hash[(255 - j) / 8] >> (j % 8)) & 1);
+  BitPluckerEncoder<F, 2> BPENC(Fs);
+  auto pk = [&](uint32_t v) {
+    auto a = BPENC.mkpacked_v32(v);
+    for (auto& e : a) W.push_back(e);
+  };
+  for (size_t j = 0; j < nblocks; ++j) {
+    for (size_t k = 0; k < 48; ++k) pk(bwb[j].outw[k]);
+    for (size_t k = 0; k < 64; ++k) {
+      pk(bwb[j].oute[k]);
+      pk(bwb[j].outa[k]);
+    }
+    for (size_t k = 0; k < 8; ++k) pk(bwb[j].h1[k]);
+  }
+  if (W.size() * F::kBytes > wit_cap) return -2;
+  for (size_t i = 0; i < W.size(); ++i) Fs.to_bytes_field(wit + i * F::kBytes, W[i]);
+  return (int)W.size();
+}
 void ref_free(void* p) { free(p); }
 }

@@ -207,6 +207,30 @@ def ecdsa_circuit(nsigs=1):
     return _take(lib().ref_ecdsa_circuit, C.c_size_t(nsigs))
 
 
+def sha_witness(nblocks, msg):
+    """witness of the nblocks-block SHA-256 circuit for `msg` (reference witness generator)"""
+    import hashlib
+    out = np.zeros(1 << 24, np.uint8)
+    n = lib().ref_sha_witness(C.c_size_t(nblocks), C.c_char_p(msg), C.c_size_t(len(msg)),
+                              C.c_char_p(hashlib.sha256(msg).digest()), _p(out), C.c_size_t(out.size))
+    if n < 0:
+        raise ValueError(f"ref_sha_witness failed: {n}")
+    return out[:n * 16].tobytes()
+
+
+def ecdsa_ntests():
+    return int(lib().ref_ecdsa_ntests())
+
+
+def ecdsa_witness(nsigs, first):
+    """witness of the nsigs-signature ECDSA circuit from the reference's test vectors P256_TEST[first ...]"""
+    out = np.zeros(1 << 22, np.uint8)
+    n = lib().ref_ecdsa_witness(C.c_size_t(nsigs), C.c_size_t(first), _p(out), C.c_size_t(out.size))
+    if n < 0:
+        raise ValueError(f"ref_ecdsa_witness failed: {n}")
+    return out[:n * 32].tobytes()
+
+
 class Circuit:
     def __init__(self, field_id, circ_bytes):
         self.field_id = field_id
@@ -399,6 +423,24 @@ def rs(fid, rows, n, m):
     nrows = rows.shape[0]
     assert lib().ref_rs(C.c_int(fid), _p(rows), C.c_size_t(n), C.c_size_t(m), C.c_size_t(nrows)) == 0
     return rows
+
+
+def fft_bench(fid, n, reps=3):
+    """seconds per FFT<Field>::fftb(n) on one host thread"""
+    f = lib().ref_fft_bench
+    f.restype = C.c_double
+    return float(f(C.c_int(fid), C.c_size_t(n), C.c_int(reps)))
+
+
+def rs_bench(fid, n, m, reps=3):
+    """seconds per ReedSolomon(n, m)::interpolate (fid 4: LCH14ReedSolomon) of one row on one host thread"""
+    if fid == 4:
+        f = lib().ref_lch14_rs_bench
+        f.restype = C.c_double
+        return float(f(C.c_size_t(n), C.c_size_t(m), C.c_int(reps)))
+    f = lib().ref_rs_bench
+    f.restype = C.c_double
+    return float(f(C.c_int(fid), C.c_size_t(n), C.c_size_t(m), C.c_int(reps)))
 
 
 def fp_mul(fid, a, b):

@@ -22,6 +22,27 @@ def rng_bytes(seed, n):
     return np.random.default_rng(seed).integers(0, 256, n, dtype=np.uint8)
 
 
+def load_witnesses(name):
+    """several distinct satisfying witnesses of a 1-instance circuit (make_golden.py distinct_witnesses):
+    an (N, witness_bytes) uint8 array"""
+    _, wit = load(name)
+    raw = zlib.decompress(open(os.path.join(GOLDEN, name + ".witnesses.z"), "rb").read())
+    return np.frombuffer(raw, np.uint8).reshape(-1, len(wit)).copy()
+
+
+def load_size(name):
+    """(circuit, witness, golden record) of one of the other published instance sizes (tests/golden/sizes)"""
+    import lzma
+    d = os.path.join(GOLDEN, "sizes")
+    circ = lzma.decompress(open(os.path.join(d, name + ".circuit.xz"), "rb").read())
+    wit = zlib.decompress(open(os.path.join(d, name + ".witness.z"), "rb").read())
+    return circ, wit, json.load(open(os.path.join(d, "golden_sizes.json")))[name]
+
+
+SIZE_NAMES = ["sha2_gf128", "sha4_gf128", "sha8_gf128", "sha16_gf128", "sha32_gf128", "sha33_gf128", "ecdsa2_p256",
+              "ecdsa3_p256"]
+
+
 def load_mdoc():
     """The frozen mdoc instance of tests/golden/make_golden_mdoc.py: the two circuits of kZkSpecs[0]
     (signature circuit then hash circuit, LFC1 bytes as the reference's circuit file holds them,

@@ -98,6 +98,34 @@ def test_rs_p256_benchmark_shape_is_consistent(ctx):
     assert (lf.ReedSolomonFactory(ctx, 1).make(n, m).interpolate(again) == cw).all()
 
 
+@pytest.mark.parametrize("fid", [100, 101, 102, 1])
+def test_rs_config1_batch_of_1024_rows(ctx, oracle, fid):
+    """BASELINE config 1's batched shape, 1024 rows of ReedSolomon(455, 4096), over every prime field:
+    sampled rows against the oracle, and all rows through linearity (row 2k+1 = row 2k + row 0 on the
+    message part => the same on the extension)."""
+    import longfellow_zk_b200 as lf
+    p, kb = MOD[fid], KB[fid]
+    rs = np.random.default_rng(fid)
+    n, m, R = 455, 4096, 1024
+    rows = np.zeros((R, m, kb), np.uint8)
+    half = rand_elts(rs, fid, (R // 2) * n).reshape(R // 2, n, kb)
+    rows[0::2, :n] = half
+    to_int = lambda a: [int.from_bytes(a[i].tobytes(), "little") for i in range(a.shape[0])]
+    r0 = to_int(half[0])
+    for k in (0, 1, 100, R // 2 - 1):   # a few odd rows = even row + row 0 (mod p)
+        rk = to_int(half[k])
+        rows[2 * k + 1, :n] = np.frombuffer(b"".join(((a + b) % p).to_bytes(kb, "little") for a, b in zip(rk, r0)),
+                                            np.uint8).reshape(n, kb)
+    got = lf.ReedSolomonFactory(ctx, fid).make(n, m).interpolate(rows)
+    for i in (0, 1, 2, 201, R - 2):
+        want = oracle.rs_interpolate(fid, n, m, rows[i:i + 1].copy())
+        assert (got[i] == want[0]).all(), i
+    e0 = to_int(got[0])
+    for k in (0, 1, 100, R // 2 - 1):
+        ek, eo = to_int(got[2 * k]), to_int(got[2 * k + 1])
+        assert all((a + b) % p == c for a, b, c in zip(ek, e0, eo)), k
+
+
 def test_fft_timing_reports(ctx):
     import json
     import os

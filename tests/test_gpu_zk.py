@@ -154,22 +154,3 @@ def test_growing_and_shrinking_batches_on_one_circuit(sha, oracle):
         W = np.repeat(np.frombuffer(wit, np.uint8)[None, :], B, axis=0)
         proofs, status = p.prove_batch(W, rng)
         assert (status == 0).all() and proofs[0] == want, B
-
-
-@pytest.mark.parametrize("name,fid", [("sha1_gf128", 4), ("ecdsa1_p256", 1)])
-def test_full_size_batch_is_accepted_by_the_reference_verifier(ctx, ref, name, fid):
-    """BASELINE's batch size (1024 independent proofs, every proof its own coins): every status is
-    zero, all proofs differ, and the unmodified reference ZkVerifier accepts every one of them"""
-    import longfellow_zk_b200 as lf
-    circ, wit = load(name)
-    c = lf.Circuit(ctx, fid, circ)
-    B, n = 1024, c.info["rng_bytes"]
-    rng = np.random.default_rng(2026).integers(0, 256, (B, n + 64), dtype=np.uint8)
-    W = np.repeat(np.frombuffer(wit, np.uint8)[None, :], B, axis=0)
-    proofs, status = lf.ZkProver(c).prove_batch(W, rng)
-    assert (status == 0).all()
-    assert len({hashlib.sha256(p).digest() for p in proofs}) == B
-    rc = ref.Circuit(fid, circ)
-    pub = wit[:c.info["npub_in"] * c.info["kbytes"]]
-    for i in range(B):
-        assert rc.verify(pub, proofs[i]) == 0, i

@@ -237,3 +237,30 @@ def test_mdoc_fixture_is_consistent(oracle):
     assert oracle.Circuit(oracle.P256_ID, raw) is not None
     e = f["expect"]
     assert e["proof_len"] == 96 + e["len_hash"] + e["len_sig"] and f["coins"].size == e["coins_total"]
+
+
+import pytest  # noqa: E402
+
+from fixtures import SIZE_NAMES, load_size, load_witnesses  # noqa: E402
+
+
+@pytest.mark.parametrize("name", SIZE_NAMES)
+def test_published_instance_sizes_match_the_reference(oracle, name):
+    """BM_ShaZK_fp2_128/2..33 and BM_ECDSAZKProver/2,3 (docs/content/en/docs/benchmarks.md:56-61,74-75):
+    the oracle's proof for seed 1 is the reference's, byte for byte (tests/golden/sizes/golden_sizes.json)"""
+    circ, wit, g = load_size(name)
+    assert hashlib.sha256(circ).hexdigest() == g["circuit_sha256"]
+    r = oracle.Circuit(g["field_id"], circ).prove(wit, rng_bytes(1, 1 << 22))
+    assert r["rng_used"] == g["proof"]["rng_used"]
+    assert len(r["proof"]) == g["proof"]["proof_len"]
+    assert hashlib.sha256(r["proof"]).hexdigest() == g["proof"]["proof_sha256"]
+
+
+@pytest.mark.parametrize("name,fid", [("sha1_gf128", 4), ("ecdsa1_p256", 1)])
+def test_distinct_witnesses_are_distinct_and_satisfying(oracle, name, fid):
+    circ, wit = load(name)
+    W = load_witnesses(name)
+    assert W.shape[0] >= 8 and len({w.tobytes() for w in W}) == W.shape[0]
+    c = oracle.Circuit(fid, circ)
+    for w in W[:3]:
+        assert len(c.prove(w.tobytes(), rng_bytes(2, 1 << 19))["proof"]) > 100000
