@@ -48,6 +48,22 @@ def load_fixture(name="sha"):
     return load(WORKLOADS[name][0])
 
 
+def witness_rows(name, B):
+    """B witnesses cycling through the distinct fixtures of the workload (other messages / signatures)"""
+    import numpy as np
+    from fixtures import load_witnesses
+    W = load_witnesses(WORKLOADS[name][0])
+    return np.ascontiguousarray(W[np.arange(B) % W.shape[0]]), W.shape[0]
+
+
+def ref_build_info():
+    """compiler and flags the reference arm (oracle/_ref) was built with (written by __graft_entry__.build)"""
+    try:
+        return json.load(open(os.path.join(ROOT, "oracle", "_ref", "build_info.json")))
+    except Exception:
+        return dict(compiler="g++ (version not recorded)", flags="see oracle/ref_build/Makefile")
+
+
 def rng_stream(seed, n):
     import numpy as np
     return np.random.default_rng(seed).integers(0, 256, n, dtype=np.uint8)
@@ -78,7 +94,7 @@ def cpu_reference_throughput(nthreads, per_thread, workload="sha"):
     med = sorted(lat)[len(lat) // 2] if lat else secs / n * 1e3
     return dict(value=n / secs, unit=UNIT, cores=nthreads, kind=kind,
                 sample=f"{nthreads} threads x {per_thread} proofs of the same workload ({secs:.2f} s wall)",
-                ms_per_proof_1thread=med)
+                ms_per_proof_1thread=med, build=ref_build_info())
 
 
 def run_reference(args):
@@ -161,8 +177,9 @@ def stage_rates(info, stage_ms, B, mul_peak, sha_peak):
     return out
 
 
-def measure_other(lf, ctx, stream, workload, B, steps=3):
-    """device-resident and end-to-end proofs/s of another circuit (single GPU, rank 0)"""
+def measure_other(lf, ctx, stream, workload, B, steps=3, reduce_max=None, world=1):
+    """device-resident and end-to-end proofs/s of another circuit; under torchrun every rank runs it on its own
+    GPU and the times are max-reduced (reduce_max), so the value is the whole-job aggregate"""
     import numpy as np
     import torch
     fixture, fid, desc = WORKLOADS[workload]
@@ -174,7 +191,8 @@ def measure_other(lf, ctx, stream, workload, B, steps=3):
     # room for a few redrawn samples per proof (prime fields: Field::sample rejects a draw >= p, 2^-32 each)
     rstride = (rb + 8 * info["rng_redraw_bytes"] + 15) & ~15
     gen = torch.Generator().manual_seed(77)
-    h_wit = torch.from_numpy(np.frombuffer(wit, np.uint8).copy()).repeat(B, 1).pin_memory()
+    W, ndistinct = witness_rows(workload, B)
+    h_wit = torch.from_numpy(W).pin_memory()
     h_rng = torch.randint(0, 256, (B, rstride), dtype=torch.uint8, generator=gen).pin_memory()
     h_out = torch.empty((B, pb), dtype=torch.uint8).pin_memory()
     h_len = torch.zeros(B, dtype=torch.int64).pin_memory()
@@ -183,6 +201,7 @@ def measure_other(lf, ctx, stream, workload, B, steps=3):
     d_out = torch.empty((B, pb), dtype=torch.uint8, device="cuda")
     d_len = torch.zeros(B, dtype=torch.int64, device="cuda")
     d_st = torch.zeros(B, dtype=torch.int32, device="cuda")
+    rmax = reduce_max or (lambda x: x)
 
     def dev():
         prover.prove_batch_ptr(B, d_wit.data_ptr(), d_rng.data_ptr(), rstride, d_out.data_ptr(), pb,
@@ -196,15 +215,17 @@ def measure_other(lf, ctx, stream, workload, B, steps=3):
     torch.cuda.synchronize()
     assert int(d_st.abs().sum().item()) == 0
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    rmax(0.0)  # rendezvous
     e0.record(stream)
     for _ in range(steps):
         dev()
     e1.record(stream)
     torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1)
+    ms = rmax(e0.elapsed_time(e1))
     prover.set_profiling(True)
     dev()
     stages = prover.stage_ms()
+    kernel_ms = prover.kernel_ms()
     prover.set_profiling(False)
     # single-proof latency (batch of one, device resident)
     def one():
@@ -219,15 +240,98 @@ def measure_other(lf, ctx, stream, workload, B, steps=3):
     torch.cuda.synchronize()
     lat1 = e0.elapsed_time(e1) / 5
     host()
+    rmax(0.0)
     t0 = time.perf_counter()
     for _ in range(2):
         host()
-    t1 = time.perf_counter()
+    t1 = rmax(time.perf_counter() - t0)
     assert int(h_st.abs().sum().item()) == 0
-    return dict(workload=desc, proofs_per_step=B, value=B * steps / (ms * 1e-3), unit=UNIT,
-                e2e=dict(value=2 * B / (t1 - t0), unit=UNIT), stage_ms=stages, latency_ms_per_proof_batch1=lat1,
+    # the verifier on the proofs just made (host buffers in, status out): BM_ECDSAZKVerifier's counterpart
+    npubb = info["npub_in"] * info["kbytes"]
+    proofs = [bytes(h_out[i, :int(h_len[i])].numpy()) for i in range(B)]
+    pubs = np.ascontiguousarray(W[:, :npubb]) if npubb else None
+    ver = lf.ZkVerifier(circuit)
+    st, _ = ver.verify_batch(pubs, proofs)
+    assert (st == 0).all(), "the GPU verifier rejected a GPU proof"
+    # raw-pointer timing (no Python packing in the timed region)
+    import ctypes as C
+    from longfellow_zk_b200 import _native
+    lens64 = np.array([len(p_) for p_ in proofs], np.uint64)
+    vst, vwhy = np.zeros(B, np.int32), np.zeros(B, np.int32)
+    pp = lambda a: a.ctypes.data_as(C.c_void_p) if a is not None else None
+    hout_np = h_out.numpy()
+
+    def verify_raw():
+        _native.check(_native.lib().lf_zk_verify_batch(circuit._h, B, pp(pubs), pp(hout_np), pb, pp(lens64), b"test", 4,
+                                                       pp(vst), pp(vwhy)))
+    verify_raw()
+    rmax(0.0)
+    t0 = time.perf_counter()
+    for _ in range(2):
+        verify_raw()
+    tv = rmax(time.perf_counter() - t0)
+    assert (vst == 0).all()
+    return dict(workload=desc, proofs_per_step=B, distinct_witnesses=ndistinct,
+                value=world * B * steps / (ms * 1e-3), unit=UNIT,
+                e2e=dict(value=world * 2 * B / t1, unit=UNIT), stage_ms=stages,
+                kernel_ms={k: dict(ms=v[0], launches=v[1]) for k, v in kernel_ms.items()},
+                latency_ms_per_proof_batch1=lat1,
                 kernels=stage_rates(info, stages, B, ctx.microbench(4 if fid == 1 else 2), ctx.microbench(3)),
+                verifier=dict(value=world * 2 * B / tv, unit="proofs verified/s", ms_per_proof=1e3 * tv / (2 * B),
+                              how="lf_zk_verify_batch, host buffers in / status out, batch of %d" % B),
                 proof_bytes=int(d_len[0].item()), total_mults_per_proof=info["total_mults"])
+
+
+def cpu_verify_ms(workload, reps=5):
+    """the reference's ZkProof::read + ZkVerifier on one host thread: ms per proof (median)"""
+    from oracle import refapi
+    import numpy as np
+    if not refapi.available():
+        return None
+    circ, wit = load_fixture(workload)
+    fid = WORKLOADS[workload][1]
+    c = refapi.Circuit(fid, circ)
+    info = refapi.circuit_info(fid, circ)
+    kb = 16 if fid == 4 else 32
+    pr = c.prove(wit, rng_stream(1, 1 << 19))["proof"]
+    ts = []
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        assert c.verify(wit[:info["npub_in"] * kb], pr) == 0
+        ts.append(1e3 * (time.perf_counter() - t0))
+    return sorted(ts)[len(ts) // 2]
+
+
+FIELDS_CONFIG1 = [("fp256_p256_fp2", 1), ("bn254_fp4", 100), ("fp128", 101), ("goldilocks_f64", 102)]
+
+
+def measure_config1(ctx):
+    """BASELINE config 1: FFT (n = 2^16) and Reed-Solomon encode per field, a single transform and 1024 rows at once,
+    device resident (CUDA events on the context stream), next to FFT<Field>::fftb / ReedSolomon::interpolate of
+    the unmodified reference on one host thread."""
+    from oracle import refapi
+    have_ref = refapi.available()
+    out = {}
+    for name, fid in FIELDS_CONFIG1:
+        r = dict(fft_65536_ms=ctx.fft_time_ms(fid, 65536, reps=20),
+                 fft_65536_x1024rows_ms=ctx.fft_time_rows_ms(fid, 65536, 1024 if fid != 1 else 512, reps=3),
+                 fft_rows=1024 if fid != 1 else 512,
+                 rs_65536_262144_ms=ctx.rs_time_ms(fid, 65536, 262144, 1, reps=3),
+                 rs_455_4096_x1024rows_ms=ctx.rs_time_ms(fid, 455, 4096, 1024, reps=5))
+        if have_ref:
+            r["cpu_1thread"] = dict(fft_65536_ms=1e3 * refapi.fft_bench(fid, 65536, 2),
+                                    rs_65536_262144_ms=1e3 * refapi.rs_bench(fid, 65536, 262144, 1),
+                                    rs_455_4096_ms_per_row=1e3 * refapi.rs_bench(fid, 455, 4096, 3))
+        out[name] = r
+    r = dict(rs_16384_65536_ms=ctx.rs_time_ms(4, 16384, 65536, 1, reps=5),
+             rs_16384_65536_x64rows_ms=ctx.rs_time_ms(4, 16384, 65536, 64, reps=3),
+             rs_455_4096_x1024rows_ms=ctx.rs_time_ms(4, 455, 4096, 1024, reps=5),
+             rs_455_4096_x20480rows_ms=ctx.rs_time_ms(4, 455, 4096, 20480, reps=5))
+    if have_ref:
+        r["cpu_1thread"] = dict(rs_16384_65536_ms=1e3 * refapi.rs_bench(4, 16384, 65536, 3),
+                                rs_455_4096_ms_per_row=1e3 * refapi.rs_bench(4, 455, 4096, 10))
+    out["gf2_128_lch14"] = r
+    return out
 
 
 def run_ours(args):
@@ -243,7 +347,6 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dist = None
     if world > 1:
-        os.environ.pop("NCCL_DEBUG", None)  # keep stdout to the one JSON line
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
@@ -260,9 +363,11 @@ def run_ours(args):
     wb, rb, pb = info["witness_bytes"], info["rng_bytes"], info["max_proof_bytes"]
     rstride = (rb + 15) & ~15
 
-    # synthetic inputs: the benchmark witness for every proof, per-proof RNG streams
+    # synthetic inputs: the proofs of a batch cycle through distinct witnesses (different SHA-256 messages),
+    # every proof has its own RNG stream
     gen = torch.Generator().manual_seed(1234 + rank)
-    h_wit = torch.from_numpy(np.frombuffer(wit, np.uint8).copy()).repeat(B, 1).pin_memory()
+    W, ndistinct = witness_rows("sha", B)
+    h_wit = torch.from_numpy(W).pin_memory()
     h_rng = torch.randint(0, 256, (B, rstride), dtype=torch.uint8, generator=gen).pin_memory()
     h_out = torch.empty((B, pb), dtype=torch.uint8).pin_memory()
     h_len = torch.zeros(B, dtype=torch.int64).pin_memory()
@@ -278,8 +383,8 @@ def run_ours(args):
 
     # More contexts on their own streams: consecutive steps (batches) go round robin over the
     # streams, so the thinly parallel kernels of one batch (zero-block hashing of the transcript,
-    # proof serialisation, Merkle tree top) run under another batch's sumcheck.
-    NS = 3  # streams in flight (tools/streams_sweep.py: 1: 11.5 k, 2: 12.1 k, 3: 12.6 k, 4: 12.7 k proofs/s)
+    # proof serialisation, Merkle tree top, the small sumcheck rounds) run under another batch's large kernels.
+    NS = 3  # streams in flight (tools/streams_sweep.py)
     xstreams = [torch.cuda.Stream() for _ in range(NS - 1)]
     xctx = [lf.Context(local, stream=s.cuda_stream) for s in xstreams]
     xprover = [lf.ZkProver(lf.Circuit(cx, lf.FIELD_GF2_128, circ)) for cx in xctx]
@@ -290,6 +395,15 @@ def run_ours(args):
         o = xout[k]
         xprover[k].prove_batch_ptr(B, d_wit.data_ptr(), d_rng.data_ptr(), rstride, o[0].data_ptr(), pb,
                                    o[1].data_ptr(), o[2].data_ptr(), device=True)
+
+    def reduce_max(x):
+        """max over ranks of a host scalar (also the rendezvous before a timed region)"""
+        torch.cuda.synchronize()
+        if dist is None:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
 
     def timed_streams(steps):
         """K steps issued round robin on the NS streams; one CUDA-event interval on `stream`
@@ -310,11 +424,9 @@ def run_ours(args):
             stream.wait_event(ej)
         e1.record(stream)
         torch.cuda.synchronize()
-        t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
-        if dist is not None:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        t = reduce_max(e0.elapsed_time(e1))
         barrier()
-        return float(t.item())
+        return t
 
     def step_host():
         prover.prove_batch_ptr(B, h_wit.data_ptr(), h_rng.data_ptr(), rstride, h_out.data_ptr(), pb,
@@ -336,12 +448,9 @@ def run_ours(args):
         e1.record(stream)
         torch.cuda.synchronize()
         t1 = time.perf_counter()
-        ms = e0.elapsed_time(e1) if use_events else (t1 - t0) * 1e3
-        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
-        if dist is not None:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        t = reduce_max(e0.elapsed_time(e1) if use_events else (t1 - t0) * 1e3)
         barrier()
-        return float(t.item())
+        return t
 
     # ---- warm-up + correctness of what is being timed
     for _ in range(max(args.warmup, 3)):
@@ -365,14 +474,18 @@ def run_ours(args):
     # the same K steps back to back on ONE stream (no overlap between batches)
     ms_one_stream = timed(step_dev, args.steps, use_events=True)
 
-    # ---- per-stage device times of one more batch (roofline of the dominant kernel)
+    # ---- per-stage and per-kernel-class device times of three more batches (roofline of the dominant kernel)
     prover.set_profiling(True)
-    stage_acc = {}
+    stage_acc, kacc = {}, {}
     nprof = 3
     for _ in range(nprof):
         step_dev()
         for k, v in prover.stage_ms().items():
             stage_acc[k] = stage_acc.get(k, 0.0) + v / nprof
+        for k, (ms_k, n_k) in prover.kernel_ms().items():
+            a = kacc.setdefault(k, [0.0, 0])
+            a[0] += ms_k / nprof
+            a[1] = n_k
     prover.set_profiling(False)
 
     # ---- end to end through the host-pointer C-ABI call (pinned host buffers)
@@ -384,7 +497,6 @@ def run_ours(args):
     assert int(h_st.abs().sum().item()) == 0
     # the same call from NS host threads, each with its own context / stream / pinned buffers, so
     # that one batch's PCIe copies overlap the other batches' kernels (what a serving loop does)
-    import threading
     hx = [[h_wit.clone().pin_memory(), h_rng.clone().pin_memory(), torch.empty((B, pb), dtype=torch.uint8).pin_memory(),
            torch.zeros(B, dtype=torch.int64).pin_memory(), torch.zeros(B, dtype=torch.int32).pin_memory()]
           for _ in range(NS - 1)]
@@ -425,12 +537,42 @@ def run_ours(args):
         step_one()
     lat_ms = timed(step_one, 10, use_events=True) / 10
 
+    # ---- BASELINE config 5 names SHA-256 AND ECDSA at N GPUs, config 3 the mdoc proof: every rank runs them
+    other = {}
+    try:
+        other["ecdsa_p256"] = measure_other(lf, ctx, stream, "ecdsa", min(B, 1024), reduce_max=reduce_max, world=world)
+    except Exception as ex:  # the headline line must not depend on the extra workload
+        other["ecdsa_p256"] = dict(error=repr(ex))
+        reduce_max(0.0)
+    try:
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        import mdoc_bench
+        md = mdoc_bench.measure(batches=(1, 128), reps=2, device=local) if rank == 0 else None
+        barrier()
+        md2 = mdoc_bench.measure_two_in_flight(B=128, rounds=2, device=local, rendezvous=barrier)
+        secs = reduce_max(md2["seconds"])
+        if rank == 0:
+            nproofs = world * md2["batches"] * 128
+            other["mdoc"] = dict(workload="BM_MdocProver: kZkSpecs[0], mdoc_tests[0] + age_over_18; hash circuit GF(2^128) "
+                                          "7.76 M terms 266x4151, signature circuit Fp256 482 k terms 19x4096; "
+                                          "commit+commit+prove+prove through the host-pointer C ABI (H2D/D2H included)",
+                                 latency_ms_per_proof_batch1=md["batches"][0]["ms_total"],
+                                 value=nproofs / secs, unit=UNIT, proofs_per_step=128, n_gpus=world,
+                                 ms_per_proof=1e3 * secs / nproofs,
+                                 how="per GPU two batches of 128 in flight (two host threads, contexts and circuit objects)",
+                                 one_batch_at_a_time=dict(value=md["batches"][1]["proofs_per_s"],
+                                                          ms_per_proof=md["batches"][1]["ms_per_proof"]),
+                                 detail=md)
+    except Exception as ex:
+        other["mdoc"] = dict(error=repr(ex))
+
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
         return
 
-    # ---- roofline of the dominant kernel (k_zk_sumcheck)
+    # ---- roofline of the dominant kernel.  The path is integer-pipe bound (GF(2^128) products out of IMAD.WIDE
+    # and LOP3), so the bound that is reported is the integer one; HBM is the secondary figure.
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -440,33 +582,54 @@ def run_ours(args):
     peak_src = "MEASURED_PEAKS.json hbm_gbs (measured)" if "hbm_gbs" in peaks else "6650 GB/s (fallback)"
     top = max(stage_acc, key=stage_acc.get)
     sc_ms = stage_acc["sumcheck"]
-    alg_bytes = info["sumcheck_alg_bytes"] * B
-    achieved = alg_bytes / (sc_ms * 1e-3) / 1e9
-    gmul_peak = ctx.microbench(2)  # measured GF(2^128) multiply rate of this formulation (Gmul/s)
-    # DRAM bytes of one launch of that kernel from the committed `ncu --set full` capture (same batch size)
+    gmul_peak = ctx.microbench(2)   # measured GF(2^128) multiply rate of this formulation (Gmul/s)
+    imad_gops = ctx.microbench(0)   # IMAD.WIDE, G warp-lane ops/s
+    lop3_gops = ctx.microbench(1)
+    # one product = 144 IMAD.WIDE + 251 LOP3 (cuobjdump of gf128_mul): the pipe-level ceiling of the formulation
+    pipe_bound = min(imad_gops / 144.0, lop3_gops / 251.0)
+    kname = max(kacc, key=lambda k: kacc[k][0]) if kacc else "k_zk_sumcheck"
+    kms, kn = kacc.get(kname, (sc_ms, 1))
+    if kname == "k_sc_eval":
+        k_bytes, k_mults = info["flat_eval_alg_bytes"] * B, info["flat_eval_mults"] * B
+    elif kname == "k_sc_bind":
+        k_bytes, k_mults = info["flat_bind_alg_bytes"] * B, info["flat_bind_mults"] * B
+    else:
+        k_bytes, k_mults = info["sumcheck_alg_bytes"] * B, info["sumcheck_mults"] * B
+    k_gmul = k_mults / (kms * 1e-3) / 1e9
+    k_gbs = k_bytes / (kms * 1e-3) / 1e9
+    # DRAM bytes of one launch of that kernel from the committed `ncu --set full` capture of the launched variant
     traffic, traffic_src = None, None
     try:
-        cap = open(os.path.join(ROOT, "profiles", "r1_sumcheck_occ8_full.txt")).read()
         import re
-        grid = int(re.search(r"launch__grid_size\s+(\d+)", cap).group(1))
-        rd = float(re.search(r"dram__bytes_read.sum\s+([\d.]+)\s+Gbyte", cap).group(1))
-        wr = float(re.search(r"dram__bytes_write.sum\s+([\d.]+)\s+Gbyte", cap).group(1))
-        traffic = (rd + wr) * 1e9 * B / grid
-        traffic_src = "profiles/r1_sumcheck_occ8_full.txt: dram__bytes_read.sum + dram__bytes_write.sum of one " \
-                      "launch of %d proofs, scaled to %d (bytes)" % (grid, B)
+        cap_file = "profiles/r2_sc_eval_full.txt"
+        cap = open(os.path.join(ROOT, cap_file)).read().split("kernel:")[1]
+        rd = float(re.search(r"dram__bytes_read.sum\s+([\d.]+)\s+Mbyte", cap).group(1))
+        wr = float(re.search(r"dram__bytes_write.sum\s+([\d.]+)\s+Mbyte", cap).group(1))
+        traffic = (rd + wr) * 1e6
+        traffic_src = cap_file + ": dram__bytes_read.sum + dram__bytes_write.sum of ONE k_sc_eval launch (layer 11 " \
+            "round 4 of 1024 proofs: 19351 entries + 5700 wires per proof, 886 MB algorithmic; the L2 holds part of it)"
     except Exception:
         pass
-    roofline = dict(bound="hbm", kernel="k_zk_sumcheck", achieved=achieved, peak=hbm_peak, unit="GB/s",
-                    frac=achieved / hbm_peak, traffic=traffic, traffic_source=traffic_src,
-                    algorithmic_bytes_per_launch=alg_bytes, peak_source=peak_src,
-                    kernel_ms_per_launch=sc_ms, share_of_step=sc_ms / sum(stage_acc.values()),
-                    algorithmic_bytes_per_proof=info["sumcheck_alg_bytes"],
-                    integer_pipe=dict(
-                        note="the kernel is integer-pipe bound (carry-less multiply out of IMAD.WIDE/LOP3); "
-                             "fraction of the measured GF(2^128) multiply rate of the same formulation",
-                        achieved_gmul_s=info["sumcheck_mults"] * B / (sc_ms * 1e-3) / 1e9,
-                        peak_gmul_s=gmul_peak,
-                        frac=info["sumcheck_mults"] * B / (sc_ms * 1e-3) / 1e9 / gmul_peak),
+    roofline = dict(bound="integer", kernel=kname, achieved=k_gmul, peak=gmul_peak, unit="Gmul/s (GF(2^128) products)",
+                    frac=k_gmul / gmul_peak,
+                    peak_source="lf_microbench(2): the same multiply formulation in a register-resident loop, measured in "
+                                "this run",
+                    launches_per_step=kn, kernel_ms_per_launch=kms / max(kn, 1), kernel_ms_per_step=kms,
+                    share_of_step=kms / sum(stage_acc.values()),
+                    algorithmic_mults_per_launch=k_mults / max(kn, 1),
+                    algorithmic_bytes_per_launch=k_bytes / max(kn, 1),
+                    traffic=traffic, traffic_source=traffic_src,
+                    pipes=dict(imad_wide_gops=imad_gops, lop3_gops=lop3_gops,
+                               per_product="144 IMAD.WIDE + 251 LOP3",
+                               pipe_bound_gmul_s=pipe_bound, frac_of_pipe_bound=k_gmul / pipe_bound),
+                    hbm=dict(achieved=k_gbs, peak=hbm_peak, unit="GB/s", frac=k_gbs / hbm_peak, peak_source=peak_src),
+                    sumcheck_stage=dict(ms=sc_ms, share_of_step=sc_ms / sum(stage_acc.values()),
+                                        algorithmic_bytes=info["sumcheck_alg_bytes"] * B,
+                                        hbm_gbs=info["sumcheck_alg_bytes"] * B / (sc_ms * 1e-3) / 1e9,
+                                        hbm_frac=info["sumcheck_alg_bytes"] * B / (sc_ms * 1e-3) / 1e9 / hbm_peak,
+                                        gmul_s=info["sumcheck_mults"] * B / (sc_ms * 1e-3) / 1e9,
+                                        frac_of_mul_peak=info["sumcheck_mults"] * B / (sc_ms * 1e-3) / 1e9 / gmul_peak,
+                                        kernel_ms={k: dict(ms=v[0], launches=v[1]) for k, v in kacc.items()}),
                     stage_ms=stage_acc, top_stage=top,
                     kernels=stage_rates(info, stage_acc, B, gmul_peak, ctx.microbench(3)))
 
@@ -477,36 +640,41 @@ def run_ours(args):
     cpu["single_thread_proofs_per_s"] = cpu1["value"]
     cpu["single_thread_ms_per_proof"] = cpu1["ms_per_proof_1thread"]
 
-    # ---- second workload (BASELINE.json configs[2]): ECDSA P-256 over Fp256, short run
-    other = {}
-    try:
-        other["ecdsa_p256"] = measure_other(lf, ctx, stream, "ecdsa", min(B, 1024))
-        ecpu = cpu_reference_throughput(nthreads, 6, "ecdsa")
-        ecpu1 = cpu_reference_throughput(1, 4, "ecdsa")
-        ecpu["single_thread_ms_per_proof"] = ecpu1["ms_per_proof_1thread"]
-        other["ecdsa_p256"]["cpu_baseline"] = ecpu
-    except Exception as ex:  # the headline line must not depend on the extra workload
-        other["ecdsa_p256"] = dict(error=str(ex))
+    if "error" not in other.get("ecdsa_p256", {}):
+        try:
+            ecpu = cpu_reference_throughput(nthreads, 6, "ecdsa")
+            ecpu1 = cpu_reference_throughput(1, 4, "ecdsa")
+            ecpu["single_thread_ms_per_proof"] = ecpu1["ms_per_proof_1thread"]
+            other["ecdsa_p256"]["cpu_baseline"] = ecpu
+            other["ecdsa_p256"]["verifier"]["cpu_1thread_ms_per_proof"] = cpu_verify_ms("ecdsa")
+        except Exception as ex:
+            other["ecdsa_p256"]["cpu_baseline"] = dict(error=repr(ex))
 
-    # ---- third workload (BASELINE.json configs[3]): the ISO mdoc proof, two circuits over two fields on one
-    # transcript (tests/golden/mdoc: the reference's benchmark claim frozen; tools/mdoc_bench.py)
+    # the SHA-256 verifier, same shape as the ECDSA one
     try:
-        sys.path.insert(0, os.path.join(ROOT, "tools"))
-        import mdoc_bench
-        md = mdoc_bench.measure(batches=(1, 128), reps=2)
-        md2 = mdoc_bench.measure_two_in_flight(B=128, rounds=2)
-        other["mdoc"] = dict(workload="BM_MdocProver: kZkSpecs[0], mdoc_tests[0] + age_over_18; hash circuit GF(2^128) "
-                                      "7.76 M terms 266x4151, signature circuit Fp256 482 k terms 19x4096; "
-                                      "commit+commit+prove+prove through the host-pointer C ABI (H2D/D2H included)",
-                             latency_ms_per_proof_batch1=md["batches"][0]["ms_total"],
-                             value=md2["proofs_per_s"], unit=UNIT, proofs_per_step=128,
-                             ms_per_proof=md2["ms_per_proof"],
-                             how="two batches of 128 in flight (two host threads, contexts and circuit objects)",
-                             one_batch_at_a_time=dict(value=md["batches"][1]["proofs_per_s"],
-                                                      ms_per_proof=md["batches"][1]["ms_per_proof"]),
-                             detail=md)
+        ver = lf.ZkVerifier(circuit)
+        proofs = [bytes(h_out[i, :int(h_len[i])].numpy()) for i in range(B)]
+        st, _ = ver.verify_batch(None, proofs)
+        assert (st == 0).all()
+        t0 = time.perf_counter()
+        st, _ = ver.verify_batch(None, proofs)
+        tv = time.perf_counter() - t0
+        sha_verifier = dict(value=B / tv, unit="proofs verified/s", ms_per_proof=1e3 * tv / B,
+                            how="lf_zk_verify_batch through the Python wrapper (packing included), batch of %d" % B,
+                            cpu_1thread_ms_per_proof=cpu_verify_ms("sha"))
+    except Exception as ex:
+        sha_verifier = dict(error=repr(ex))
+
+    # ---- BASELINE config 1: stand-alone FFT / RS per field with the reference's CPU time beside it
+    try:
+        other["config1_fft_rs"] = measure_config1(ctx)
+    except Exception as ex:
+        other["config1_fft_rs"] = dict(error=repr(ex))
+
+    # ---- mdoc: the reference's prover on the host cores
+    try:
         from oracle import refapi
-        if refapi.mdoc_available():
+        if "error" not in other.get("mdoc", {}) and refapi.mdoc_available():
             from fixtures import load_mdoc
             mc = refapi.MdocCase(load_mdoc()["raw"])
             coins = np.random.default_rng(1).integers(0, 256, 1 << 20, dtype=np.uint8)
@@ -529,14 +697,15 @@ def run_ours(args):
             other["mdoc"]["cpu_baseline"] = dict(value=2 * nthreads / wall, unit=UNIT, cores=nthreads, kind="reference",
                                                  sample="%d threads x 2 proofs (run_mdoc_prover from 'Run prover' on, "
                                                         "oracle/ref_build/ref_mdoc.cc)" % nthreads,
-                                                 single_thread_ms_per_proof=1e3 * one)
+                                                 single_thread_ms_per_proof=1e3 * one, build=ref_build_info())
     except Exception as ex:
-        other["mdoc"] = dict(error=str(ex))
+        other.setdefault("mdoc", {})["cpu_baseline"] = dict(error=repr(ex))
 
     line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3),
                 ms_per_step=ms_total / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None,
                 dtype="gf2^128 (u32 limbs)", data="synthetic",
                 config=dict(workload=WORKLOAD, proofs_per_step_per_gpu=B, parallelism=f"independent proofs x{world}",
+                            distinct_witnesses=ndistinct,
                             l2="inputs+working set of one step (>%d MB) exceed the 126 MB L2" %
                                (B * (wb + rb + pb) // (1 << 20)),
                             ninputs=info["ninputs"], nterms=info["nterms"], tableau=[info["nrow"], info["block_enc"]],
@@ -552,9 +721,10 @@ def run_ours(args):
                              "thread, context and stream each) so PCIe copies overlap the other batches' kernels",
                          one_batch_at_a_time=dict(value=e2e_serial, ms_per_step=ms_e2e / e2e_steps)),
                 gpu_launches=launches, roofline=roofline, cpu_baseline=cpu,
-                latency_ms_per_proof_batch1=lat_ms,
+                latency_ms_per_proof_batch1=lat_ms, verifier=sha_verifier,
                 ms_per_proof=ms_total / args.steps / B, other_workloads=other)
     print(json.dumps(line))
+    sys.stdout.flush()
     if dist is not None:
         dist.destroy_process_group()
 

@@ -78,5 +78,5 @@ def test_batch_of_distinct_witnesses(ctx, oracle, ref, name, fid):
         assert rc.verify(pubs[i].tobytes(), proofs[i]) == 0, i
     if npub:
         # a proof checked against ANOTHER witness's public inputs is rejected
-        st, _ = lf.ZkVerifier(c).verify_batch(np.roll(pubs, 1, axis=0)[:Ws.shape[0]], proofs[:Ws.shape[0]])
+        st, _ = lf.ZkVerifier(c).verify_batch(np.roll(pubs[:Ws.shape[0]], 1, axis=0), proofs[:Ws.shape[0]])
         assert (st == -8).all()

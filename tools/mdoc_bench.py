@@ -9,9 +9,9 @@ from longfellow_zk_b200 import api
 from fixtures import load_mdoc
 
 
-def measure(batches=(1, 8, 32), reps=3):
+def measure(batches=(1, 8, 32), reps=3, device=0):
     f = load_mdoc(); e = f["expect"]
-    ctx = lf.Context(0)
+    ctx = lf.Context(device)
     t0 = time.perf_counter()
     sig = lf.Circuit(ctx, lf.FIELD_P256, f["raw"], rate=e["rate"], nreq=e["nreq"], block_enc=e["block_enc_sig"])
     hsh = lf.Circuit(ctx, lf.FIELD_GF2_128, f["raw"][sig.info["lfc1_bytes"]:], rate=e["rate"], nreq=e["nreq"],
@@ -46,14 +46,14 @@ def measure(batches=(1, 8, 32), reps=3):
     return res
 
 
-def measure_two_in_flight(B=128, rounds=2):
+def measure_two_in_flight(B=128, rounds=2, device=0, rendezvous=None):
     """two host threads, each with its own context and circuit objects, each proving `rounds` batches of B:
     one batch's serial zero-block hashing (118 ms for the hash circuit) runs under the other's sumcheck"""
     import threading
     f = load_mdoc(); e = f["expect"]
     lanes = []
     for _ in range(2):
-        ctx = lf.Context(0)
+        ctx = lf.Context(device)
         sig = lf.Circuit(ctx, lf.FIELD_P256, f["raw"], rate=e["rate"], nreq=e["nreq"], block_enc=e["block_enc_sig"])
         hsh = lf.Circuit(ctx, lf.FIELD_GF2_128, f["raw"][sig.info["lfc1_bytes"]:], rate=e["rate"], nreq=e["nreq"],
                          block_enc=e["block_enc_hash"])
@@ -73,6 +73,8 @@ def measure_two_in_flight(B=128, rounds=2):
     for lane in lanes:
         one_batch(lane)  # warm-up
     ths = [threading.Thread(target=lambda l=l: [one_batch(l) for _ in range(rounds)]) for l in lanes]
+    if rendezvous:
+        rendezvous()
     t0 = time.perf_counter()
     for th in ths:
         th.start()
