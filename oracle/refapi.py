@@ -319,6 +319,48 @@ def zstd_decompress(data):
     return buf.raw[:n]
 
 
+def zstd_compress(data, level=3):
+    z = C.CDLL("libzstd.so.1")
+    z.ZSTD_compressBound.restype = C.c_size_t
+    z.ZSTD_compressBound.argtypes = [C.c_size_t]
+    z.ZSTD_compress.restype = C.c_size_t
+    z.ZSTD_compress.argtypes = [C.c_void_p, C.c_size_t, C.c_char_p, C.c_size_t, C.c_int]
+    cap = z.ZSTD_compressBound(len(data))
+    buf = C.create_string_buffer(cap)
+    n = z.ZSTD_compress(buf, cap, data, len(data), level)
+    assert not z.ZSTD_isError(n)
+    return buf.raw[:n]
+
+
+# ---- run_mdoc_prover compiled unchanged against the CUDA back end (oracle/_ref/libref_mdoc_gpu.so) ----
+LIBREF_MDOC_GPU = os.path.join(_HERE, "_ref", "libref_mdoc_gpu.so")
+_mdoc_gpu_lib = None
+
+
+def mdoc_gpu_available():
+    return os.path.exists(LIBREF_MDOC_GPU)
+
+
+def mdoc_gpu_lib():
+    global _mdoc_gpu_lib
+    if _mdoc_gpu_lib is None:
+        _mdoc_gpu_lib = C.CDLL(LIBREF_MDOC_GPU)
+        _mdoc_gpu_lib.ref_mdoc_gpu_nclaims.restype = C.c_size_t
+        _mdoc_gpu_lib.ref_mdoc_gpu_claim_name.restype = C.c_char_p
+        _mdoc_gpu_lib.ref_mdoc_gpu_claim_name.argtypes = [C.c_size_t]
+        _mdoc_gpu_lib.ref_mdoc_gpu_run_claim.argtypes = [C.c_size_t, C.c_char_p, C.c_size_t, C.POINTER(C.c_size_t),
+                                                         C.c_int]
+    return _mdoc_gpu_lib
+
+
+def mdoc_gpu_run_claim(i, circuit_zstd, tamper=False):
+    """MdocZKTest::run_test for claim i of mdoc_zk_test.cc:119-170: the reference's run_mdoc_prover on the GPU
+    back end, then the reference's run_mdoc_verifier.  Returns (code, proof_len); code 0 = proved and accepted."""
+    n = C.c_size_t()
+    rc = mdoc_gpu_lib().ref_mdoc_gpu_run_claim(i, circuit_zstd, len(circuit_zstd), C.byref(n), int(tamper))
+    return int(rc), int(n.value)
+
+
 class MdocCase:
     """mdoc_tests[0] + age_over_18 on kZkSpecs[0] (the reference's benchmark claim,
     circuits/mdoc/mdoc_zk_test.cc:652-656): filled witnesses, and run_mdoc_prover from

@@ -83,3 +83,36 @@ def test_circuit_id_is_recomputed(ctx):
         with pytest.raises(lf.LongfellowError) as e:
             cb.verify_id()
         assert e.value.code == -3
+
+
+def test_two_devices_in_one_process(oracle):
+    """lf_ctx_create(device, ...) on two GPUs of one process: kernel attributes (dynamic shared memory,
+    cluster size) are per device, so every launch shape must work on the second device too (batch of one
+    = 16-CTA clusters, RS rows above 48 KB of shared memory, the 64 KB FFT tiles)"""
+    import numpy as np
+    import torch
+    import longfellow_zk_b200 as lf
+    from fixtures import load, rng_bytes
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs in the box")
+    circ, wit = load("sha1_gf128")
+    want = None
+    for dev in (0, 1, 0):
+        cx = lf.Context(dev)
+        c = lf.Circuit(cx, lf.FIELD_GF2_128, circ)
+        coins = rng_bytes(3, c.info["rng_bytes"])
+        if want is None:
+            want = oracle.Circuit(4, circ).prove(wit, coins)["proof"]
+        for B in (1, 40, 300):
+            proofs, status = lf.ZkProver(c).prove_batch(np.repeat(np.frombuffer(wit, np.uint8)[None, :], B, axis=0),
+                                                        np.repeat(coins[None, :], B, axis=0))
+            assert (status == 0).all() and proofs[0] == want and proofs[-1] == want, (dev, B)
+        rs = np.random.default_rng(0)
+        rows = rs.integers(0, 256, (2, 4096, 16), dtype=np.uint8)
+        got = lf.LCH14ReedSolomonFactory(cx).make(2000, 4096).interpolate(rows)
+        assert (got == oracle.lch14_interpolate(2000, 4096, rows)).all()
+        x = rs.integers(0, 256, (65536, 8), dtype=np.uint8)
+        x[:, 7] &= 0x7f
+        assert (cx.fft(lf.FIELD_GOLDILOCKS, cx.fft(lf.FIELD_GOLDILOCKS, x, 65536), 65536, forward=True).shape == x.shape)
+        c.close()
+        cx.close()

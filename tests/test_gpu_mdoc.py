@@ -88,3 +88,27 @@ def test_mdoc_proof_matches_reference(ctx):
     assert st[0] == 0 and len(proof_s[0]) == want["len_sig"]
     got = macs + proof_h[0] + proof_s[0]
     assert got == want["proof"]
+
+
+def test_run_mdoc_prover_drop_in_all_claims(ctx):
+    """N1: the reference's run_mdoc_prover, compiled UNCHANGED with ZkProver resolved to ZkProverGpu
+    (include/longfellow_b200_adapters.h; oracle/ref_build/ref_mdoc_gpu.cc), on every (claim, mdoc) pair of
+    lib/circuits/mdoc/mdoc_zk_test.cc:119-170 -- 27 different documents, issuers, attributes and session
+    transcripts, fresh SecureRandomEngine coins each -- and the reference's own run_mdoc_verifier accepts
+    every proof; a proof with one byte flipped is rejected."""
+    from oracle import refapi as ref
+    if not ref.mdoc_gpu_available():
+        pytest.skip("oracle/_ref/libref_mdoc_gpu.so not built")
+    from fixtures import load_mdoc
+    circuit = ref.zstd_compress(load_mdoc()["raw"])
+    lib = ref.mdoc_gpu_lib()
+    n = lib.ref_mdoc_gpu_nclaims()
+    assert n == 27
+    lens = set()
+    for i in range(n):
+        code, plen = ref.mdoc_gpu_run_claim(i, circuit)
+        assert code == 0, (i, lib.ref_mdoc_gpu_claim_name(i), code)
+        assert 300000 < plen < 400000
+        lens.add(plen)
+    code, _ = ref.mdoc_gpu_run_claim(0, circuit, tamper=True)
+    assert code != 0 and code < 1000   # the prover succeeded, the verifier refused
