@@ -198,23 +198,23 @@ __global__ void k_sc_bindg_fix(ZkDims d, ZkBufs<typename F::Elt> b, const uint32
 template <class F>
 __global__ void __launch_bounds__(32 * kFlatEvalWarps, kFlatEvalMinCta)
 k_sc_eval(ZkDims d, ZkBufs<typename F::Elt> b, const uint32_t* __restrict__ arena, LayerDesc L, StepDesc S,
-          FlatStepDesc FS, uint32_t t) {
+          FlatStepDesc FS, uint32_t t, uint32_t mode) {
   typedef typename F::Elt Elt;
   typedef typename F::Acc Acc;
   const size_t p = blockIdx.y;
   if (b.status[p] != 0) return;
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t bin = blockIdx.x * kFlatEvalWarps + warp;
-  if (bin >= FS.nbin) return;
+  if (bin >= FS.nbin[mode]) return;
   const FlatPtrs<F> P(d, b, L, p, t);
   const Elt *Wh = P.Wh, *Wo = P.Wo, *HQ = P.HQ;
   Acc c0, c2;
   F::acc_zero(c0);
   F::acc_zero(c2);
   // the bin's items (balanced on the host by their entry counts): sliced-ELL warps of row pairs, then heavy-row chunks
-  const uint32_t i0 = arena[FS.bin_off + bin], i1 = arena[FS.bin_off + bin + 1];
+  const uint32_t i0 = arena[FS.bin_off[mode] + bin], i1 = arena[FS.bin_off[mode] + bin + 1];
   for (uint32_t ii = i0; ii < i1; ++ii) {
-    const uint32_t item = arena[FS.bin_item + ii];
+    const uint32_t item = arena[FS.bin_item[mode] + ii];
     if (item < FS.nwarp_pair) {
       const uint32_t wb = item, slot = wb * 32 + lane;
       const uint32_t pair = arena[FS.pw_pair + slot];
@@ -255,9 +255,42 @@ k_sc_eval(ZkDims d, ZkBufs<typename F::Elt> b, const uint32_t* __restrict__ aren
   // no CTA-level reduction (a barrier here made every warp wait for the CTA's slowest): one partial per warp
   const Elt s0 = warp_sum<F>(F::reduce(c0)), s2 = warp_sum<F>(F::reduce(c2));
   if (lane == 0) {
-    Elt* part = b.part + p * 2 * (size_t)kFlatMaxBins;
+    Elt* part = b.part + p * b.part_stride;
     part[2 * bin] = s0;
     part[2 * bin + 1] = s2;
+  }
+}
+
+// many bins (a few proofs of a large circuit): the partials of a proof are added by one CTA first, so that
+// k_sc_round's single thread per proof reads two values.  part[0], part[1] = the sums.
+template <class F>
+__global__ void __launch_bounds__(256)
+k_sc_partsum(ZkBufs<typename F::Elt> b, uint32_t nbin) {
+  typedef typename F::Elt Elt;
+  const size_t p = blockIdx.x;
+  if (b.status[p] != 0) return;
+  Elt* part = b.part + p * b.part_stride;
+  Elt s0 = F::zero(), s2 = F::zero();
+  for (uint32_t i = threadIdx.x; i < nbin; i += blockDim.x) {
+    s0 = F::add(s0, part[2 * i]);
+    s2 = F::add(s2, part[2 * i + 1]);
+  }
+  __shared__ Elt red[2][8];
+  s0 = warp_sum<F>(s0);
+  s2 = warp_sum<F>(s2);
+  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) {
+    red[0][warp] = s0;
+    red[1][warp] = s2;
+  }
+  __syncthreads();  // also: every thread has read its partials before part[0..1] is overwritten
+  if (threadIdx.x == 0) {
+    for (uint32_t w = 1; w < blockDim.x / 32; ++w) {
+      s0 = F::add(s0, red[0][w]);
+      s2 = F::add(s2, red[1][w]);
+    }
+    part[0] = s0;
+    part[1] = s2;
   }
 }
 
@@ -283,7 +316,7 @@ k_sc_round(ZkDims d, ZkBufs<typename F::Elt> b, LayerDesc L, uint32_t t, uint32_
   const size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= nproofs || b.status[p] != 0) return;
   ScCore<F>* core = reinterpret_cast<ScCore<F>*>(b.scst + p * sizeof(ScCore<F>));
-  const Elt* part = b.part + p * 2 * (size_t)kFlatMaxBins;
+  const Elt* part = b.part + p * b.part_stride;
   Elt s0 = part[0], s2 = part[1];
   for (uint32_t c = 1; c < nbin; ++c) {
     s0 = F::add(s0, part[2 * c]);

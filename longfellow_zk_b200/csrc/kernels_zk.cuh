@@ -974,7 +974,7 @@ template <class F>
 __global__ void __launch_bounds__(kScClThreads, 1)
 k_zk_sumcheck_cluster(ZkDims d, ZkBufs<typename F::Elt> b, const uint32_t* __restrict__ arena,
                       const LayerDesc* __restrict__ layers, const StepDesc* __restrict__ steps,
-                      const typename F::Elt* __restrict__ consts) {
+                      const typename F::Elt* __restrict__ consts, ScRange R) {
   __shared__ ScShared<F> sh;
   __shared__ typename F::Elt hp[kScClThreads];
   __shared__ uint32_t hr[kScClThreads];
@@ -983,7 +983,7 @@ k_zk_sumcheck_cluster(ZkDims d, ZkBufs<typename F::Elt> b, const uint32_t* __res
     sh.hr = hr;
   }
   __syncthreads();
-  sumcheck_body<F, true>(d, b, arena, layers, steps, consts, sh, ScRange{0, d.nl, 0, 1});
+  sumcheck_body<F, true>(d, b, arena, layers, steps, consts, sh, R);
 }
 
 // ----------------------------------------------------------------------------

@@ -8,6 +8,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <atomic>
 #include <map>
 #include <set>
 #include <memory>
@@ -371,6 +372,7 @@ struct lf_ctx {
   std::set<const void*> fft_attr;
   // grow-only work arrays of the large-row RS / convolution paths (stream ordered: a later call on this
   // context's stream reuses them only after the earlier kernels are done)
+  int cluster_fit[2][4] = {{-1, -1, -1, -1}, {-1, -1, -1, -1}};  // resident clusters of 16 / 8 / 4 / 2 CTAs, per field
   void* work[2] = {nullptr, nullptr};
   size_t work_cap[2] = {0, 0};
 };

@@ -65,16 +65,22 @@ constexpr uint32_t kFlatHeavyRow = 48;     // entries of one row a pair thread s
 constexpr uint32_t kFlatHeavyChunk = 256;  // entries per heavy-row warp chunk
 constexpr uint32_t kFlatEvalWarps = 4;     // warps per CTA of k_sc_eval
 constexpr uint32_t kFlatEvalMinCta = 5;    // resident CTAs per SM the kernel is compiled for (register cap)
-constexpr uint32_t kFlatMaxBins = 128;     // warps (bins of work) per proof of k_sc_eval; k_sc_round adds their partials
+// warps (bins of work) per proof of k_sc_eval, by batch size: a large batch fills the GPU with few warps per
+// proof; a handful of proofs of a large circuit (one mdoc hash proof is 72 M multiplications) need thousands
+constexpr uint32_t kFlatBinModes = 3;
+constexpr uint32_t kFlatBinCap[kFlatBinModes] = {32, 256, 4096};   // mode 0: B >= 128, 1: B >= 8, 2: B < 8
+constexpr uint32_t kFlatBinModeMaxB[kFlatBinModes] = {0xffffffffu, 127, 7};
+constexpr uint32_t kFlatSumDirect = 64;    // k_sc_round adds up to this many partials itself; above, k_sc_partsum first
 constexpr uint32_t kFlatBinCost = 8;       // smallest bin worth a warp, in multiplications per lane
 constexpr uint32_t kFlatNone = 0xffffffffu;
 
 struct FlatStepDesc {
   uint32_t nwarp_pair;   // sliced-ELL warps of row pairs
   uint32_t nwarp_heavy;  // heavy-row chunks, one warp each
-  uint32_t nbin;         // warps per proof: each takes the items bin_item[bin_off[w] .. bin_off[w+1])
-  uint32_t bin_off;      // [nbin + 1]
-  uint32_t bin_item;     // [nwarp_pair + nwarp_heavy] item < nwarp_pair: sliced-ELL warp; else heavy chunk + nwarp_pair
+  // per bin mode: warps per proof, each takes the items bin_item[bin_off[w] .. bin_off[w+1])
+  uint32_t nbin[kFlatBinModes];
+  uint32_t bin_off[kFlatBinModes];   // [nbin + 1]
+  uint32_t bin_item[kFlatBinModes];  // [nwarp_pair + nwarp_heavy] item < nwarp_pair: sliced-ELL warp; else heavy chunk + nwarp_pair
   uint32_t pw_pair;      // [32 * nwarp_pair] pair index of each lane (kFlatNone: padding)
   uint32_t pw_cnt;       // [32 * nwarp_pair] entries of row 2i | entries of row 2i+1 << 16
   uint32_t pw_base;      // [nwarp_pair] entry offset of the warp's column-major block
@@ -141,7 +147,8 @@ struct ZkBufs {
   Elt* hb;         // [nhb] hand challenges
   Elt* alphas;     // [nl] per-layer alpha
   uint8_t* scst;   // [sizeof(ScCore<F>)] sumcheck prover state between the kernels of the flat path
-  Elt* part;       // [2 * kFlatMaxBins] per-warp partial sums of the two dot products of a round
+  Elt* part;       // [part_stride] per-warp partial sums of the two dot products of a round
+  size_t part_stride;
   Elt* chal;       // [1 + nchal] alpha_in, u_ldt, alphal, alphaq, u_quad
   Elt* avec;       // [nwqrow * w]
   Elt* aext;       // [nwqrow * dblock]

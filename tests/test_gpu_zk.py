@@ -149,7 +149,7 @@ def test_growing_and_shrinking_batches_on_one_circuit(sha, oracle):
     c, circ, wit = sha
     p = lf.ZkProver(c)
     want = oracle.Circuit(GF, circ).prove(wit, rng_bytes(1, c.info["rng_bytes"]))["proof"]
-    for B in (1, 3, 2, 11, 5):
+    for B in (1, 3, 2, 11, 5, 300, 16, 1, 40):
         rng = np.stack([rng_bytes(1 + i, c.info["rng_bytes"]) for i in range(B)])
         W = np.repeat(np.frombuffer(wit, np.uint8)[None, :], B, axis=0)
         proofs, status = p.prove_batch(W, rng)

@@ -21,7 +21,9 @@ for which, fid in (("sha1_gf128", 4), ("ecdsa1_p256", 1)):
     d_len = torch.zeros(BMAX, dtype=torch.int64, device="cuda")
     d_st = torch.zeros(BMAX, dtype=torch.int32, device="cuda")
     rows = []
-    for B in (2048, 1, 2, 4, 9, 10, 16, 32, 64, 128, 147, 148, 192, 256, 384, 512, 768, 1024, 1536, 2048):
+    BS = [int(x) for x in os.environ["LF_SWEEP"].split(",")] if os.environ.get("LF_SWEEP") else \
+        [1, 2, 4, 9, 10, 16, 32, 64, 128, 147, 148, 192, 256, 384, 512, 768, 1024, 1536, 2048]
+    for B in [2048] + BS:
         def step():
             p.prove_batch_ptr(B, d_wit.data_ptr(), d_rng.data_ptr(), rstride, d_out.data_ptr(), info["max_proof_bytes"],
                               d_len.data_ptr(), d_st.data_ptr(), device=True)
