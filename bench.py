@@ -347,6 +347,8 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dist = None
     if world > 1:
+        # NCCL's own log lines (NCCL_DEBUG=VERSION/INFO) go to stderr, so that stdout stays the one JSON line
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
