@@ -603,7 +603,7 @@ def run_ours(args):
     traffic, traffic_src = None, None
     try:
         import re
-        cap_file = "profiles/r2_sc_eval_full.txt"
+        cap_file = "profiles/r2_sc_eval_final.txt"
         cap = open(os.path.join(ROOT, cap_file)).read().split("kernel:")[1]
         rd = float(re.search(r"dram__bytes_read.sum\s+([\d.]+)\s+Mbyte", cap).group(1))
         wr = float(re.search(r"dram__bytes_write.sum\s+([\d.]+)\s+Mbyte", cap).group(1))

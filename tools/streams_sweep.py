@@ -9,7 +9,7 @@ which = sys.argv[1] if len(sys.argv) > 1 else "sha1_gf128"
 B = int(sys.argv[2]) if len(sys.argv) > 2 else 1024
 circ, wit = load(which)
 fid = 4 if "gf128" in which else 1
-S_MAX = 4
+S_MAX = 6
 streams = [torch.cuda.Stream() for _ in range(S_MAX)]
 ctxs = [lf.Context(0, stream=s.cuda_stream) for s in streams]
 provers = [lf.ZkProver(lf.Circuit(c, fid, circ)) for c in ctxs]
@@ -28,7 +28,7 @@ def step(i):
 for i in range(S_MAX):
     step(i); step(i)
 torch.cuda.synchronize()
-for S in (1, 2, 3, 4):
+for S in (1, 2, 3, 4, 5, 6):
     K = 12
     torch.cuda.synchronize(); t0 = time.perf_counter()
     for k in range(K):
