@@ -4,7 +4,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB = os.path.join(HERE, "liblongfellow_b200.so")
+LIB = os.environ.get("LF_LIB_PATH") or os.path.join(HERE, "liblongfellow_b200.so")  # LF_LIB_PATH: tuning builds
 
 _lib = None
 

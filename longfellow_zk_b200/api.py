@@ -33,12 +33,16 @@ class Context:
     """One CUDA device + stream (lf_ctx)."""
 
     def __init__(self, device=0, stream=None):
+        import weakref
         self._h = C.c_void_p()
+        self._circuits = weakref.WeakSet()  # circuits uploaded on this context: freed before the context is
         check(_native.lib().lf_ctx_create(int(device), C.c_void_p(stream) if stream else None,
                                           C.byref(self._h)))
 
     def close(self):
         if self._h:
+            for c in list(self._circuits):  # lf_circuit_free needs the live lf_ctx
+                c.close()
             _native.lib().lf_ctx_destroy(self._h)
             self._h = C.c_void_p()
 
@@ -169,6 +173,7 @@ class Circuit:
         self._h = C.c_void_p()
         check(_native.lib().lf_circuit_upload(ctx._h, field_id, lfc1_bytes, len(lfc1_bytes), rate, nreq,
                                               block_enc, C.byref(self._h)))
+        ctx._circuits.add(self)
         info = _native.CircuitInfo()
         check(_native.lib().lf_circuit_get_info(self._h, C.byref(info)))
         self.info = {n: int(getattr(info, n)) for n, _ in info._fields_}

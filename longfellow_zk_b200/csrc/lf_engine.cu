@@ -22,6 +22,7 @@
 #include "hash.cuh"
 #include "kernels_commit.cuh"
 #include "kernels_fft.cuh"
+#include "kernels_rscrt.cuh"
 #include "kernels_zk.cuh"
 #include "kernels_scflat.cuh"
 #include "kernels_verify.cuh"
@@ -372,11 +373,16 @@ struct lf_ctx {
   std::set<const void*> fft_attr;
   // grow-only work arrays of the large-row RS / convolution paths (stream ordered: a later call on this
   // context's stream reuses them only after the earlier kernels are done)
+  // CRT Reed-Solomon over P-256 (kernels_rscrt.cuh): constants, twiddles per transform size, spectra per (n, m)
+  void* d_crt_consts = nullptr;
+  std::vector<uint32_t> crt_p, crt_w;                  // primes, a generator-derived root of order 2^13 each
+  std::map<uint32_t, std::pair<uint32_t*, uint32_t*>> crt_tw;        // logN -> (forward, inverse) [17][N/2]
+  std::map<std::pair<size_t, size_t>, uint32_t*> crt_spec;           // (n, m) -> [17][N]
   int cluster_fit[2][4] = {{-1, -1, -1, -1}, {-1, -1, -1, -1}};  // resident clusters of 16 / 8 / 4 / 2 CTAs, per field
   void* work[2] = {nullptr, nullptr};
   size_t work_cap[2] = {0, 0};
 };
-enum { kAttrRsGf = 1, kAttrRsFp = 2, kAttrScCluster = 4 };
+enum { kAttrRsGf = 1, kAttrRsFp = 2, kAttrScCluster = 4 /* and 8: the prime-field cluster kernel */, kAttrRsCrt = 16 };
 
 namespace lf {
 
@@ -617,6 +623,217 @@ static int ctx_rs_fp_tables(lf_ctx* ctx, size_t n, size_t m, RsFpTables** out) {
   return 0;
 }
 
+
+// ---- CRT Reed-Solomon over P-256: host tables (kernels_rscrt.cuh) ---------------------------------
+namespace crt {
+static uint32_t mulmod(uint32_t a, uint32_t b, uint32_t p) { return (uint32_t)((uint64_t)a * b % p); }
+static uint32_t powmod(uint32_t a, uint64_t e, uint32_t p) {
+  uint32_t r = 1;
+  while (e) {
+    if (e & 1) r = mulmod(r, a, p);
+    a = mulmod(a, a, p);
+    e >>= 1;
+  }
+  return r;
+}
+static bool is_prime(uint32_t n) {
+  if (n < 2 || n % 2 == 0) return n == 2;
+  for (uint32_t i = 3; (uint64_t)i * i <= n; i += 2)
+    if (n % i == 0) return false;
+  return true;
+}
+constexpr uint32_t kLogMax = 13;  // transforms up to 2^13 points
+// x mod p for a 256-bit integer given as 8 little-endian limbs
+static uint32_t limbs_mod(const uint32_t* w, uint32_t p) {
+  uint64_t r = 0;
+  for (int l = 7; l >= 0; --l) r = ((r << 32) | w[l]) % p;
+  return (uint32_t)r;
+}
+}  // namespace crt
+
+static int ctx_crt_consts(lf_ctx* ctx) {
+  if (ctx->d_crt_consts) return 0;
+  const P256Host& H = p256_host();
+  // the 17 largest primes k 2^13 + 1 below 2^31 and, for each, an element of order 2^13
+  std::vector<uint32_t> pr, wr;
+  for (uint32_t k = (1u << (31 - crt::kLogMax)) - 1; pr.size() < (size_t)kCrtPrimes; --k) {
+    const uint32_t p = (k << crt::kLogMax) + 1;
+    if (!crt::is_prime(p)) continue;
+    uint32_t g = 2;
+    for (;; ++g) {
+      if (crt::powmod(g, (p - 1) / 2, p) == 1) continue;  // a quadratic residue cannot have full 2-power order
+      const uint32_t w = crt::powmod(g, (p - 1) >> crt::kLogMax, p);
+      if (crt::powmod(w, 1u << (crt::kLogMax - 1), p) == p - 1) {
+        wr.push_back(w);
+        break;
+      }
+    }
+    pr.push_back(p);
+  }
+  auto small = [&](uint32_t v) {
+    fpw<8> r = H.zero();
+    r.w[0] = v;
+    return r;
+  };
+  fpw<8> rsq;
+  for (int i = 0; i < 8; ++i) rsq.w[i] = H.C.rsq[i];
+  // raw integers modulo P: a*b = mul(mul(a, R^2), b);  a*R^-1 = mul(a, 1)
+  auto mulraw = [&](const fpw<8>& a, const fpw<8>& b) { return H.mul(H.mul(a, rsq), b); };
+  CrtConsts cc;
+  memset(&cc, 0, sizeof(cc));
+  for (int j = 0; j < kCrtPrimes; ++j) {
+    const uint32_t p = pr[j];
+    CrtPrime& q = cc.pr[j];
+    q.p = p;
+    uint32_t inv = p;  // Newton: p * inv = 1 mod 2^32
+    for (int it = 0; it < 5; ++it) inv *= 2 - p * inv;
+    q.pinv = inv;
+    uint64_t t = ((uint64_t)1 << 32) % p;  // 2^32 mod p
+    const uint32_t r32 = (uint32_t)t;
+    uint32_t cur = r32;  // 2^(32 l) * 2^32 for l = 0
+    for (int l = 0; l < 8; ++l) {
+      q.k[l] = cur;
+      cur = crt::mulmod(cur, r32, p);
+    }
+    q.f = (uint32_t)(((uint64_t)1 << kCrtQBits) / p);
+    fpw<8> x = small(1);
+    for (int i = 0; i < kCrtPrimes; ++i)
+      if (i != j) x = mulraw(x, small(pr[i]));
+    const fpw<8> c = H.mul(x, small(1));  // (M / p_j) R^-1 mod P
+    for (int l = 0; l < 8; ++l) cc.C[j][l] = c.w[l];
+  }
+  {
+    fpw<8> x = small(1);
+    for (int i = 0; i < kCrtPrimes; ++i) x = mulraw(x, small(pr[i]));
+    const fpw<8> dd = H.mul(x, small(1));  // M R^-1 mod P
+    fpw<8> e = H.zero();
+    for (int q = 0; q <= kCrtPrimes; ++q) {
+      for (int l = 0; l < 8; ++l) cc.E[q][l] = e.w[l];
+      e = H.sub(e, dd);
+    }
+  }
+  LF_CUDA(cudaMalloc(&ctx->d_crt_consts, sizeof(cc)));
+  LF_CUDA(cudaMemcpy(ctx->d_crt_consts, &cc, sizeof(cc), cudaMemcpyHostToDevice));
+  ctx->crt_p = pr;
+  ctx->crt_w = wr;
+  return 0;
+}
+
+// forward / inverse twiddles w^k 2^32 mod p, k < N/2, for every prime
+static int ctx_crt_twiddles(lf_ctx* ctx, uint32_t logN, uint32_t** f, uint32_t** b) {
+  auto it = ctx->crt_tw.find(logN);
+  if (it == ctx->crt_tw.end()) {
+    const uint32_t N = 1u << logN, half = N / 2;
+    std::vector<uint32_t> tf((size_t)kCrtPrimes * half), tb((size_t)kCrtPrimes * half);
+    for (int j = 0; j < kCrtPrimes; ++j) {
+      const uint32_t p = ctx->crt_p[j];
+      const uint32_t w = crt::powmod(ctx->crt_w[j], 1u << (crt::kLogMax - logN), p), wi = crt::powmod(w, p - 2, p);
+      const uint32_t r32 = (uint32_t)(((uint64_t)1 << 32) % p);
+      uint32_t a = r32, c = r32;
+      for (uint32_t k = 0; k < half; ++k) {
+        tf[(size_t)j * half + k] = a;
+        tb[(size_t)j * half + k] = c;
+        a = crt::mulmod(a, w, p);
+        c = crt::mulmod(c, wi, p);
+      }
+    }
+    uint32_t *df = nullptr, *db = nullptr;
+    LF_CUDA(cudaMalloc(&df, tf.size() * 4));
+    LF_CUDA(cudaMalloc(&db, tb.size() * 4));
+    LF_CUDA(cudaMemcpy(df, tf.data(), tf.size() * 4, cudaMemcpyHostToDevice));
+    LF_CUDA(cudaMemcpy(db, tb.data(), tb.size() * 4, cudaMemcpyHostToDevice));
+    it = ctx->crt_tw.emplace(logN, std::make_pair(df, db)).first;
+  }
+  *f = it->second.first;
+  *b = it->second.second;
+  return 0;
+}
+
+// spectrum of the 1/i table modulo every prime, with N^-1, (M/p)^-1 and the Montgomery factor folded in,
+// in the bit-reversed order the DIF transform leaves
+static int ctx_crt_spectrum(lf_ctx* ctx, size_t n, size_t m, uint32_t logN, const std::vector<fpw<8>>& inv,
+                            uint32_t** out) {
+  auto key = std::make_pair(n, m);
+  auto it = ctx->crt_spec.find(key);
+  if (it == ctx->crt_spec.end()) {
+    const uint32_t N = 1u << logN;
+    std::vector<uint32_t> sp((size_t)kCrtPrimes * N);
+    std::vector<uint32_t> a(N);
+    for (int j = 0; j < kCrtPrimes; ++j) {
+      const uint32_t p = ctx->crt_p[j];
+      const uint32_t w = crt::powmod(ctx->crt_w[j], 1u << (crt::kLogMax - logN), p);
+      for (uint32_t i = 0; i < N; ++i) a[i] = i < m ? crt::limbs_mod(inv[i].w, p) : 0;
+      // the same decimation-in-frequency network as the kernel's
+      for (uint32_t s = 0; s < logN; ++s) {
+        const uint32_t lh = logN - 1 - s, half = 1u << lh;
+        std::vector<uint32_t> wp(half);
+        const uint32_t ws = crt::powmod(w, 1u << s, p);
+        wp[0] = 1;
+        for (uint32_t k = 1; k < half; ++k) wp[k] = crt::mulmod(wp[k - 1], ws, p);
+        for (uint32_t t = 0; t < N / 2; ++t) {
+          const uint32_t lo = t & (half - 1), i0 = ((t >> lh) << (lh + 1)) + lo, i1 = i0 + half;
+          const uint32_t x = a[i0], y = a[i1];
+          a[i0] = (x + y) % p;
+          a[i1] = crt::mulmod((x + p - y) % p, wp[lo], p);
+        }
+      }
+      uint32_t mj = 1;  // (M / p_j) mod p_j
+      for (int i = 0; i < kCrtPrimes; ++i)
+        if (i != j) mj = crt::mulmod(mj, ctx->crt_p[i] % p, p);
+      uint32_t scale = crt::powmod(mj, p - 2, p);
+      scale = crt::mulmod(scale, crt::powmod(N % p, p - 2, p), p);
+      scale = crt::mulmod(scale, (uint32_t)(((uint64_t)1 << 32) % p), p);
+      for (uint32_t i = 0; i < N; ++i) sp[(size_t)j * N + i] = crt::mulmod(a[i], scale, p);
+    }
+    uint32_t* d = nullptr;
+    LF_CUDA(cudaMalloc(&d, sp.size() * 4));
+    LF_CUDA(cudaMemcpy(d, sp.data(), sp.size() * 4, cudaMemcpyHostToDevice));
+    it = ctx->crt_spec.emplace(key, d).first;
+  }
+  *out = it->second;
+  return 0;
+}
+
+static int launch_rs_p256_crt(lf_ctx* ctx, fpw<8>* d_rows, size_t row_stride, size_t nrows, size_t batch_stride,
+                              size_t nbatch, size_t n, size_t m, const RsFpTables* t) {
+  uint32_t logN = 1;
+  while (((size_t)1 << logN) < m) ++logN;
+  int rc = ctx_crt_consts(ctx);
+  if (rc) return rc;
+  uint32_t *twf, *twb, *spec;
+  if ((rc = ctx_crt_twiddles(ctx, logN, &twf, &twb))) return rc;
+  auto sit = ctx->crt_spec.find(std::make_pair(n, m));
+  if (sit == ctx->crt_spec.end()) {
+    std::vector<fpw<8>> inv, lead, binom;
+    rs_tables_host(p256_host(), n, m, inv, lead, binom);
+    if ((rc = ctx_crt_spectrum(ctx, n, m, logN, inv, &spec))) return rc;
+  } else {
+    spec = sit->second;
+  }
+  const size_t smem = (8 * n + ((size_t)1 << logN) + ((size_t)1 << logN) / 32 + 32) * 4;
+  if (!(ctx->attr_mask & kAttrRsCrt)) {
+    LF_CUDA(cudaFuncSetAttribute(k_rs_crt_rows<FFp256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    ctx->attr_mask |= kAttrRsCrt;
+  }
+  // residue scratch: rows in chunks that keep it bounded (batches, then rows of a batch)
+  const size_t per_row = (size_t)kCrtPrimes * (m - n) * 4;
+  const size_t max_rows = std::max<size_t>(1, kWorkChunkBytes / per_row);
+  uint32_t* scratch;
+  const size_t total = nrows * nbatch;
+  if ((rc = ctx_work(ctx, 0, std::min(total, max_rows) * per_row, (void**)&scratch))) return rc;
+  const size_t bstep = std::max<size_t>(1, max_rows / nrows);  // whole batches per launch
+  if (nrows > max_rows) return fail(LF_ERR_UNSUPPORTED, "rs: too many rows per batch for the CRT path");
+  for (size_t b0 = 0; b0 < nbatch; b0 += bstep) {
+    const size_t nb = std::min(bstep, nbatch - b0);
+    k_rs_crt_rows<FFp256><<<dim3((unsigned)nrows, (unsigned)nb), 256, smem, ctx->stream>>>(
+        d_rows + b0 * batch_stride, row_stride, batch_stride, (uint32_t)n, (uint32_t)m, logN,
+        (const CrtConsts*)ctx->d_crt_consts, twf, twb, spec, t->d_lead, t->d_binom, scratch);
+    ctx->launches++;
+  }
+  LF_CUDA(cudaGetLastError());
+  return 0;
+}
+
 static int rs_conv_run_p256(lf_ctx* ctx, fpw<8>* d_rows, size_t row_stride, size_t nrows, size_t batch_stride,
                             size_t nbatch, size_t n, size_t m);
 static int launch_rs_p256(lf_ctx* ctx, fpw<8>* d_rows, size_t row_stride, size_t nrows, size_t batch_stride,
@@ -636,6 +853,10 @@ static int launch_rs_p256(lf_ctx* ctx, fpw<8>* d_rows, size_t row_stride, size_t
   static const bool force_direct = getenv("LF_RS_DIRECT") != nullptr;
   const size_t fft_smem = ((size_t)64) << t->logM;
   // the direct Toeplitz sum costs n*(m-n) multiplications, the FFT ~ 10 N log N
+  // LF_RS_P256=fft keeps the Fp2 real-FFT kernel of round 1 (for comparison); default: the CRT transform
+  static const bool use_fft = getenv("LF_RS_P256") && !strcmp(getenv("LF_RS_P256"), "fft");
+  if (!force_direct && !use_fft && n * (m - n) > 4096 && m <= (1u << crt::kLogMax) && (8 * n + 3 * m) * 4 <= 200 * 1024)
+    return launch_rs_p256_crt(ctx, d_rows, row_stride, nrows, batch_stride, nbatch, n, m, t);
   if (!force_direct && n * (m - n) > 4096 && fft_smem <= 200 * 1024) {
     // one radix-4 group per thread and pass: M/4 threads (the 455 -> 909 rows of the Ligero
     // prove have M = 512: 128 threads and four CTAs per SM instead of 512 mostly idle threads)
@@ -1066,6 +1287,12 @@ void lf_ctx_destroy(lf_ctx* ctx) {
   cudaFree(ctx->d_tw);
   cudaFree(ctx->work[0]);
   cudaFree(ctx->work[1]);
+  cudaFree(ctx->d_crt_consts);
+  for (auto& kv : ctx->crt_tw) {
+    cudaFree(kv.second.first);
+    cudaFree(kv.second.second);
+  }
+  for (auto& kv : ctx->crt_spec) cudaFree(kv.second);
   if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
 }

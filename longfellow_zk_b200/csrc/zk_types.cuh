@@ -64,7 +64,10 @@ struct StepDesc {
 constexpr uint32_t kFlatHeavyRow = 48;     // entries of one row a pair thread still takes
 constexpr uint32_t kFlatHeavyChunk = 256;  // entries per heavy-row warp chunk
 constexpr uint32_t kFlatEvalWarps = 4;     // warps per CTA of k_sc_eval
-constexpr uint32_t kFlatEvalMinCta = 5;    // resident CTAs per SM the kernel is compiled for (register cap)
+#ifndef LF_EVAL_MINCTA
+#define LF_EVAL_MINCTA 5
+#endif
+constexpr uint32_t kFlatEvalMinCta = LF_EVAL_MINCTA;    // resident CTAs per SM the kernel is compiled for (register cap)
 // warps (bins of work) per proof of k_sc_eval, by batch size: a large batch fills the GPU with few warps per
 // proof; a handful of proofs of a large circuit (one mdoc hash proof is 72 M multiplications) need thousands
 constexpr uint32_t kFlatBinModes = 3;
