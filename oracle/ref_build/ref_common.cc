@@ -198,8 +198,13 @@ static int zk_verify_t(const Field& F, const RSF& rsf,
   ReadBuffer pb(proof, proof_len);
   if (!zkp->read(pb, F)) return 1;
   if (pb.remaining() != 0) return 2;
-  ZkVerifier<Field, RSF> ver(*c, rsf, rate, nreq, F);
   Transcript tv(tinit, tinit_len);
+  if (block_enc == 0) {
+    ZkVerifier<Field, RSF> ver(*c, rsf, rate, nreq, F);
+    ver.recv_commitment(*zkp, tv);
+    return ver.verify(*zkp, P, tv) ? 0 : 3;
+  }
+  ZkVerifier<Field, RSF> ver(*c, rsf, rate, nreq, block_enc, F);
   ver.recv_commitment(*zkp, tv);
   return ver.verify(*zkp, P, tv) ? 0 : 3;
 }

@@ -207,3 +207,28 @@ def test_full_batch_verifies(ctx, name, fid):
     st, why = lf.ZkVerifier(c).verify_batch(np.repeat(pub[None, :], B, axis=0), proofs)
     for i in range(B):
         assert (st[i] != 0) == (i in badset), (i, st[i], why[i])
+
+
+@pytest.mark.parametrize("rate,nreq,block_enc,tinit", [(4, 189, 0, b"test"), (7, 132, 4151, b"mdoc-style block_enc"),
+                                                       (2, 64, 0, b""), (16, 40, 0, b"x" * 100)])
+def test_verifier_other_ligero_parameters(ctx, oracle, ref, rate, nreq, block_enc, tinit):
+    """other (rate, nreq, block_enc) choices and transcript seeds: proofs of the oracle and of the GPU are
+    accepted under the same parameters, refused under the default ones, and the reference agrees"""
+    import longfellow_zk_b200 as lf
+    circ, wit = load("sha1_gf128")
+    c = lf.Circuit(ctx, 4, circ, rate=rate, nreq=nreq, block_enc=block_enc)
+    coins = rng_bytes(13, c.info["rng_bytes"])
+    po = oracle.Circuit(4, circ).prove(wit, coins, tinit=tinit, rate=rate, nreq=nreq, block_enc=block_enc)["proof"]
+    pg, st = lf.ZkProver(c).prove_batch(np.frombuffer(wit, np.uint8)[None, :], coins[None, :], tinit=tinit)
+    assert st[0] == 0 and pg[0] == po
+    bad = bytearray(po)
+    bad[len(bad) // 3] ^= 2
+    stv, _ = lf.ZkVerifier(c).verify_batch(None, [po, bytes(bad)], tinit=tinit)
+    assert stv[0] == 0 and stv[1] != 0
+    rc = ref.Circuit(4, circ)
+    assert rc.verify(b"", po, tinit=tinit, rate=rate, nreq=nreq, block_enc=block_enc) == 0
+    assert rc.verify(b"", bytes(bad), tinit=tinit, rate=rate, nreq=nreq, block_enc=block_enc) != 0
+    if (rate, nreq, block_enc) != (7, 132, 0):
+        c0 = lf.Circuit(ctx, 4, circ)
+        stv, _ = lf.ZkVerifier(c0).verify_batch(None, [po], tinit=tinit)
+        assert stv[0] != 0

@@ -28,7 +28,7 @@ def step(i):
 for i in range(S_MAX):
     step(i); step(i)
 torch.cuda.synchronize()
-for S in (1, 2, 3, 4, 5, 6):
+for S in ([int(x) for x in os.environ["LF_STREAMS"].split(",")] if os.environ.get("LF_STREAMS") else (1, 2, 3, 4, 5, 6)):
     K = 12
     torch.cuda.synchronize(); t0 = time.perf_counter()
     for k in range(K):
