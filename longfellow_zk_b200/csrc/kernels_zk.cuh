@@ -1278,15 +1278,37 @@ __device__ __forceinline__ void put_digest(uint8_t* dst, const uint32_t* be_word
 // all threads of a CTA; y in the layout of ZkBufs::y; msg: scratch for the message bytes
 // (>= 64 + 36 + (block + 2 dblock + r - block) kBytes ... i.e. what the arrays serialise to);
 // perm [n], mark [2n bytes] scratch; on return idx[0..nreq) and mark[n + idx] = 1, *gts updated.
+// mode 0: everything; 1: only assemble the message bytes in msg (k_lig_msg); 2: the message has been absorbed
+// by k_lig_hash (one thread per proof, for large batches), only the columns are drawn
 template <class F>
 __device__ __forceinline__ void lig_absorb_and_choose(const ZkDims& d, const typename F::Elt* __restrict__ y,
                                                       Transcript* gts, uint8_t* msg, uint32_t* perm, uint8_t* mark,
-                                                      uint32_t* idx, const AesTables* aes) {
+                                                      uint32_t* idx, const AesTables* aes, int mode = 0) {
   const uint32_t tid = threadIdx.x, nth = blockDim.x;
   const uint32_t n = d.block_ext;
-  const AesTables& s_aes = *aes;
-  for (uint32_t i = tid; i < n; i += nth) perm[i] = i;
-  for (uint32_t i = tid; i < 2 * n; i += nth) mark[i] = 0;
+  if (mode != 1) {
+    for (uint32_t i = tid; i < n; i += nth) perm[i] = i;
+    for (uint32_t i = tid; i < 2 * n; i += nth) mark[i] = 0;
+  }
+  if (mode == 2) {
+    __syncthreads();
+    if (tid == 0) {
+      Transcript ts = *gts;
+      ts.use_tables(aes);
+      ts.have_prf = 0;
+      for (uint32_t i = 0; i < d.nreq; ++i) {
+        uint32_t j = i + ts.nat(n - i);
+        uint32_t t = perm[i];
+        perm[i] = perm[j];
+        perm[j] = t;
+        idx[i] = perm[i];
+        mark[perm[i] + n] = 1;
+      }
+      *gts = ts;
+    }
+    __syncthreads();
+    return;
+  }
   // ---- the four response arrays enter the transcript (ligero_prover.h:84-146) ----
   // Their bytes are known up front, so only the 64 rounds per block have to be serial:
   // the CTA assembles the byte stream (the transcript's pending buffer bytes, the array
@@ -1334,6 +1356,7 @@ __device__ __forceinline__ void lig_absorb_and_choose(const ZkDims& d, const typ
     }
   }
   __syncthreads();
+  if (mode == 1) return;
   const uint32_t nblk = tbytes / 64;
   for (uint32_t c0 = 0; c0 < nblk; c0 += kChunk) {
     const uint32_t cnt = min(kChunk, nblk - c0);
@@ -1351,7 +1374,7 @@ __device__ __forceinline__ void lig_absorb_and_choose(const ZkDims& d, const typ
   }
   if (tid == 0) {
     Transcript ts = *gts;
-    ts.use_tables(&s_aes);
+    ts.use_tables(aes);
     ts.have_prf = 0;  // a write drops the challenge stream (transcript.h:174-178)
     for (int k = 0; k < 8; ++k) ts.sha.h[k] = s_h[k];
     ts.sha.len = s_len0 + (tbytes - pos0);
@@ -1372,12 +1395,58 @@ __device__ __forceinline__ void lig_absorb_and_choose(const ZkDims& d, const typ
   __syncthreads();
 }
 
+// Large batches: the responses enter the transcript in two steps.  k_lig_msg (one CTA per proof) assembles the
+// byte stream at the start of the output slot; k_lig_hash (one THREAD per proof: a warp hashes 32 proofs in
+// lockstep) runs the compressions.  In k_lig_finish one thread of a 128-thread CTA runs them, which is the
+// faster way for a handful of proofs and 17x the issue slots for a thousand.
+template <class F>
+__global__ void __launch_bounds__(128, 8)
+k_lig_msg(ZkDims d, ZkBufs<typename F::Elt> b) {
+  const size_t p = blockIdx.x;
+  if (b.status[p] != 0) return;
+  lig_absorb_and_choose<F>(d, b.y + p * (size_t)(d.block + 2 * d.dblock),
+                           reinterpret_cast<Transcript*>(b.ts + p * sizeof(Transcript)), b.out + p * b.out_stride, nullptr,
+                           nullptr, nullptr, nullptr, 1);
+}
+// msg: per proof msg_stride bytes as k_lig_msg / lig_absorb_and_choose(mode 1) left them: the transcript's pending
+// bytes, then the four arrays with their headers; kbytes = bytes per element
+__global__ void __launch_bounds__(32)
+k_lig_hash(ZkDims d, uint8_t* ts_base, const uint8_t* msg, size_t msg_stride, const int32_t* status, uint32_t kbytes,
+           size_t nproofs) {
+  const size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= nproofs || status[p] != 0) return;
+  Transcript* gts = reinterpret_cast<Transcript*>(ts_base + p * sizeof(Transcript));
+  uint32_t h[8];
+  for (int k = 0; k < 8; ++k) h[k] = gts->sha.h[k];
+  const uint64_t len0 = gts->sha.len;
+  const uint32_t pos0 = (uint32_t)(len0 & 63);
+  const uint32_t tbytes = pos0 + 4 * 9 + (2 * d.dblock + d.r) * kbytes;
+  const uint32_t nblk = tbytes / 64;
+  const uint32_t* m32 = reinterpret_cast<const uint32_t*>(msg + p * msg_stride);
+  for (uint32_t j = 0; j < nblk; ++j) {
+    uint32_t w[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) w[k] = bswap32(m32[16 * (size_t)j + k]);
+    sha256_compress(h, w);
+  }
+  for (int k = 0; k < 8; ++k) gts->sha.h[k] = h[k];
+  gts->sha.len = len0 + (tbytes - pos0);
+  const uint8_t* mb = msg + p * msg_stride;
+  uint32_t buf[16];
+#pragma unroll
+  for (int k = 0; k < 16; ++k) buf[k] = 0;
+  for (uint32_t k = nblk * 64; k < tbytes; ++k) buf[(k & 63) >> 2] |= (uint32_t)mb[k] << (24 - 8 * (k & 3));
+#pragma unroll
+  for (int k = 0; k < 16; ++k) gts->sha.buf[k] = buf[k];
+  gts->have_prf = 0;
+}
+
 // 128 threads, 8 CTAs per SM: the kernel is bound by one thread per proof running the
 // SHA-256 rounds, so a whole batch of 1024 proofs should be resident at once (at 256
 // threads and 124 registers only 2 CTAs fitted an SM: 3.5 waves).
 template <class F>
 __global__ void __launch_bounds__(128, 8)
-k_lig_finish(ZkDims d, ZkBufs<typename F::Elt> b, const LayerDesc* __restrict__ layers) {
+k_lig_finish(ZkDims d, ZkBufs<typename F::Elt> b, const LayerDesc* __restrict__ layers, int hashed) {
   typedef typename F::Elt Elt;
   const size_t p = blockIdx.x;
   if (b.status[p] != 0) {
@@ -1406,7 +1475,7 @@ k_lig_finish(ZkDims d, ZkBufs<typename F::Elt> b, const LayerDesc* __restrict__ 
   aes_stage_tables(&s_aes);
 
   lig_absorb_and_choose<F>(d, y, reinterpret_cast<Transcript*>(b.ts + p * sizeof(Transcript)), out, perm, mark, idx,
-                           &s_aes);
+                           &s_aes, hashed ? 2 : 0);
   // compressed_merkle_proof_tree (merkle_tree.h:75-98), level by level
   if (n >= 2) {
     int top = 31 - __clz(n - 1);
