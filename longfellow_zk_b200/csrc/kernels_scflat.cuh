@@ -370,4 +370,117 @@ k_sc_bind(ZkDims d, ZkBufs<typename F::Elt> b, const uint32_t* __restrict__ aren
   }
 }
 
+// ----------------------------------------------------------------------------
+// k_sc_bind_tab: k_sc_bind over GF(2^128) with the products by the round's challenge taken from a table.
+// Every product of a bind round has the same factor r (per proof), so the CTA builds
+//   T[w][b] = r * b(x) * x^(8w)  mod  x^128 + x^7 + x^2 + x + 1,      w < 16, b < 256      (64 KB)
+// once -- 128 basis elements r x^k by a shift and the usual fold, the rest as XORs of them -- and then
+// r * v = XOR_w T[w][byte w of v]: 16 LDS.128 and 16 XORs instead of 144 IMAD.WIDE + 251 LOP3.  Random
+// 16-byte reads conflict in the banks (about 9 clk per warp load), which makes the table form no faster
+// than the multiplier on its own -- but it runs on the shared-memory pipe, which the multiplier leaves
+// idle, so the elements of a thread alternate between the two forms (every `imad_every`-th goes to the
+// multiplier) and the two pipes work side by side.  Same field elements either way.
+// grid = (ceil((npair + n_out) / chunk), proofs), 256 threads, 64 KB dynamic shared memory.
+// ----------------------------------------------------------------------------
+__device__ __forceinline__ uint4 gf_tab_mul(const uint4* __restrict__ T, const gf128& v) {
+  uint4 acc = make_uint4(0, 0, 0, 0);
+#pragma unroll
+  for (int w = 0; w < 16; ++w) {
+    const uint32_t byte = (v.w[w >> 2] >> (8 * (w & 3))) & 255u;
+    const uint4 e = T[w * 256 + byte];
+    acc.x ^= e.x;
+    acc.y ^= e.y;
+    acc.z ^= e.z;
+    acc.w ^= e.w;
+  }
+  return acc;
+}
+
+__global__ void __launch_bounds__(256, 3)
+k_sc_bind_tab(ZkDims d, ZkBufs<gf128> b, const uint32_t* __restrict__ arena, LayerDesc L, StepDesc S, uint32_t t,
+              uint32_t chunk, uint32_t imad_every) {
+  typedef FGf128 F;
+  extern __shared__ __align__(16) uint4 bt_tab[];
+  const size_t p = blockIdx.y;
+  if (b.status[p] != 0) return;
+  const uint32_t tid = threadIdx.x;
+  const gf128 r = reinterpret_cast<const ScCore<F>*>(b.scst + p * sizeof(ScCore<F>))->r;
+  // basis: r x^k, k < 128, at T[k / 8][1 << (k % 8)]; T[w][0] = 0
+  if (tid < 128) {
+    uint32_t wide[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) wide[i] = 0;
+    const uint32_t ws = tid >> 5, bs = tid & 31;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      wide[i + ws] |= r.w[i] << bs;
+      if (bs) wide[i + ws + 1] |= r.w[i] >> (32 - bs);
+    }
+    const gf128 e = gf_reduce(wide);
+    bt_tab[(tid >> 3) * 256 + (1u << (tid & 7))] = make_uint4(e.w[0], e.w[1], e.w[2], e.w[3]);
+  } else if (tid < 144) {
+    bt_tab[(tid - 128) * 256] = make_uint4(0, 0, 0, 0);
+  }
+  __syncthreads();
+  for (uint32_t e = tid; e < 4096; e += blockDim.x) {
+    const uint32_t w = e >> 8, j = e & 255;
+    if (__popc(j) < 2) continue;
+    uint4 acc = make_uint4(0, 0, 0, 0);
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+      if (j & (1u << k)) {
+        const uint4 x = bt_tab[w * 256 + (1u << k)];
+        acc.x ^= x.x;
+        acc.y ^= x.y;
+        acc.z ^= x.z;
+        acc.w ^= x.w;
+      }
+    bt_tab[e] = acc;
+  }
+  __syncthreads();
+  const uint32_t npair = (S.n0 + 1) / 2, total = npair + S.n_out;
+  const FlatPtrs<F> P(d, b, L, p, t);
+  const uint32_t i0 = blockIdx.x * chunk, i1 = min(total, i0 + chunk);
+  // operands of the next element are fetched before the current one is multiplied (the table lookups would
+  // otherwise wait behind the global loads)
+  auto fetch = [&](uint32_t i, gf128& f0, gf128& f1, gf128*& dst) {
+    if (i < npair) {
+      f0 = P.Wh[2 * i];
+      f1 = (2 * i + 1 < S.n0) ? P.Wh[2 * i + 1] : F::zero();
+      dst = &P.Wn[i];
+    } else {
+      const uint32_t j = i - npair, m = arena[S.merge + j], src = m >> 2, kind = m & 3;
+      const gf128 v = P.HQ[src];
+      f0 = kind == 2 ? F::zero() : v;
+      f1 = kind == 0 ? P.HQ[src + 1] : (kind == 2 ? v : F::zero());
+      dst = &P.HQn[j];
+    }
+  };
+  uint32_t k = 0;
+  uint32_t i = i0 + tid;
+  gf128 f0, f1, nf0, nf1;
+  gf128 *dst = nullptr, *ndst = nullptr;
+  if (i < i1) fetch(i, f0, f1, dst);
+  for (; i < i1; i += blockDim.x, ++k) {
+    const uint32_t inext = i + blockDim.x;
+    if (inext < i1) fetch(inext, nf0, nf1, ndst);
+    // affine_interpolation: f0 + r (f1 - f0)
+    const gf128 dlt = gf_add(f0, f1);
+    gf128 o;
+    if (imad_every && (k % imad_every) == imad_every - 1) {
+      o = gf_add(f0, F::mul(r, dlt));
+    } else {
+      const uint4 pr = gf_tab_mul(bt_tab, dlt);
+      o.w[0] = f0.w[0] ^ pr.x;
+      o.w[1] = f0.w[1] ^ pr.y;
+      o.w[2] = f0.w[2] ^ pr.z;
+      o.w[3] = f0.w[3] ^ pr.w;
+    }
+    *dst = o;
+    f0 = nf0;
+    f1 = nf1;
+    dst = ndst;
+  }
+}
+
 }  // namespace lf

@@ -382,7 +382,7 @@ struct lf_ctx {
   void* work[2] = {nullptr, nullptr};
   size_t work_cap[2] = {0, 0};
 };
-enum { kAttrRsGf = 1, kAttrRsFp = 2, kAttrScCluster = 4 /* and 8: the prime-field cluster kernel */, kAttrRsCrt = 16 };
+enum { kAttrRsGf = 1, kAttrRsFp = 2, kAttrScCluster = 4 /* and 8: the prime-field cluster kernel */, kAttrRsCrt = 16, kAttrBindTab = 32 };
 
 namespace lf {
 
