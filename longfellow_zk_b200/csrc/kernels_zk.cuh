@@ -333,6 +333,18 @@ __global__ void k_zk_transcript_export(ZkBufs<typename F::Elt> b, TranscriptStat
   reinterpret_cast<const Transcript*>(b.ts + p * sizeof(Transcript))->export_state(ext + p);
 }
 
+template <class F>
+__device__ __forceinline__ typename F::Elt warp_sum(typename F::Elt s) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    typename F::Elt t;
+#pragma unroll
+    for (int k = 0; k < F::kWords; ++k) t.w[k] = __shfl_xor_sync(0xffffffffu, s.w[k], o);
+    s = F::add(s, t);
+  }
+  return s;
+}
+
 // ----------------------------------------------------------------------------
 // k_zk_eval_layer: V[g] = sum over the quad terms of gate g of v * W[l] * W[r]
 // (prover_layers.h:278-305), gathered through the CSR-by-gate plan.  Assert-zero
@@ -345,15 +357,10 @@ k_zk_eval_layer(ZkDims d, ZkBufs<typename F::Elt> b, const uint32_t* __restrict_
   typedef typename F::Elt Elt;
   const size_t p = blockIdx.y;
   const uint32_t gi = blockIdx.x * blockDim.x + threadIdx.x;
-  if (gi >= L.nout) return;
-  const uint32_t g = arena[L.ev_perm + gi];
   const Elt* W = b.wl + p * d.wl_elts + L.w_off;
   const uint32_t* off = arena + L.ev_off;
   const uint32_t *h0 = arena + L.ev_h0, *h1 = arena + L.ev_h1, *vi = arena + L.ev_vi;
-  typename F::Acc acc;
-  F::acc_zero(acc);
-  bool bad = false;
-  for (uint32_t t = off[g]; t < off[g + 1]; ++t) {
+  auto term = [&](typename F::Acc& acc, bool& bad, uint32_t t) {
     uint32_t v = vi[t];
     Elt x = F::mul(W[h1[t]], W[h0[t]]);
     if (v & kViZero) {
@@ -363,14 +370,45 @@ k_zk_eval_layer(ZkDims d, ZkBufs<typename F::Elt> b, const uint32_t* __restrict_
     } else {
       F::mac(acc, consts[v & kViMask], x);
     }
+  };
+  auto finish = [&](uint32_t g, const Elt& out, bool bad) {
+    if (is_output) {
+      bad |= !F::is_zero(out);  // zk_prover.h:117-122: all outputs must be zero
+    } else {
+      b.wl[p * d.wl_elts + L.out_off + g] = out;
+    }
+    if (bad) atomicCAS(&b.status[p], 0, -5);
+  };
+  // Gates are ordered by decreasing term count, so a warp's heaviest gate is its first lane's.  A few gates
+  // sum hundreds of terms (the ECDSA circuit has one with 769): a warp whose first gate is that heavy takes its
+  // gates one after the other with all 32 lanes on the terms, instead of leaving 31 lanes waiting for one.
+  const uint32_t gi0 = gi & ~31u;
+  uint32_t heavy = 0;
+  if (gi0 < L.nout) {
+    const uint32_t g0 = arena[L.ev_perm + gi0];
+    heavy = off[g0 + 1] - off[g0];
   }
-  Elt out = F::reduce(acc);
-  if (is_output) {
-    bad |= !F::is_zero(out);  // zk_prover.h:117-122: all outputs must be zero
-  } else {
-    b.wl[p * d.wl_elts + L.out_off + g] = out;
+  if (heavy > 64) {
+    const uint32_t lane = threadIdx.x & 31;
+    for (uint32_t k = 0; k < 32 && gi0 + k < L.nout; ++k) {
+      const uint32_t g = arena[L.ev_perm + gi0 + k];
+      typename F::Acc acc;
+      F::acc_zero(acc);
+      bool bad = false;
+      for (uint32_t t = off[g] + lane; t < off[g + 1]; t += 32) term(acc, bad, t);
+      const Elt out = warp_sum<F>(F::reduce(acc));
+      bad = __any_sync(0xffffffffu, bad);
+      if (lane == 0) finish(g, out, bad);
+    }
+    return;
   }
-  if (bad) atomicCAS(&b.status[p], 0, -5);
+  if (gi >= L.nout) return;
+  const uint32_t g = arena[L.ev_perm + gi];
+  typename F::Acc acc;
+  F::acc_zero(acc);
+  bool bad = false;
+  for (uint32_t t = off[g]; t < off[g + 1]; ++t) term(acc, bad, t);
+  finish(g, F::reduce(acc), bad);
 }
 
 // ----------------------------------------------------------------------------
@@ -460,18 +498,6 @@ __device__ __noinline__ void sc_load(ScShared<F>* sh, const ScCore<F>* g) {
   sh->wc[0] = g->wc[0];
   sh->wc[1] = g->wc[1];
   sh->fail = g->fail;
-}
-
-template <class F>
-__device__ __forceinline__ typename F::Elt warp_sum(typename F::Elt s) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    typename F::Elt t;
-#pragma unroll
-    for (int k = 0; k < F::kWords; ++k) t.w[k] = __shfl_xor_sync(0xffffffffu, s.w[k], o);
-    s = F::add(s, t);
-  }
-  return s;
 }
 
 // Work distribution of one proof: CL == false, one CTA (tid/nth); CL == true, a
