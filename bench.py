@@ -384,9 +384,12 @@ def run_ours(args):
         raise SystemExit("bench.py: no CUDA device; the prover has no CPU fallback")
     torch.cuda.set_device(local)
     dist = None
+    # stdout is the one JSON line: whatever a library prints there (NCCL's version / INFO lines under NCCL_DEBUG,
+    # which stays as the driver set it) is sent to stderr at the file-descriptor level
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     if world > 1:
-        # NCCL's own log lines (NCCL_DEBUG=VERSION/INFO) go to stderr, so that stdout stays the one JSON line
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
@@ -763,8 +766,8 @@ def run_ours(args):
                 gpu_launches=launches, roofline=roofline, cpu_baseline=cpu,
                 latency_ms_per_proof_batch1=lat_ms, verifier=sha_verifier,
                 ms_per_proof=ms_total / args.steps / B, other_workloads=other)
-    print(json.dumps(line))
     sys.stdout.flush()
+    os.write(real_stdout, (json.dumps(line) + "\n").encode())
     if dist is not None:
         dist.destroy_process_group()
 
