@@ -1308,33 +1308,46 @@ uint64_t lf_ctx_launch_count(const lf_ctx* ctx) { return ctx ? ctx->launches : 0
 }  // extern "C"
 
 namespace {
+// a device allocation that is freed on every way out of a function (LF_CUDA returns early on errors)
+struct DevBuf {
+  void* p = nullptr;
+  DevBuf() {}
+  DevBuf(const DevBuf&) = delete;
+  DevBuf& operator=(const DevBuf&) = delete;
+  ~DevBuf() {
+    if (p) cudaFree(p);
+  }
+  cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, std::max<size_t>(bytes, 16)); }
+  template <class T>
+  T* as() const { return static_cast<T*>(p); }
+  void* release() {
+    void* q = p;
+    p = nullptr;
+    return q;
+  }
+};
+
 // host wire buffer -> device elements (Montgomery for prime fields)
 template <class F>
 int upload_elts(lf_ctx* ctx, const void* host, size_t n, typename F::Elt** d_out) {
-  typename F::Elt* d;
-  LF_CUDA(cudaMalloc(&d, std::max<size_t>(n, 1) * sizeof(typename F::Elt)));
+  DevBuf d, raw, bad;
+  LF_CUDA(d.alloc(std::max<size_t>(n, 1) * sizeof(typename F::Elt)));
   if (F::kChar2) {
-    LF_CUDA(cudaMemcpyAsync(d, host, n * F::kBytes, cudaMemcpyHostToDevice, ctx->stream));
+    LF_CUDA(cudaMemcpyAsync(d.p, host, n * F::kBytes, cudaMemcpyHostToDevice, ctx->stream));
   } else {
-    uint8_t* raw;
-    int* bad;
-    LF_CUDA(cudaMalloc(&raw, std::max<size_t>(n, 1) * F::kBytes));
-    LF_CUDA(cudaMalloc(&bad, sizeof(int)));
-    LF_CUDA(cudaMemsetAsync(bad, 0, sizeof(int), ctx->stream));
-    LF_CUDA(cudaMemcpyAsync(raw, host, n * F::kBytes, cudaMemcpyHostToDevice, ctx->stream));
-    k_from_wire<F><<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(raw, d, n, bad);
+    LF_CUDA(raw.alloc(std::max<size_t>(n, 1) * F::kBytes));
+    LF_CUDA(bad.alloc(sizeof(int)));
+    LF_CUDA(cudaMemsetAsync(bad.p, 0, sizeof(int), ctx->stream));
+    LF_CUDA(cudaMemcpyAsync(raw.p, host, n * F::kBytes, cudaMemcpyHostToDevice, ctx->stream));
+    k_from_wire<F><<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(raw.as<uint8_t>(), d.as<typename F::Elt>(), n,
+                                                                      bad.as<int>());
     ctx->launches++;
     int hbad = 0;
-    LF_CUDA(cudaMemcpyAsync(&hbad, bad, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    LF_CUDA(cudaMemcpyAsync(&hbad, bad.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     LF_CUDA(cudaStreamSynchronize(ctx->stream));
-    cudaFree(raw);
-    cudaFree(bad);
-    if (hbad) {
-      cudaFree(d);
-      return fail(LF_ERR_FORMAT, "element is not canonical (>= modulus)");
-    }
+    if (hbad) return fail(LF_ERR_FORMAT, "element is not canonical (>= modulus)");
   }
-  *d_out = d;
+  *d_out = static_cast<typename F::Elt*>(d.release());
   return 0;
 }
 template <class F>
@@ -1342,13 +1355,12 @@ int download_elts(lf_ctx* ctx, const typename F::Elt* d, size_t n, void* host) {
   if (F::kChar2) {
     LF_CUDA(cudaMemcpyAsync(host, d, n * F::kBytes, cudaMemcpyDeviceToHost, ctx->stream));
   } else {
-    uint32_t* raw;
-    LF_CUDA(cudaMalloc(&raw, std::max<size_t>(n, 1) * F::kBytes));
-    k_to_wire<F><<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(d, raw, n);
+    DevBuf raw;
+    LF_CUDA(raw.alloc(std::max<size_t>(n, 1) * F::kBytes));
+    k_to_wire<F><<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(d, raw.as<uint32_t>(), n);
     ctx->launches++;
-    LF_CUDA(cudaMemcpyAsync(host, raw, n * F::kBytes, cudaMemcpyDeviceToHost, ctx->stream));
+    LF_CUDA(cudaMemcpyAsync(host, raw.p, n * F::kBytes, cudaMemcpyDeviceToHost, ctx->stream));
     LF_CUDA(cudaStreamSynchronize(ctx->stream));
-    cudaFree(raw);
   }
   LF_CUDA(cudaStreamSynchronize(ctx->stream));
   return 0;
@@ -1389,12 +1401,14 @@ int merkle_commit_t(lf_ctx* ctx, size_t nrow, size_t block_enc, size_t dblock, c
                     const uint8_t* nonces, uint8_t root_out[32], uint8_t* nodes_out) {
   size_t block_ext = block_enc - dblock;
   typename F::Elt* d_tab = nullptr;
-  uint8_t* d_nonce = nullptr;
-  uint32_t* d_nodes = nullptr;
   int rc = upload_elts<F>(ctx, tableau, nrow * block_enc, &d_tab);
   if (rc) return rc;
-  LF_CUDA(cudaMalloc(&d_nonce, block_ext * 32));
-  LF_CUDA(cudaMalloc(&d_nodes, 2 * block_ext * 32));
+  DevBuf tab_owner, nonce_buf, nodes_buf;
+  tab_owner.p = d_tab;
+  LF_CUDA(nonce_buf.alloc(block_ext * 32));
+  LF_CUDA(nodes_buf.alloc(2 * block_ext * 32));
+  uint8_t* d_nonce = nonce_buf.as<uint8_t>();
+  uint32_t* d_nodes = nodes_buf.as<uint32_t>();
   LF_CUDA(cudaMemsetAsync(d_nodes, 0, 2 * block_ext * 32, ctx->stream));
   LF_CUDA(cudaMemcpyAsync(d_nonce, nonces, block_ext * 32, cudaMemcpyHostToDevice, ctx->stream));
   rc = launch_merkle<F>(ctx, d_tab, 0, (uint32_t)nrow, (uint32_t)block_enc, (uint32_t)dblock, d_nonce, 0, d_nodes,
@@ -1417,9 +1431,6 @@ int merkle_commit_t(lf_ctx* ctx, size_t nrow, size_t block_enc, size_t dblock, c
     if (nodes_out)
       for (size_t i = 0; i < 2 * block_ext; ++i) put(nodes_out + 32 * i, i);
   }
-  cudaFree(d_tab);
-  cudaFree(d_nonce);
-  cudaFree(d_nodes);
   return rc;
 }
 }  // namespace
