@@ -57,3 +57,39 @@ def load_mdoc():
                 w_sig=rd("w_sig"), w_hash=rd("w_hash"), w_sig_mac=rd("w_sig_mac"), w_hash_mac=rd("w_hash_mac"),
                 coins=np.fromfile(os.path.join(d, "coins.bin"), np.uint8),
                 expect=json.load(open(os.path.join(d, "expect.json"))))
+
+
+def load_rfc_vector(oracle):
+    """The reference's own known-answer ZK test (tests/golden/make_golden_rfc.py): returns
+    (record, circuit bytes, witness bytes, coin stream, expected proof bytes).  `oracle` supplies the
+    GF(2^128) helpers (subfield embedding, multiply, LigeroParam) needed to rebuild the inputs the test
+    describes; the expected bytes are the reference's."""
+    rec = json.load(open(os.path.join(GOLDEN, "rfc_zk_vector1.json")))
+    gf = rec["field_id"]
+    circ = bytes.fromhex(rec["circuit"])
+    one = np.zeros((1, 16), np.uint8)
+    one[0, 0] = 1
+    x = np.zeros((1, 16), np.uint8)
+    x[0, 0] = 2
+    n, m = (oracle.gf128_of_scalar([s]) for s in rec["subfield_scalars"])
+    w3 = oracle.gf128_mul(oracle.elt_op(gf, "add", n, m), x)
+    wit = np.concatenate([one, n, m, w3]).tobytes()
+    # header of the circuit (proto/circuit_reader.h:83-120): 3-byte little-endian numbers after the version byte
+    num = lambda i: int.from_bytes(circ[1 + 3 * i:4 + 3 * i], "little")
+    npub, sb_abs, ninputs, nl = num(3), num(4), num(5), num(6)
+    assert nl == 1
+    logw = int.from_bytes(circ[1 + 3 * 8 + 16 * num(7):][:3], "little")
+    npad = 4 * logw + 2                      # fill_pad: zk_prover.h:152-188
+    nw, nq = (ninputs - npub) + npad + 1, nl
+    P = oracle.ligero_param(gf, nw, nq, rec["rate"], rec["nreq"], rec["block_enc"])
+    sb = max(sb_abs - npub, 0)
+    # every RandomEngine::bytes(n) call of the test returns 02 00 ... 00: 16 bytes per field element,
+    # 2 per subfield element (random/random.h:36-50), 32 per Merkle nonce (merkle_commitment.h:48-52)
+    e16, e2, n32 = b"\x02" + bytes(15), b"\x02\x00", b"\x02" + bytes(31)
+    st = e16 * npad + e16 * P["block"] + e16 * P["dblock"] * 2
+    for i in range(P["nwrow"]):
+        st += (e2 if (i + 1) * P["w"] <= sb else e16) * P["r"]
+    st += e16 * 3 * P["nqtriples"] * P["r"]
+    st += n32 * (P["block_ext"])
+    want = bytes.fromhex(rec["commitment"] + rec["sumcheck_proof"] + rec["ligero_proof"])
+    return rec, circ, wit, np.frombuffer(st, np.uint8).copy(), want

@@ -154,3 +154,29 @@ def test_growing_and_shrinking_batches_on_one_circuit(sha, oracle):
         W = np.repeat(np.frombuffer(wit, np.uint8)[None, :], B, axis=0)
         proofs, status = p.prove_batch(W, rng)
         assert (status == 0).all() and proofs[0] == want, B
+
+
+def test_reference_known_answer_zk_vector(ctx, oracle):
+    """The reference's own known-answer test of the whole ZK prover (rust/runtime/zk/tests/zk.rs:228-558,
+    bytes from the C++ prover; tests/golden/rfc_zk_vector1.json): the GPU's proof of that 3-term circuit
+    with rate 4, nreq 6, block_enc 128 and the test's constant coins equals the recorded commitment,
+    sumcheck proof and Ligero proof, alone and in a batch, and the GPU verifier accepts it."""
+    import longfellow_zk_b200 as lf
+    from fixtures import load_rfc_vector
+    rec, circ, wit, coins, want = load_rfc_vector(oracle)
+    tinit = rec["transcript_seed"].encode()
+    c = lf.Circuit(ctx, rec["field_id"], circ, rate=rec["rate"], nreq=rec["nreq"], block_enc=rec["block_enc"])
+    assert c.info["rng_bytes"] == coins.size and c.info["max_proof_bytes"] >= len(want)
+    W = np.frombuffer(wit, np.uint8)
+    for B in (1, 70):
+        proofs, status = lf.ZkProver(c).prove_batch(np.repeat(W[None, :], B, axis=0),
+                                                    np.repeat(coins[None, :], B, axis=0), tinit=tinit)
+        assert (status == 0).all()
+        assert all(p == want for p in proofs), B
+    pub = np.frombuffer(wit[:16 * c.info["npub_in"]], np.uint8)[None, :]
+    status, why = lf.ZkVerifier(c).verify_batch(pub, [want], tinit=tinit)
+    assert status[0] == 0, why
+    bad = bytearray(want)
+    bad[40] ^= 1
+    status, why = lf.ZkVerifier(c).verify_batch(pub, [bytes(bad)], tinit=tinit)
+    assert status[0] != 0

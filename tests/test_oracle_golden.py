@@ -5,6 +5,8 @@ holds for this path:
   * rust/runtime/merkle/tests/{merkle,commitment}_test_vector.bin (C++-generated;
     layouts per rust/runtime/merkle/tests/merkle.rs:219-299,302-417)
   * tests/golden/golden.json: proofs produced by the unmodified reference
+  * tests/golden/rfc_zk_vector1.json: the reference's known-answer test of the whole ZK prover
+    (rust/runtime/zk/tests/zk.rs:228-558, bytes produced by the C++ prover)
 CPU only."""
 import hashlib
 import struct
@@ -203,6 +205,23 @@ def test_reference_golden_proofs(oracle):
             assert r["root"].hex() == pr["root"]
             assert len(r["proof"]) == pr["proof_len"]
             assert hashlib.sha256(r["proof"]).hexdigest() == pr["proof_sha256"]
+
+
+def test_reference_known_answer_zk_vector(oracle):
+    """rust/runtime/zk/tests/zk.rs:228-558 `test_zk_rfc_testvector1`: a 3-term circuit, rate 4, nreq 6,
+    block_enc 128, every RandomEngine call returning 02 00 ... 00.  Commitment root, sumcheck proof and
+    Ligero proof (subfield run-length coding included) are the bytes that test holds."""
+    from fixtures import load_rfc_vector
+    rec, circ, wit, coins, want = load_rfc_vector(oracle)
+    c = oracle.Circuit(rec["field_id"], circ)
+    assert c.id() == circ[-32:]
+    r = c.prove(wit, coins, tinit=rec["transcript_seed"].encode(), rate=rec["rate"], nreq=rec["nreq"],
+                block_enc=rec["block_enc"], dump=True)
+    assert r["rng_used"] == coins.size
+    assert r["root"] == bytes.fromhex(rec["commitment"])
+    assert r["proof"][32:32 + 160] == bytes.fromhex(rec["sumcheck_proof"])
+    assert r["proof"][192:] == bytes.fromhex(rec["ligero_proof"])
+    assert r["proof"] == want
 
 
 def test_lch14_known_answers(oracle):
