@@ -744,6 +744,29 @@ def run_ours(args):
     except Exception as ex:
         other.setdefault("mdoc", {})["cpu_baseline"] = dict(error=repr(ex))
 
+    # ---- mdoc verifier: the reference's run_mdoc_verifier, unchanged, with its two ZkVerifier objects on the
+    # host (libref_mdoc_gpu.so) and resolved to ZkVerifierGpu (libref_mdoc_gpuv.so); both calls decompress and
+    # parse the circuit file first, as run_mdoc_verifier does on every call (mdoc_zk.cc:549-716)
+    try:
+        from oracle import refapi
+        if "error" not in other.get("mdoc", {}) and refapi.mdoc_gpu_available() and refapi.mdoc_gpuv_available():
+            from fixtures import load_mdoc
+            circuit = refapi.zstd_compress(load_mdoc()["raw"])
+            A, V = refapi.mdoc_gpu_lib(), refapi.mdoc_gpuv_lib()
+            code, proof = refapi.mdoc_prove_claim(V, 0, circuit)
+            res = {}
+            for name, L in (("reference_1thread", A), ("gpu", V)):
+                rc = refapi.mdoc_verify_claim(L, 0, circuit, proof)   # warm: device copy of the circuits cached
+                t0 = time.perf_counter()
+                for _ in range(3):
+                    rc |= refapi.mdoc_verify_claim(L, 0, circuit, proof)
+                res[name + "_ms"] = 1e3 * (time.perf_counter() - t0) / 3
+                res[name + "_accepted"] = (code == 0 and rc == 0)
+            other["mdoc"]["verifier"] = dict(res, how="run_mdoc_verifier end to end (circuit file decompressed and "
+                                             "parsed by the reference's code inside every call), one proof")
+    except Exception as ex:
+        other.setdefault("mdoc", {})["verifier"] = dict(error=repr(ex))
+
     line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3),
                 ms_per_step=ms_total / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None,
                 dtype="gf2^128 (u32 limbs)", data="synthetic",

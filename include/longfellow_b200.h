@@ -252,6 +252,17 @@ int lf_zk_verify_batch(lf_circuit* c, size_t nproofs, const uint8_t* pub_inputs,
                        size_t proof_stride, const size_t* proof_lens, const uint8_t* tinit, size_t tinit_len,
                        int* status, int* why);
 
+/* ZkVerifier::verify on a caller-owned transcript (lib/zk/zk_verifier.h:69-106).  The reference's
+ * recv_commitment and verify take the caller's Transcript so that several proofs can be composed on one:
+ * run_mdoc_verifier does recv_commitment(hash), recv_commitment(sig), draws the MAC key, then verify(hash),
+ * verify(sig) (lib/circuits/mdoc/mdoc_zk.cc:673-706).  ts[i] in: the transcript that has already received
+ * this proof's commitment (recv_commitment is one write of the 32-byte root,
+ * lib/ligero/ligero_transcript.h:31-34: lf_transcript_write_bytes(&ts, root, 32)); out: the transcript as
+ * verify left it (after the draw of the opened columns).  Everything else as lf_zk_verify_batch. */
+int lf_zk_verify_committed_batch(lf_circuit* c, size_t nproofs, const uint8_t* pub_inputs, const uint8_t* proofs,
+                                 size_t proof_stride, const size_t* proof_lens, lf_transcript* ts, int* status,
+                                 int* why);
+
 /* Test hook, the analogue of BadReedSolomonFactory in lib/ligero/ligero_test.cc:114-160: make exactly one of the
  * verifier's own computations wrong so that each check of LigeroVerifier::verify can be seen to fire on an
  * otherwise valid proof.  fault: 0 none; 1 the interpolation of y_ldt (low_degree_check); 2 of y_dot

@@ -27,6 +27,9 @@
  *       exactly that (make mdoc_gpu -> oracle/_ref/libref_mdoc_gpu.so exports run_mdoc_prover with the
  *       signature of lib/circuits/mdoc/mdoc_zk.h:157-164).
  *
+ *   ZkVerifierGpu<Field, RSFactory>  drop-in for the reference's ZkVerifier<Field, RSFactory>
+ *       (lib/zk/zk_verifier.h:41-111), see the class comment; with it run_mdoc_verifier runs on the GPU.
+ *
  * oracle/ref_build/ref_common.cc compiles both against the unmodified
  * reference (make gpu -> oracle/_ref/libref_gpu.so); tests/test_gpu_adapters.py
  * checks that the reference's ZkProver running on GpuReedSolomonFactory, and
@@ -383,6 +386,70 @@ class ZkProverGpu {
   lf_circuit* circ_ = nullptr;
   lf_circuit_info info_{};
   std::vector<uint8_t> lfc1_;
+};
+
+/* Drop-in for the reference's ZkVerifier<Field, RSFactory> (lib/zk/zk_verifier.h:41-111): the same two
+ * constructors and the same
+ *     void recv_commitment(const ZkProof<Field>&, Transcript&) const;
+ *     bool verify(const ZkProof<Field>&, const Dense<Field>& pub, Transcript&) const;
+ * recv_commitment is the reference's one transcript write (lib/ligero/ligero_transcript.h:31-34) on the
+ * caller's Transcript; verify serialises the ZkProof with the reference's own ZkProof::write, carries the
+ * Transcript across the C ABI and back (lf_zk_verify_committed_batch) and returns the device's verdict.
+ * run_mdoc_verifier (lib/circuits/mdoc/mdoc_zk.cc:549-716: two verifiers over two fields on ONE transcript,
+ * MAC key drawn between recv_commitment and verify) compiles unchanged with `ZkVerifier` naming this class:
+ * oracle/ref_build/ref_mdoc_gpu.cc with -DLF_GPU_VERIFIER (make mdoc_gpu -> libref_mdoc_gpuv.so). */
+template <class Field, class RSFactory>
+class ZkVerifierGpu {
+ public:
+  ZkVerifierGpu(const proofs::Circuit<Field>& c, const RSFactory&, size_t rate, size_t nreq, const Field& F)
+      : c_(c), f_(F), rate_(rate), nreq_(nreq), block_enc_(0) {}
+  ZkVerifierGpu(const proofs::Circuit<Field>& c, const RSFactory&, size_t rate, size_t nreq, size_t block_enc,
+                const Field& F)
+      : c_(c), f_(F), rate_(rate), nreq_(nreq), block_enc_(block_enc) {}
+
+  void recv_commitment(const proofs::ZkProof<Field>& zk, proofs::Transcript& t) const {
+    t.write(zk.com.root.data, proofs::Digest::kLength);
+  }
+
+  bool verify(const proofs::ZkProof<Field>& zk, const proofs::Dense<Field>& pub, proofs::Transcript& tv) const {
+    /* the ZkProof was constructed with the verifier's parameters (it could not have been read otherwise);
+     * its LigeroParam holds the resolved block_enc, which is the key the prover's device copy is cached under */
+    proofs::check(zk.param.rateinv == rate_ && zk.param.nreq == nreq_ &&
+                      (block_enc_ == 0 || zk.param.block_enc == block_enc_),
+                  "ZkProof and ZkVerifier were constructed with different Ligero parameters");
+    lf_circuit* circ = cached_circuit(c_.id, (int)LfFieldId<Field>::value, rate_, nreq_, zk.param.block_enc,
+                                      &ZkVerifierGpu::serialize, const_cast<ZkVerifierGpu*>(this));
+    lfc1_.clear();
+    lfc1_.shrink_to_fit();
+    lf_circuit_info info;
+    lf_check(lf_circuit_get_info(circ, &info));
+    proofs::check(info.block_enc == zk.param.block_enc && info.nrow == zk.param.nrow &&
+                      info.block == zk.param.block,
+                  "Ligero parameters of the device circuit differ from the ZkProof's");
+    std::vector<uint8_t> bytes;
+    zk.write(bytes, f_);
+    std::vector<uint8_t> pubb(std::max<size_t>(info.npub_in * Field::kBytes, 1));
+    for (size_t k = 0; k < info.npub_in; ++k) f_.to_bytes_field(&pubb[k * Field::kBytes], pub.v_[k]);
+    lf_transcript ts;
+    transcript_export(tv, &ts);
+    const size_t len = bytes.size();
+    int st = 0, why = 0;
+    lf_check(lf_zk_verify_committed_batch(circ, 1, info.npub_in ? pubb.data() : nullptr, bytes.data(), len, &len, &ts,
+                                          &st, &why));
+    transcript_import(tv, ts);
+    return st == LF_OK;
+  }
+
+ private:
+  static const std::vector<uint8_t>& serialize(void* self) {
+    auto* p = static_cast<ZkVerifierGpu*>(self);
+    proofs::CircuitWriter<Field>(p->f_, LfFieldId<Field>::value).to_bytes(p->c_, p->lfc1_);
+    return p->lfc1_;
+  }
+  const proofs::Circuit<Field>& c_;
+  const Field& f_;
+  const size_t rate_, nreq_, block_enc_;
+  mutable std::vector<uint8_t> lfc1_;
 };
 
 }  // namespace longfellow_b200

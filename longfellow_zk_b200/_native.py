@@ -38,7 +38,7 @@ EXPORTS = [
     "lf_zk_prove_batch_dev", "lf_zk_debug_fetch", "lf_ctx_launch_count", "lf_microbench",
     "lf_circuit_set_profiling", "lf_circuit_get_stage_ms", "lf_fft", "lf_fft_time",
     "lf_zk_commit_batch", "lf_zk_prove_committed_batch", "lf_transcript_init", "lf_transcript_write_bytes",
-    "lf_transcript_challenge_bytes", "lf_zk_rng_consumed", "lf_circuit_verify_id", "lf_zk_verify_batch", "lf_zk_verify_set_fault", "lf_fft_time_rows", "lf_rs_time", "lf_circuit_get_kernel_ms",
+    "lf_transcript_challenge_bytes", "lf_zk_rng_consumed", "lf_circuit_verify_id", "lf_zk_verify_batch", "lf_zk_verify_committed_batch", "lf_zk_verify_set_fault", "lf_fft_time_rows", "lf_rs_time", "lf_circuit_get_kernel_ms",
 ]
 
 
@@ -100,6 +100,8 @@ def lib():
         L.lf_zk_verify_set_fault.argtypes = [C.c_void_p, C.c_int]
         L.lf_zk_verify_batch.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p,
                                          C.c_char_p, C.c_size_t, C.c_void_p, C.c_void_p]
+        L.lf_zk_verify_committed_batch.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_size_t,
+                                                   C.c_void_p, C.POINTER(Transcript), C.c_void_p, C.c_void_p]
         _lib = L
     return _lib
 

@@ -303,10 +303,13 @@ class ZkVerifier:
         """test hook (lf_zk_verify_set_fault): break one of the verifier's interpolations"""
         check(_native.lib().lf_zk_verify_set_fault(self.c._h, int(fault)))
 
-    def verify_batch(self, pub_inputs, proofs, tinit=b"test"):
+    def verify_batch(self, pub_inputs, proofs, tinit=b"test", transcripts=None):
         """pub_inputs: (B, npub_in*kBytes) uint8 (or None when the circuit has no public inputs); proofs: a list
         of B byte strings.  Returns (status, why) int32 arrays: status 0 accepted, LF_ERR_FORMAT (-3) not a
-        proof of this shape, LF_ERR_VERIFY (-8) rejected with why = index into WHY."""
+        proof of this shape, LF_ERR_VERIFY (-8) rejected with why = index into WHY.
+        transcripts: an array of B caller-owned transcripts that have already received the commitments
+        (recv_commitment); they continue and come back as ZkVerifier::verify leaves them
+        (lf_zk_verify_committed_batch); tinit is then unused."""
         info = self.c.info
         B = len(proofs)
         stride = max(16, max(len(p) for p in proofs))
@@ -322,6 +325,11 @@ class ZkVerifier:
             assert pub.shape[1] == pubb, pub.shape
         status = np.zeros(B, np.int32)
         why = np.zeros(B, np.int32)
+        if transcripts is not None:
+            check(_native.lib().lf_zk_verify_committed_batch(self.c._h, B, _p(pub) if pub is not None else None,
+                                                             _p(buf), stride, _p(lens), transcripts, _p(status),
+                                                             _p(why)))
+            return status, why
         check(_native.lib().lf_zk_verify_batch(self.c._h, B, _p(pub) if pub is not None else None, _p(buf), stride,
                                                _p(lens), tinit, len(tinit), _p(status), _p(why)))
         return status, why

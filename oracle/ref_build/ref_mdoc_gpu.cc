@@ -5,7 +5,8 @@
 // ZkProver's constructor and commit/prove signatures that runs on the GPU through the C ABI.  Everything
 // else of run_mdoc_prover -- CBOR parsing, witness filling, the MAC arithmetic, the Transcript, the
 // SecureRandomEngine, proof serialisation through ZkProof::write -- is the reference's own code, and so
-// is run_mdoc_verifier (ZkVerifier is not substituted), which the tests use to check the GPU's proofs.
+// is run_mdoc_verifier (ZkVerifier is not substituted unless LF_GPU_VERIFIER is defined, below), which the
+// tests use to check the GPU's proofs.
 // Exports run_mdoc_prover / run_mdoc_verifier with the signatures of lib/circuits/mdoc/mdoc_zk.h:157-189,
 // plus a small driver over the (claim, mdoc) pairs of lib/circuits/mdoc/mdoc_zk_test.cc:119-170.
 #include "zk/zk_prover.h"  // the reference's own ZkProver is defined first, under its own name
@@ -26,9 +27,20 @@ struct LfFieldId<proofs::Fp256Base> {
 };
 }  // namespace longfellow_b200
 
+// -DLF_GPU_VERIFIER (oracle/_ref/libref_mdoc_gpuv.so): `ZkVerifier` resolves to longfellow_b200::ZkVerifierGpu
+// as well, so run_mdoc_verifier -- CBOR/transcript handling, MAC checks and the two ZkVerifier objects on one
+// transcript, all the reference's own code -- verifies on the GPU too.  The tests load both libraries: proofs
+// made by either are checked by the reference's verifier (this file without the flag) and by the GPU's.
+#include "zk/zk_verifier.h"  // the reference's own ZkVerifier is defined first, under its own name
 #define ZkProver ::longfellow_b200::ZkProverGpu
+#ifdef LF_GPU_VERIFIER
+#define ZkVerifier ::longfellow_b200::ZkVerifierGpu
+#endif
 #include "circuits/mdoc/mdoc_zk.cc"  // NOLINT
 #undef ZkProver
+#ifdef LF_GPU_VERIFIER
+#undef ZkVerifier
+#endif
 
 #include "circuits/mdoc/mdoc_examples.h"
 #include "circuits/mdoc/mdoc_test_attributes.h"
@@ -102,5 +114,50 @@ int ref_mdoc_gpu_run_claim(size_t i, const uint8_t* circuit, size_t circuit_len,
                                                zkproof, len, t->doc_type, &zk_spec);
   free(zkproof);
   return (int)vr;
+}
+
+// the two halves separately, so that a proof made by one library can be checked by the other:
+// run_mdoc_prover for claim i into out (cap bytes); returns the prover's code
+int ref_mdoc_gpu_prove_claim(size_t i, const uint8_t* circuit, size_t circuit_len, uint8_t* out, size_t cap,
+                             size_t* proof_len) {
+  set_log_level(ERROR);
+  const Claim& c = kClaims[i];
+  const MdocTests* t = &mdoc_tests[c.mdoc];
+  const ZkSpecStruct zk_spec = kZkSpecs[0];
+  RequestedAttribute attrs[1] = {c.attr};
+  uint8_t* zkproof = nullptr;
+  size_t len = 0;
+  MdocProverErrorCode pr = run_mdoc_prover(circuit, circuit_len, t->mdoc, t->mdoc_size, t->pkx.as_pointer,
+                                           t->pky.as_pointer, t->transcript, t->transcript_size, attrs, 1,
+                                           (const char*)t->now, &zkproof, &len, &zk_spec);
+  if (pr != MDOC_PROVER_SUCCESS) return (int)pr;
+  *proof_len = len;
+  if (len > cap) {
+    free(zkproof);
+    return -1;
+  }
+  memcpy(out, zkproof, len);
+  free(zkproof);
+  return 0;
+}
+// run_mdoc_verifier for claim i on the given proof bytes; returns the verifier's code
+int ref_mdoc_gpu_verify_claim(size_t i, const uint8_t* circuit, size_t circuit_len, const uint8_t* proof,
+                              size_t proof_len) {
+  set_log_level(ERROR);
+  const Claim& c = kClaims[i];
+  const MdocTests* t = &mdoc_tests[c.mdoc];
+  const ZkSpecStruct zk_spec = kZkSpecs[0];
+  RequestedAttribute attrs[1] = {c.attr};
+  return (int)run_mdoc_verifier(circuit, circuit_len, t->pkx.as_pointer, t->pky.as_pointer, t->transcript,
+                                t->transcript_size, attrs, 1, (const char*)t->now, proof, proof_len, t->doc_type,
+                                &zk_spec);
+}
+// 1 when run_mdoc_verifier of this library runs on the GPU
+int ref_mdoc_gpu_verifier_is_gpu() {
+#ifdef LF_GPU_VERIFIER
+  return 1;
+#else
+  return 0;
+#endif
 }
 }  // extern "C"

@@ -344,13 +344,50 @@ def mdoc_gpu_available():
 def mdoc_gpu_lib():
     global _mdoc_gpu_lib
     if _mdoc_gpu_lib is None:
-        _mdoc_gpu_lib = C.CDLL(LIBREF_MDOC_GPU)
-        _mdoc_gpu_lib.ref_mdoc_gpu_nclaims.restype = C.c_size_t
-        _mdoc_gpu_lib.ref_mdoc_gpu_claim_name.restype = C.c_char_p
-        _mdoc_gpu_lib.ref_mdoc_gpu_claim_name.argtypes = [C.c_size_t]
-        _mdoc_gpu_lib.ref_mdoc_gpu_run_claim.argtypes = [C.c_size_t, C.c_char_p, C.c_size_t, C.POINTER(C.c_size_t),
-                                                         C.c_int]
+        _mdoc_gpu_lib = _mdoc_gpu_protos(C.CDLL(LIBREF_MDOC_GPU))
+        assert _mdoc_gpu_lib.ref_mdoc_gpu_verifier_is_gpu() == 0
     return _mdoc_gpu_lib
+
+
+def _mdoc_gpu_protos(L):
+    L.ref_mdoc_gpu_nclaims.restype = C.c_size_t
+    L.ref_mdoc_gpu_claim_name.restype = C.c_char_p
+    L.ref_mdoc_gpu_claim_name.argtypes = [C.c_size_t]
+    L.ref_mdoc_gpu_run_claim.argtypes = [C.c_size_t, C.c_char_p, C.c_size_t, C.POINTER(C.c_size_t), C.c_int]
+    L.ref_mdoc_gpu_prove_claim.argtypes = [C.c_size_t, C.c_char_p, C.c_size_t, C.c_void_p, C.c_size_t,
+                                           C.POINTER(C.c_size_t)]
+    L.ref_mdoc_gpu_verify_claim.argtypes = [C.c_size_t, C.c_char_p, C.c_size_t, C.c_char_p, C.c_size_t]
+    return L
+
+
+# the same with run_mdoc_verifier on the GPU too (ZkVerifier -> ZkVerifierGpu): oracle/_ref/libref_mdoc_gpuv.so
+LIBREF_MDOC_GPUV = os.path.join(_HERE, "_ref", "libref_mdoc_gpuv.so")
+_mdoc_gpuv_lib = None
+
+
+def mdoc_gpuv_available():
+    return os.path.exists(LIBREF_MDOC_GPUV)
+
+
+def mdoc_gpuv_lib():
+    global _mdoc_gpuv_lib
+    if _mdoc_gpuv_lib is None:
+        _mdoc_gpuv_lib = _mdoc_gpu_protos(C.CDLL(LIBREF_MDOC_GPUV))
+        assert _mdoc_gpuv_lib.ref_mdoc_gpu_verifier_is_gpu() == 1
+    return _mdoc_gpuv_lib
+
+
+def mdoc_prove_claim(L, i, circuit_zstd, cap=1 << 20):
+    """run_mdoc_prover of library L (either of the two above) for claim i: (code, proof bytes)"""
+    out = C.create_string_buffer(cap)
+    n = C.c_size_t()
+    rc = L.ref_mdoc_gpu_prove_claim(i, circuit_zstd, len(circuit_zstd), out, cap, C.byref(n))
+    return int(rc), out.raw[:n.value] if rc == 0 else b""
+
+
+def mdoc_verify_claim(L, i, circuit_zstd, proof):
+    """run_mdoc_verifier of library L for claim i on the given proof: the MdocVerifierErrorCode (0 = accepted)"""
+    return int(L.ref_mdoc_gpu_verify_claim(i, circuit_zstd, len(circuit_zstd), proof, len(proof)))
 
 
 def mdoc_gpu_run_claim(i, circuit_zstd, tamper=False):

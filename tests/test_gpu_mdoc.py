@@ -112,3 +112,36 @@ def test_run_mdoc_prover_drop_in_all_claims(ctx):
         lens.add(plen)
     code, _ = ref.mdoc_gpu_run_claim(0, circuit, tamper=True)
     assert code != 0 and code < 1000   # the prover succeeded, the verifier refused
+
+
+def test_run_mdoc_verifier_drop_in(ctx):
+    """N2 from the reference's side: run_mdoc_verifier compiled UNCHANGED with ZkVerifier resolved to
+    ZkVerifierGpu (include/longfellow_b200_adapters.h; ref_mdoc_gpu.cc -DLF_GPU_VERIFIER ->
+    libref_mdoc_gpuv.so): two verifiers over two fields on ONE caller transcript, the MAC key drawn between
+    recv_commitment and verify (mdoc_zk.cc:673-706), through lf_zk_verify_committed_batch.  For every
+    (claim, mdoc) pair of mdoc_zk_test.cc:119-170 the proof of run_mdoc_prover is accepted by the GPU
+    verifier; for a sample of them the reference's own verifier agrees, and a flipped byte anywhere in the
+    MACs, the hash proof or the signature proof is refused by both with the same code."""
+    from oracle import refapi as ref
+    if not (ref.mdoc_gpu_available() and ref.mdoc_gpuv_available()):
+        pytest.skip("oracle/_ref/libref_mdoc_gpu.so / libref_mdoc_gpuv.so not built")
+    from fixtures import load_mdoc
+    circuit = ref.zstd_compress(load_mdoc()["raw"])
+    A, V = ref.mdoc_gpu_lib(), ref.mdoc_gpuv_lib()
+    n = A.ref_mdoc_gpu_nclaims()
+    for i in range(n):
+        code, proof = ref.mdoc_prove_claim(A, i, circuit)
+        assert code == 0 and len(proof) > 300000, (i, code)
+        assert ref.mdoc_verify_claim(V, i, circuit, proof) == 0, (i, A.ref_mdoc_gpu_claim_name(i))
+        if i % 9 == 0:
+            assert ref.mdoc_verify_claim(A, i, circuit, proof) == 0
+            for pos in (3, 96 + 40, 96 + 5000, len(proof) // 2, len(proof) - 7):
+                bad = bytearray(proof)
+                bad[pos] ^= 0x10
+                want = ref.mdoc_verify_claim(A, i, circuit, bytes(bad))
+                got = ref.mdoc_verify_claim(V, i, circuit, bytes(bad))
+                assert want != 0 and got == want, (i, pos, want, got)
+    # a proof for another claim's session does not verify
+    _, p0 = ref.mdoc_prove_claim(V, 0, circuit)   # both halves on the GPU, one library
+    assert ref.mdoc_verify_claim(V, 0, circuit, p0) == 0
+    assert ref.mdoc_verify_claim(V, 1, circuit, p0) != 0

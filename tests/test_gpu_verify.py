@@ -232,3 +232,43 @@ def test_verifier_other_ligero_parameters(ctx, oracle, ref, rate, nreq, block_en
         c0 = lf.Circuit(ctx, 4, circ)
         stv, _ = lf.ZkVerifier(c0).verify_batch(None, [po], tinit=tinit)
         assert stv[0] != 0
+
+
+@pytest.mark.parametrize("B", [3, 40])
+def test_verify_on_a_caller_owned_transcript(case, B):
+    """lf_zk_verify_committed_batch (ZkVerifier::recv_commitment / ::verify on the caller's Transcript,
+    zk_verifier.h:69-106): the transcript that received the commitment continues on the device and comes back
+    as verify left it -- which is, by Fiat-Shamir, the state the prover's transcript is in after prove
+    (lf_zk_prove_committed_batch), so both must yield the same next challenge bytes.  A transcript that did
+    not receive the commitment (or received another) makes the same proof fail.  B = 3: head of the
+    transcript on the host; 40: on the device."""
+    import longfellow_zk_b200 as lf
+    from longfellow_zk_b200 import api
+    c = case["c"]
+    n = c.info["rng_bytes"]
+    seed = b"caller-owned"
+    rng = np.stack([rng_bytes(900 + i, n + 256) for i in range(B)])
+    W = np.repeat(np.frombuffer(case["wit"], np.uint8)[None, :], B, axis=0)
+    p = lf.ZkProver(c)
+    tp = api.transcripts(B, seed)
+    roots, st = p.commit_batch(W, rng, tp)
+    assert (st == 0).all()
+    proofs, st = p.prove_committed_batch(W, tp)
+    assert (st == 0).all()
+    tv = api.transcripts(B, seed)
+    for i in range(B):
+        assert proofs[i][:32] == bytes(roots[i])
+        api.transcript_write(tv[i], proofs[i][:32])      # recv_commitment (ligero_transcript.h:31-34)
+    status, why = case["v"].verify_batch(_pubs(case, B), proofs, transcripts=tv)
+    assert (status == 0).all(), (status, why)
+    for i in (0, B - 1):
+        assert api.transcript_challenge(tv[i], 48) == api.transcript_challenge(tp[i], 48)
+    # the same call equals the self-contained one
+    status, _ = case["v"].verify_batch(_pubs(case, B), proofs, tinit=seed)
+    assert (status == 0).all()
+    # no commitment received / the neighbour's commitment received: rejected
+    tv = api.transcripts(B, seed)
+    for i in range(1, B):
+        api.transcript_write(tv[i], proofs[i - 1][:32])
+    status, _ = case["v"].verify_batch(_pubs(case, B), proofs, transcripts=tv)
+    assert (status != 0).all()
