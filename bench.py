@@ -256,7 +256,35 @@ def measure_other(lf, ctx, stream, workload, B, steps=3, reduce_max=None, world=
     ms = rmax(e0.elapsed_time(e1)) * steps / nsteps3   # per `steps` steps, comparable with ms_one
     for o_ in xo:
         assert int(o_[2].abs().sum().item()) == 0
-    del xp, xo
+    # end to end with the same three batches in flight: one host thread, context, stream and pinned
+    # buffers each, so that one batch's PCIe copies overlap the other batches' kernels (as the headline's e2e)
+    hx = [[h_wit.clone().pin_memory(), h_rng.clone().pin_memory(), torch.empty((B, pb), dtype=torch.uint8).pin_memory(),
+           torch.zeros(B, dtype=torch.int64).pin_memory(), torch.zeros(B, dtype=torch.int32).pin_memory()]
+          for _ in range(NS - 1)]
+
+    def host_x(k):
+        h = hx[k]
+        xp[k].prove_batch_ptr(B, h[0].data_ptr(), h[1].data_ptr(), rstride, h[2].data_ptr(), pb, h[3].data_ptr(),
+                              h[4].data_ptr(), device=False)
+    host()
+    for k in range(NS - 1):
+        host_x(k)
+    n_pipe = 2
+    rmax(0.0)
+    t0 = time.perf_counter()
+    ths = [threading.Thread(target=lambda k=k: [host_x(k) for _ in range(n_pipe)]) for k in range(NS - 1)]
+    for th in ths:
+        th.start()
+    for _ in range(n_pipe):
+        host()
+    for th in ths:
+        th.join()
+    t_pipe = rmax(time.perf_counter() - t0)
+    for h in hx:
+        assert int(h[4].abs().sum().item()) == 0
+    assert int(h_st.abs().sum().item()) == 0
+    e2e_pipe = world * B * NS * n_pipe / t_pipe
+    del xp, xo, hx
     for c_ in xc:
         c_.close()
     prover.set_profiling(True)
@@ -311,7 +339,9 @@ def measure_other(lf, ctx, stream, workload, B, steps=3, reduce_max=None, world=
     return dict(workload=desc, proofs_per_step=B, distinct_witnesses=ndistinct,
                 value=world * B * steps / (ms * 1e-3), unit=UNIT,
                 streams=dict(n=3, one_stream=dict(value=world * B * steps / (ms_one * 1e-3))),
-                e2e=dict(value=world * 2 * B / t1, unit=UNIT, how="one batch at a time"), stage_ms=stages,
+                e2e=dict(value=e2e_pipe, unit=UNIT, how="lf_zk_prove_batch with pinned host buffers, three batches in "
+                         "flight (one host thread, context and stream each)",
+                         one_batch_at_a_time=dict(value=world * 2 * B / t1)), stage_ms=stages,
                 kernel_ms={k: dict(ms=v[0], launches=v[1]) for k, v in kernel_ms.items()},
                 latency_ms_per_proof_batch1=lat1,
                 kernels=stage_rates(info, stages, B, ctx.microbench(4 if fid == 1 else 2), ctx.microbench(3)),
