@@ -47,7 +47,13 @@ struct ZkVBufs {
   size_t msg_stride;
   uint8_t* def;     // [2 * block_ext] "defined" flags of MerkleTreeVerifier::verify_compressed_proof
   int32_t* why;     // [1]
+  // small batches (k_zkv_bind_quad_split): eight half EQ tables of half_cap entries each, and the per-CTA
+  // partial sums of one layer
+  Elt* half;        // [8 * half_cap]
+  Elt* part;        // [kVPartMax]
+  uint32_t half_cap, pad_;
 };
+constexpr uint32_t kVPartMax = 1024;
 
 __device__ __forceinline__ uint32_t ld_u32le(const uint8_t* p) {
   return (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24);
@@ -296,6 +302,95 @@ k_zkv_bind_quad(ZkDims d, ZkBufs<typename F::Elt> b, ZkVBufs<typename F::Elt> v,
     for (uint32_t k = 1; k < nth / 32; ++k) tot = F::add(tot, red[k]);
     b.bq[p * d.nl + ly] = tot;
   }
+}
+
+// ----------------------------------------------------------------------------
+// The same for small batches.  One CTA per proof leaves the GPU idle, and a layer of millions of terms (the
+// mdoc hash circuit: 7.76 M) keeps a single SM busy for ~0.1 s.  An EQ table is a tensor product over its
+// variables (eqs.h:46-78), EQ(X)[i] = EQ(X_lo)[i & m] * EQ(X_hi)[i >> s], so the grid-wide form needs only the
+// half tables -- at most 2^ceil(log/2) entries, built by one warp each (k_zkv_eq_halves: G0, alpha*G1, H0, H1,
+// low and high halves) -- and takes every table value as a product of two: 7 multiplications per term
+// instead of 3, spread over the whole GPU (k_zkv_bind_quad_split, grid = chunks x proofs), partial sums added
+// by k_zkv_bq_reduce.  Field sums are exact, so the regrouping gives the same element.
+// ----------------------------------------------------------------------------
+template <class F>
+__global__ void __launch_bounds__(256)
+k_zkv_eq_halves(ZkDims d, ZkBufs<typename F::Elt> b, ZkVBufs<typename F::Elt> v, LayerDesc L, LayerDesc Lprev,
+                uint32_t ly, uint32_t logv) {
+  typedef typename F::Elt Elt;
+  const size_t p = blockIdx.x;
+  if (b.status[p] != 0) return;
+  const uint32_t w = threadIdx.x >> 5, lane = threadIdx.x & 31;  // warp w builds table w
+  const Elt* hb = b.hb + p * d.nhb;
+  const bool isG = w < 4;
+  const uint32_t hand = (w >> 1) & 1, hi = w & 1;
+  const uint32_t n = isG ? logv : L.logw, s = n / 2;
+  const uint32_t first = hi ? s : 0, count = hi ? n - s : s;
+  Elt* T = v.half + (p * 8 + w) * (size_t)v.half_cap;
+  if (lane == 0) T[0] = (isG && hand == 1 && !hi) ? b.alphas[p * d.nl + ly] : F::one();
+  __syncwarp();
+  for (uint32_t j = 0; j < count; ++j) {
+    const uint32_t l = first + j, S = 1u << j;
+    const Elt c = isG ? (ly == 0 ? v.G[p * 40 + l] : hb[Lprev.hb_off + 2 * l + hand]) : hb[L.hb_off + 2 * l + hand];
+    for (uint32_t k = lane; k < S; k += 32) {
+      const Elt x = T[k], h = F::mul(x, c);
+      T[k] = F::sub(x, h);
+      T[k + S] = h;
+    }
+    __syncwarp();
+  }
+}
+
+template <class F>
+__global__ void __launch_bounds__(256)
+k_zkv_bind_quad_split(ZkDims d, ZkBufs<typename F::Elt> b, ZkVBufs<typename F::Elt> v,
+                      const uint32_t* __restrict__ arena, LayerDesc L, uint32_t ly, uint32_t logv,
+                      const typename F::Elt* __restrict__ consts) {
+  typedef typename F::Elt Elt;
+  typedef typename F::Acc Acc;
+  const size_t p = blockIdx.y;
+  if (b.status[p] != 0) return;
+  const uint32_t tid = threadIdx.x, nth = blockDim.x;
+  const Elt* H = v.half + p * 8 * (size_t)v.half_cap;
+  const uint32_t cap = v.half_cap;
+  const Elt *G0lo = H, *G0hi = H + cap, *G1lo = H + 2 * cap, *G1hi = H + 3 * cap;
+  const Elt *H0lo = H + 4 * cap, *H0hi = H + 5 * cap, *H1lo = H + 6 * cap, *H1hi = H + 7 * cap;
+  const uint32_t sG = logv / 2, mG = (1u << sG) - 1, sH = L.logw / 2, mH = (1u << sH) - 1;
+  const Elt beta = v.beta[p * d.nl + ly];
+  Acc acc;
+  F::acc_zero(acc);
+  const uint32_t *tg = arena + L.bg_g, *tv = arena + L.bg_vi;
+  const uint32_t* seg = arena + L.bg_seg;
+  const uint32_t *ch0 = arena + L.vq_h0, *ch1 = arena + L.vq_h1;
+  for (uint32_t t = blockIdx.x * nth + tid; t < L.nterms; t += gridDim.x * nth) {
+    const uint32_t vv = tv[t], c = seg[t], g = tg[t];
+    const uint32_t h0 = ch0[c], h1 = ch1[c];
+    const Elt dot = F::add(F::mul(G0lo[g & mG], G0hi[g >> sG]), F::mul(G1lo[g & mG], G1hi[g >> sG]));
+    const Elt q = (vv & kViOne) ? dot : F::mul((vv & kViZero) ? beta : consts[vv & kViMask], dot);
+    const Elt e0 = F::mul(H0lo[h0 & mH], H0hi[h0 >> sH]), e1 = F::mul(H1lo[h1 & mH], H1hi[h1 >> sH]);
+    F::mac(acc, F::mul(q, e0), e1);
+  }
+  __shared__ Elt red[8];
+  const Elt s = warp_sum<F>(F::reduce(acc));
+  if ((tid & 31) == 0) red[tid >> 5] = s;
+  __syncthreads();
+  if (tid == 0) {
+    Elt tot = red[0];
+    for (uint32_t k = 1; k < nth / 32; ++k) tot = F::add(tot, red[k]);
+    v.part[p * kVPartMax + blockIdx.x] = tot;
+  }
+}
+
+template <class F>
+__global__ void __launch_bounds__(32)
+k_zkv_bq_reduce(ZkDims d, ZkBufs<typename F::Elt> b, ZkVBufs<typename F::Elt> v, uint32_t ly, uint32_t nchunk) {
+  typedef typename F::Elt Elt;
+  const size_t p = blockIdx.x;
+  if (b.status[p] != 0) return;
+  Elt s = F::zero();
+  for (uint32_t k = threadIdx.x; k < nchunk; k += 32) s = F::add(s, v.part[p * kVPartMax + k]);
+  s = warp_sum<F>(s);
+  if (threadIdx.x == 0) b.bq[p * d.nl + ly] = s;
 }
 
 // ----------------------------------------------------------------------------

@@ -4,6 +4,7 @@ holds for this path:
   * docs/specs/testvectors.md:23-98 + lib/random/transcript_test.cc:131-341   (Fiat-Shamir)
   * rust/runtime/merkle/tests/{merkle,commitment}_test_vector.bin (C++-generated;
     layouts per rust/runtime/merkle/tests/merkle.rs:219-299,302-417)
+  * rust/runtime/random/tests/transcript_test_vector.bin (C++-generated; transcript.rs:18-67)
   * tests/golden/golden.json: proofs produced by the unmodified reference
   * tests/golden/rfc_zk_vector1.json: the reference's known-answer test of the whole ZK prover
     (rust/runtime/zk/tests/zk.rs:228-558, bytes produced by the C++ prover)
@@ -174,6 +175,24 @@ def test_fiat_shamir_spec_vectors(oracle):
     for m, want in CHOOSE:
         assert list(rest[k:k + 20]) == want, m
         k += 20
+
+
+def test_rust_tree_transcript_vector(oracle):
+    """rust/runtime/random/tests/transcript.rs:18-67 `test_transcript_cpp_compatibility` with the C++-generated
+    transcript_test_vector.bin: 100 iterations of write(64 bytes), write0(100 + i), one P-256 element, an array
+    of five, then 256 challenge bytes, on Transcript([1..8])."""
+    want = open(f"{GOLDEN}/transcript_test_vector.bin", "rb").read()
+    assert len(want) == 100 * 256
+    u8 = lambda f: bytes((f(j) & 0xFF) for j in range(32))
+    script = b""
+    for i in range(100):
+        script += b"B" + struct.pack("<I", 64) + bytes(((i * 7 + j * 13) & 0xFF) for j in range(64))
+        script += b"Z" + struct.pack("<I", 100 + i)
+        script += b"E" + u8(lambda j: i * 17 + j * 19)
+        script += b"A" + struct.pack("<I", 5) + b"".join(u8(lambda j, k=k: i * 23 + k * 29 + j * 31) for k in range(5))
+        script += b"R" + struct.pack("<I", 256)
+    got = oracle.transcript_script(bytes(range(1, 9)), script, fid=1)
+    assert got == want
 
 
 def test_transcript_key_and_prf_blocks(oracle):
