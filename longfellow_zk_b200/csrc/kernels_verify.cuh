@@ -220,6 +220,166 @@ k_zkv_replay(ZkDims d, ZkBufs<typename F::Elt> b, ZkVBufs<typename F::Elt> v, co
 }
 
 // ----------------------------------------------------------------------------
+// k_zkv_replay_par: the same transcript without its serial latency.  On the verifier's side every byte
+// that enters the transcript is proof data, known before the first challenge is drawn, and a challenge
+// never feeds a write.  So the pass splits in three (one CTA per proof):
+//   (1) all threads lay the whole byte stream out: the transcript's pending bytes, then per round
+//       tag | p(0), tag | p(2), per layer the array header and the two claims;
+//   (2) ONE thread runs the SHA-256 chain over the full 64-byte blocks and keeps the chaining value
+//       after every block: 0.53 (GF(2^128)) / 1.03 (P-256) compressions per round, nothing else;
+//   (3) one thread per KEY POINT -- a stream position after which challenges are drawn: the start
+//       (Q, G, alpha_0, beta_0), the end of every round (its challenge), the end of every layer but
+//       the last (alpha, beta of the next) -- rebuilds the Transcript as it stood there (chaining value
+//       of the blocks before it + the tail bytes), and draws with the ordinary Transcript code: digest
+//       snapshot, AES-256 key schedule, blocks, Field::sample with its rejection loop.
+// The serial part drops from (absorb + snapshot + key schedule + blocks) per round to the absorb alone.
+// rmsg: per proof [rmsg_stride] bytes of stream, then (rmsg_stride / 64 + 1) x 8 words of chaining values.
+// ----------------------------------------------------------------------------
+template <class F>
+__global__ void __launch_bounds__(256)
+k_zkv_replay_par(ZkDims d, ZkBufs<typename F::Elt> b, ZkVBufs<typename F::Elt> v,
+                 const LayerDesc* __restrict__ layers, uint8_t* __restrict__ rmsg, size_t rmsg_stride) {
+  typedef typename F::Elt Elt;
+  constexpr uint32_t kB = F::kBytes, kEw = 1 + kB;   // bytes of one tagged element write
+  __shared__ AesTables s_aes;
+  __shared__ uint32_t s_h0[8], s_pos0, s_total, s_nkey;
+  __shared__ uint64_t s_len0;
+  aes_stage_tables(&s_aes);
+  const size_t p = blockIdx.x;
+  if (b.status[p] != 0) return;
+  const uint32_t tid = threadIdx.x, nth = blockDim.x;
+  Transcript* gts = reinterpret_cast<Transcript*>(b.ts + p * sizeof(Transcript));
+  uint8_t* M = rmsg + p * (rmsg_stride + (rmsg_stride / 64 + 1) * 32);
+  uint32_t* H = reinterpret_cast<uint32_t*>(M + rmsg_stride);
+  const Elt* sc = b.sc + p * d.sc_elts;
+  if (tid == 0) {
+    const uint32_t pos0 = (uint32_t)(gts->sha.len & 63);
+    s_pos0 = pos0;
+    s_len0 = gts->sha.len;
+    for (int k = 0; k < 8; ++k) s_h0[k] = gts->sha.h[k];
+    for (uint32_t k = 0; k < pos0; ++k) M[k] = (uint8_t)(gts->sha.buf[k >> 2] >> (24 - 8 * (k & 3)));
+    uint32_t tot = pos0, nkey = 1;
+    for (uint32_t ly = 0; ly < d.nl; ++ly) {
+      tot += 2 * layers[ly].logw * 2 * kEw + 9 + 2 * kB;
+      nkey += 2 * layers[ly].logw + (ly + 1 < d.nl ? 1 : 0);
+    }
+    s_total = tot;
+    s_nkey = nkey;
+  }
+  __syncthreads();
+  const uint32_t pos0 = s_pos0, total = s_total;
+  // (1) the byte stream: one thread per element write
+  {
+    uint32_t base = pos0;
+    for (uint32_t ly = 0; ly < d.nl; ++ly) {
+      const LayerDesc L = layers[ly];
+      const uint32_t nw = 4 * L.logw + 2;   // tagged writes of the rounds, then the two array elements
+      for (uint32_t i = tid; i < nw; i += nth) {
+        uint32_t off, src;
+        bool tagged = true;
+        if (i < 4 * L.logw) {
+          const uint32_t t = i >> 1, k2 = i & 1, hand = t & 1, round = t >> 1;
+          off = base + i * kEw;
+          src = L.sc_off + 4 * round + 2 * k2 + hand;
+        } else {
+          const uint32_t k = i - 4 * L.logw;
+          off = base + 4 * L.logw * kEw + 9 + k * kB;
+          src = L.sc_off + 4 * L.logw + k;
+          tagged = false;
+        }
+        uint32_t w[F::kWords];
+        F::to_wire(w, sc[src]);
+        uint8_t* o = M + off;
+        if (tagged) *o++ = 1;   // TAG_FIELD_ELEM (transcript.h:136-141)
+#pragma unroll
+        for (int q = 0; q < F::kWords; ++q) {
+          o[4 * q] = (uint8_t)w[q];
+          o[4 * q + 1] = (uint8_t)(w[q] >> 8);
+          o[4 * q + 2] = (uint8_t)(w[q] >> 16);
+          o[4 * q + 3] = (uint8_t)(w[q] >> 24);
+        }
+      }
+      if (tid == 0) {   // array header: TAG_ARRAY, 64-bit little-endian length 2 (transcript.h:144-153,160-171)
+        uint8_t* o = M + base + 4 * L.logw * kEw;
+        o[0] = 2;
+        o[1] = 2;
+        for (int k = 2; k < 9; ++k) o[k] = 0;
+      }
+      base += 4 * L.logw * kEw + 9 + 2 * kB;
+    }
+  }
+  __syncthreads();
+  // (2) the chain over the full blocks
+  const uint32_t nfull = total / 64;
+  if (tid == 0) {
+    uint32_t h[8];
+    for (int k = 0; k < 8; ++k) h[k] = s_h0[k];
+    const uint32_t* m32 = reinterpret_cast<const uint32_t*>(M);
+    for (uint32_t j = 0; j < nfull; ++j) {
+      uint32_t w[16];
+#pragma unroll
+      for (int k = 0; k < 16; ++k) w[k] = bswap32(m32[16 * (size_t)j + k]);
+      sha256_compress_fn(h, w);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) H[8 * (size_t)j + k] = h[k];
+    }
+  }
+  __syncthreads();
+  // the Transcript as it stands once the first `pos` bytes of the stream are absorbed
+  auto at = [&](uint32_t pos, Transcript* ts) {
+    const uint32_t nb = pos / 64;
+    for (int k = 0; k < 8; ++k) ts->sha.h[k] = nb ? H[8 * (size_t)(nb - 1) + k] : s_h0[k];
+    for (int k = 0; k < 16; ++k) ts->sha.buf[k] = 0;
+    for (uint32_t k = 64 * nb; k < pos; ++k) ts->sha.buf[(k & 63) >> 2] |= (uint32_t)M[k] << (24 - 8 * (k & 3));
+    ts->sha.len = s_len0 - pos0 + pos;
+    ts->have_prf = 0;
+    ts->nblock = 0;
+    ts->rdptr = 16;
+    ts->use_tables(&s_aes);
+  };
+  // (3) the key points
+  Elt* hbs = b.hb + p * d.nhb;
+  for (uint32_t j = tid; j < s_nkey; j += nth) {
+    Transcript ts;
+    if (j == 0) {
+      // begin_circuit: Q[40] then G[40] (transcript_sumcheck.h:49-52), then alpha, beta of layer 0
+      at(pos0, &ts);
+      for (int i = 0; i < 40; ++i) (void)ts_challenge<F>(&ts);
+      for (int i = 0; i < 40; ++i) v.G[p * 40 + i] = ts_challenge<F>(&ts);
+      b.alphas[p * d.nl] = ts_challenge<F>(&ts);
+      v.beta[p * d.nl] = ts_challenge<F>(&ts);
+      continue;
+    }
+    uint32_t k = j - 1, base = pos0;
+    for (uint32_t ly = 0; ly < d.nl; ++ly) {
+      const LayerDesc L = layers[ly];
+      const uint32_t nr = 2 * L.logw;
+      if (k < nr) {   // the challenge after round k of this layer
+        at(base + (k + 1) * 2 * kEw, &ts);
+        hbs[L.hb_off + k] = ts_challenge<F>(&ts);
+        break;
+      }
+      k -= nr;
+      base += 2 * nr * kEw + 9 + 2 * kB;
+      if (k == 0) {   // the end of this layer: alpha, beta of the next
+        at(base, &ts);
+        b.alphas[p * d.nl + ly + 1] = ts_challenge<F>(&ts);
+        v.beta[p * d.nl + ly + 1] = ts_challenge<F>(&ts);
+        break;
+      }
+      k -= 1;
+    }
+  }
+  __syncthreads();
+  // the transcript as the pass leaves it (LigeroVerifier::verify continues on it)
+  if (tid == 0) {
+    Transcript ts = *gts;
+    at(total, &ts);
+    *gts = ts;
+  }
+}
+
+// ----------------------------------------------------------------------------
 // k_zkv_bind_quad: bq[ly] = Quad::bind_gh_all (quad.h:188-210)
 //   = sum over the layer's terms of prep_v(v, EQ2(G0, G1, alpha)[g]) * EQ(H0)[h0] * EQ(H1)[h1],
 // G = the bindings of the layer above (begin_circuit's G for layer 0), H = this layer's hand
