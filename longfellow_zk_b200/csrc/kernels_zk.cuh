@@ -444,7 +444,7 @@ struct ScShared {
   typename F::Elt cred[2][16];   // leader only: a0 / a2 partial of every CTA
   AesTables aes;        // AES S-box and round tables staged in shared memory
   int fail;
-  long long prof[8];    // LF_PROF: cycles of thread 0 per phase
+  long long prof[16];   // LF_PROF: cycles of thread 0 per phase ([7] layer set-up, [8] QW, [9] evaluations, [10] bind, [11] solo rounds)
 };
 
 // What the sumcheck prover carries from one kernel to the next when a proof's rounds are split
@@ -768,7 +768,7 @@ __device__ __forceinline__ void sumcheck_body(const ZkDims& d, const ZkBufs<type
   aes_stage_tables(&sh.aes);
   ScCore<F>* core = reinterpret_cast<ScCore<F>*>(b.scst + p * sizeof(ScCore<F>));
   if (leader) {
-    for (int i = 0; i < 8; ++i) sh.prof[i] = 0;
+    for (int i = 0; i < 16; ++i) sh.prof[i] = 0;
     sh.prof[3] = clock64();
     if (R.first) sc_begin<F>(&sh, reinterpret_cast<const Transcript*>(b.ts + p * sizeof(Transcript)));
     else sc_load<F>(&sh, core);
@@ -780,6 +780,7 @@ __device__ __forceinline__ void sumcheck_body(const ZkDims& d, const ZkBufs<type
     const LayerDesc L = layers[ly];
     // a launch may pick a layer up at round t0 > 0: the earlier rounds ran as flat kernels
     const uint32_t t0 = ly == R.ly_begin ? R.t_begin : 0;
+    const long long tl0 = clock64();
     if (t0 == 0) {
     if (leader) {
       sc_begin_layer<F>(&sh, &b.alphas[p * d.nl + ly]);
@@ -837,9 +838,11 @@ __device__ __forceinline__ void sumcheck_body(const ZkDims& d, const ZkBufs<type
     const Elt* pad = wit + d.n_witness + L.pad_off;
 
     bool solo = false;
+    if (leader) sh.prof[7] += clock64() - tl0;
     for (uint32_t t = t0; t < 2 * L.logw; ++t) {
       const StepDesc S = steps[L.step0 + t];
       const uint32_t hand = t & 1, round = t >> 1;
+      const long long tr0 = clock64();
       // Cluster mode: once a layer's steps are small, a cluster-wide phase costs
       // more (barrier + an L2 round trip per phase, ~2 us) than its work; the
       // leader CTA then finishes the layer alone with CTA barriers and the other
@@ -873,6 +876,7 @@ __device__ __forceinline__ void sumcheck_body(const ZkDims& d, const ZkBufs<type
       }
       // the two dot products of ProverLayers::evaluations (prover_layers.h:357-402)
       const uint32_t npair = (S.n0 + 1) / 2;
+      const long long tr1 = clock64();
       {
         Acc a0, a2;
         F::acc_zero(a0);
@@ -907,6 +911,9 @@ __device__ __forceinline__ void sumcheck_body(const ZkDims& d, const ZkBufs<type
       Q.sync();
       long long tp0 = clock64();
       if (leader) {
+        sh.prof[8] += tr1 - tr0;
+        sh.prof[9] += tp0 - tr1;
+        if (CL && solo) sh.prof[11] += 1;
         Elt s0 = sh.cred[0][0], s2 = sh.cred[1][0];
         for (uint32_t c = 1; c < Q.ncta; ++c) {
           s0 = F::add(s0, sh.cred[0][c]);
@@ -920,6 +927,7 @@ __device__ __forceinline__ void sumcheck_body(const ZkDims& d, const ZkBufs<type
         sh.prof[1] += 1;
       }
       Q.sync();
+      const long long tb0 = clock64();
       const Elt r = Q.remote(&sh, 0)->r;
       if (leader) sc_new_claim<F>(&sh);  // off the critical path: the others are already binding
       // Dense::bind (dense.h:70-89)
@@ -942,6 +950,7 @@ __device__ __forceinline__ void sumcheck_body(const ZkDims& d, const ZkBufs<type
         HQn[j] = affine<F>(r, f0, f1);
       }
       Q.sync();
+      if (leader) sh.prof[10] += clock64() - tb0;
       if (hand) {
         wcur1 = Wn;
         wpar1 ^= 1;
@@ -966,7 +975,8 @@ __device__ __forceinline__ void sumcheck_body(const ZkDims& d, const ZkBufs<type
       if (sh.fail) atomicCAS(&b.status[p], 0, -100);  // (the first error of a proof sticks) internal inconsistency: never expected
       sh.prof[2] = clock64() - sh.prof[3];
       long long* dbg = reinterpret_cast<long long*>(hqbuf);  // free after the last layer
-      for (int i = 0; i < 8; ++i) dbg[i] = sh.prof[i];
+      const int nd = (int)min((size_t)16, 2 * (size_t)d.max_hq * sizeof(Elt) / 8);  // tiny circuits: a short buffer
+      for (int i = 0; i < nd; ++i) dbg[i] = sh.prof[i];
     } else {
       sc_save<F>(&sh, core);  // the flat kernels of the next layer continue from here
     }

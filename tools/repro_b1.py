@@ -15,6 +15,9 @@ W = np.repeat(np.frombuffer(wit, np.uint8)[None, :], B, axis=0)
 pr0 = lf.ZkProver(c)
 proofs, status = pr0.prove_batch(W, rng)
 dbg = pr0.debug_fetch(0, 99).view(np.int64)
+if len(dbg) >= 12:
+    print('per round: QW', dbg[8] / dbg[1], 'evaluations+barrier', dbg[9] / dbg[1], 'bind+barrier', dbg[10] / dbg[1],
+          'layer set-up total', dbg[7], 'solo rounds', dbg[11])
 print('serial cycles', dbg[0], 'rounds', dbg[1], 'cycles/round', dbg[0] / max(dbg[1], 1), 'kernel cycles', dbg[2], 'per round: evals', dbg[4] / dbg[1], 'absorb', dbg[5] / dbg[1], 'challenge', dbg[6] / dbg[1])
 print("ok", which, B, [len(p) for p in proofs][:4], status[:4])
 pr = lf.ZkProver(c)
