@@ -277,6 +277,61 @@ struct Sha256 {
   LF_HD void update_le_words(const uint32_t* w, int nwords) {
     for (int i = 0; i < nwords; ++i) put_word_be(bswap32(w[i]));
   }
+  // nbytes (<= 4 * NS) bytes given as big-endian stream words S[0..NS) (unused low bytes of the last word
+  // zero), appended at any byte position in one pass: the words are shifted to the buffer's alignment with
+  // funnel shifts and OR-ed in (the buffer is zero beyond the write position), with at most one compression
+  // in between.  The element writes of a Fiat-Shamir round (tag + 16 or 32 bytes, transcript.h:136-153) take
+  // this path instead of five or nine byte-granular calls.
+  template <int NS>
+  LF_HD void put_stream_words(const uint32_t* S, uint32_t nbytes) {
+    const uint32_t pos = (uint32_t)(len & 63), k = pos & 3, wi = pos >> 2, sh = 8 * k;
+    len += nbytes;
+    uint32_t T[NS + 1];
+#ifdef __CUDA_ARCH__
+    T[0] = S[0] >> sh;
+#pragma unroll
+    for (int j = 1; j < NS; ++j) T[j] = __funnelshift_r(S[j], S[j - 1], sh);
+    T[NS] = __funnelshift_r(0u, S[NS - 1], sh);
+#else
+    T[0] = S[0] >> sh;
+    for (int j = 1; j < NS; ++j) T[j] = (uint32_t)(((((uint64_t)S[j - 1]) << 32) | S[j]) >> sh);
+    T[NS] = (uint32_t)((((uint64_t)S[NS - 1]) << 32) >> sh);
+#endif
+    const uint32_t nT = (k + nbytes + 3) >> 2;        // buffer words touched
+    const uint32_t end = pos + nbytes;                // >= 64: the block fills
+    const uint32_t nb = end >= 64 ? 16 - wi : nT;     // words that go in before the compression
+#pragma unroll
+    for (int j = 0; j <= NS; ++j)
+      if ((uint32_t)j < nb) buf[wi + j] |= T[j];
+    if (end >= 64) {
+      compress_block();
+#pragma unroll
+      for (int j = 0; j <= NS; ++j)
+        if ((uint32_t)j >= nb && (uint32_t)j < nT) buf[j - nb] = T[j];
+    }
+  }
+  // tag byte + N little-endian element words
+  template <int N>
+  LF_HD void put_tagged_le_words(uint32_t tag, const uint32_t* w) {
+    uint32_t S[N + 1];
+    uint32_t prev = tag << 24;
+#pragma unroll
+    for (int j = 0; j < N; ++j) {
+      const uint32_t x = bswap32(w[j]);
+      S[j] = prev | (x >> 8);
+      prev = x << 24;
+    }
+    S[N] = prev;
+    put_stream_words<N + 1>(S, 4 * N + 1);
+  }
+  // N little-endian element words, no tag (array elements)
+  template <int N>
+  LF_HD void put_le_words(const uint32_t* w) {
+    uint32_t S[N];
+#pragma unroll
+    for (int j = 0; j < N; ++j) S[j] = bswap32(w[j]);
+    put_stream_words<N>(S, 4 * N);
+  }
   // digest of the bytes so far, without disturbing the running state
   // (Transcript::get, lib/random/transcript.h:99-105). out = 8 big-endian words
   LF_HD void snapshot(uint32_t out[8]) const {
@@ -555,15 +610,26 @@ struct Transcript {
   }
   // transcript.h:136-141 ; e = wire-order little-endian words of the element
   LF_HD void write_elt_words(const uint32_t* e, int nwords) {
-    raw_byte(1);
-    sha.update_le_words(e, nwords);
+    have_prf = 0;
+    if (nwords == 4) {
+      sha.put_tagged_le_words<4>(1, e);
+    } else if (nwords == 8) {
+      sha.put_tagged_le_words<8>(1, e);
+    } else {
+      sha.put_byte(1);
+      sha.update_le_words(e, nwords);
+    }
   }
   // transcript.h:144-153 header of an array write; follow with n x elt_words()
   LF_HD void begin_array(uint64_t n) {
     raw_byte(2);
     raw_len(n);
   }
-  LF_HD void elt_words(const uint32_t* e, int nwords) { sha.update_le_words(e, nwords); }
+  LF_HD void elt_words(const uint32_t* e, int nwords) {
+    if (nwords == 4) sha.put_le_words<4>(e);
+    else if (nwords == 8) sha.put_le_words<8>(e);
+    else sha.update_le_words(e, nwords);
+  }
 
   // transcript.h:46-62,89-96
   // (re)key the PRF if a write intervened, then produce the next 16-byte block;

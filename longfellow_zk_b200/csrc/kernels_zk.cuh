@@ -28,13 +28,15 @@ template <class F>
 __device__ __noinline__ void ts_array_elt(Transcript* ts, typename F::Elt e) {
   uint32_t w[F::kWords];
   F::to_wire(w, e);
-#pragma unroll
-  for (int k = 0; k < F::kWords; ++k) ts->sha.put_word_be(bswap32(w[k]));
+  ts->sha.template put_le_words<F::kWords>(w);
 }
+// tag + element in one pass over the buffer (Sha256::put_stream_words)
 template <class F>
-__device__ __forceinline__ void ts_write_elt(Transcript* ts, typename F::Elt e) {
-  ts->raw_byte(1);  // TAG_FIELD_ELEM
-  ts_array_elt<F>(ts, e);
+__device__ __noinline__ void ts_write_elt(Transcript* ts, typename F::Elt e) {
+  uint32_t w[F::kWords];
+  F::to_wire(w, e);
+  ts->have_prf = 0;  // a write drops the challenge stream (transcript.h:174-178)
+  ts->sha.template put_tagged_le_words<F::kWords>(1, w);  // TAG_FIELD_ELEM
 }
 // Field::sample on the transcript (random.h:37-41), out of line for the same reason
 template <class F>
@@ -930,24 +932,31 @@ __device__ __forceinline__ void sumcheck_body(const ZkDims& d, const ZkBufs<type
       const long long tb0 = clock64();
       const Elt r = Q.remote(&sh, 0)->r;
       if (leader) sc_new_claim<F>(&sh);  // off the critical path: the others are already binding
-      // Dense::bind (dense.h:70-89)
+      // Dense::bind (dense.h:70-89) and HQuad::bind_h (hquad.h:89-123) through the merge plan, over ONE index
+      // space: in the small rounds both lists fit the threads once, and two loops would be two latency
+      // chains (load, multiply, store) one after the other
       Elt* Wn = whbuf + (size_t)(2 * hand + (hand ? wpar1 : wpar0)) * d.max_nw;
-      for (uint32_t i = gtid; i < npair; i += gnth) {
-        // affine_interpolation_nz_z(r, f0) == affine_interpolation(r, f0, 0) (affine.h:25-52)
-        Elt f0 = Wh[2 * i], f1 = (2 * i + 1 < S.n0) ? Wh[2 * i + 1] : F::zero();
-        Wn[i] = affine<F>(r, f0, f1);
-      }
-      // HQuad::bind_h (hquad.h:89-123) through the merge plan
       Elt* HQn = hqbuf + (size_t)(hqpar ^ 1) * d.max_hq;
       const uint32_t* mg = arena + S.merge;
-      for (uint32_t j = gtid; j < S.n_out; j += gnth) {
-        // pair: (v0, v1); lone even corner: (v0, 0); lone odd corner: (0, v0) -- the
-        // three affine_interpolation variants of hquad.h:99-115 are one formula
-        uint32_t m = mg[j], src = m >> 2, kind = m & 3;
-        Elt v = HQ[src];
-        Elt f0 = kind == 2 ? F::zero() : v;
-        Elt f1 = kind == 0 ? HQ[src + 1] : (kind == 2 ? v : F::zero());
-        HQn[j] = affine<F>(r, f0, f1);
+      for (uint32_t k = gtid; k < npair + S.n_out; k += gnth) {
+        Elt f0, f1;
+        Elt* dst;
+        if (k < npair) {
+          // affine_interpolation_nz_z(r, f0) == affine_interpolation(r, f0, 0) (affine.h:25-52)
+          f0 = Wh[2 * k];
+          f1 = (2 * k + 1 < S.n0) ? Wh[2 * k + 1] : F::zero();
+          dst = Wn + k;
+        } else {
+          // pair: (v0, v1); lone even corner: (v0, 0); lone odd corner: (0, v0) -- the
+          // three affine_interpolation variants of hquad.h:99-115 are one formula
+          const uint32_t j = k - npair;
+          const uint32_t m = mg[j], src = m >> 2, kind = m & 3;
+          const Elt v = HQ[src];
+          f0 = kind == 2 ? F::zero() : v;
+          f1 = kind == 0 ? HQ[src + 1] : (kind == 2 ? v : F::zero());
+          dst = HQn + j;
+        }
+        *dst = affine<F>(r, f0, f1);
       }
       Q.sync();
       if (leader) sh.prof[10] += clock64() - tb0;

@@ -95,6 +95,22 @@ int main(int argc, char** argv) {
       a.encrypt(x, y, aes_default_sbox());
       fwrite(y, 1, 16, stdout);
     }
+  } else if (!strcmp(argv[1], "transcript8")) {
+    // the same script language with 32-byte elements (P-256 wire bytes): the 8-word element writes
+    Transcript t;
+    t.init((const uint8_t*)"test", 4);
+    size_t p = 0;
+    auto rd32 = [&]() { uint32_t v; memcpy(&v, &in[p], 4); p += 4; return v; };
+    while (p < in.size()) {
+      char op = (char)in[p++];
+      if (op == 'B') { uint32_t n = rd32(); t.write_bytes(&in[p], n); p += n; }
+      else if (op == 'Z') { t.write0(rd32()); }
+      else if (op == 'E') { uint32_t w[8]; memcpy(w, &in[p], 32); p += 32; t.write_elt_words(w, 8); }
+      else if (op == 'A') { uint32_t n = rd32(); t.begin_array(n);
+        for (uint32_t i = 0; i < n; ++i) { uint32_t w[8]; memcpy(w, &in[p], 32); p += 32; t.elt_words(w, 8); } }
+      else if (op == 'R') { uint32_t n = rd32(); std::vector<uint8_t> o(n); t.bytes(o.data(), n); fwrite(o.data(), 1, n, stdout); }
+      else return 3;
+    }
   } else if (!strcmp(argv[1], "transcript")) {
     // same script language as oracle (GF(2^128) elements); init = "test"
     Transcript t;

@@ -76,6 +76,20 @@ def test_device_sha_aes_transcript_source_on_host(prim, oracle):
     s += b"Z" + u32(1000) + b"N" + u32(3187) + b"N" + u32(256) + b"N" + u32(1)
     s += b"A" + u32(2) + bytes(range(32)) + b"Z" + u32(155197) + b"R" + u32(17) + b"Z" + u32(3) + b"G" + u32(1)
     assert prim("transcript", s) == oracle.transcript_script(b"test", s)
+    # the single-pass element writes (Sha256::put_stream_words) at every byte alignment and across block
+    # boundaries: runs of tagged elements and arrays separated by byte strings of every length mod 64
+    for kb, mode, fid in ((16, "transcript", 4), (32, "transcript8", 1)):
+        s = b""
+        for i in range(140):
+            e = lambda: rs.integers(0, 256, kb - 1, dtype=np.uint8).tobytes() + b"\x00"   # canonical for P-256 too
+            s += b"B" + u32(i % 67) + rs.integers(0, 256, i % 67, dtype=np.uint8).tobytes()
+            s += b"E" + e() + b"E" + e()
+            if i % 3 == 0:
+                s += b"A" + u32(2) + e() + e()
+            if i % 5 == 0:
+                s += b"E" + e() + b"E" + e() + b"E" + e()
+            s += b"R" + u32(16 if i % 4 else 35)
+        assert prim(mode, s) == oracle.transcript_script(b"test", s, fid=fid), mode
 
 
 def test_oracle_matches_unmodified_reference(oracle, ref):
