@@ -21,6 +21,19 @@ for name, fid in (("sha1_gf128", 4), ("ecdsa1_p256", 1)):
         sv, _ = lf.ZkVerifier(c).verify_batch(np.ascontiguousarray(Wb[:, :npub]) if npub else None, proofs)
         assert (sv == 0).all()
         print(name, B, "ok", flush=True)
+# the reference's tiny known-answer circuit (3 terms, block_enc 128): the smallest buffers of every kind
+from fixtures import load_rfc_vector
+from oracle import portapi as O
+rec, circ, wit, coins, want = load_rfc_vector(O)
+c = lf.Circuit(ctx, rec["field_id"], circ, rate=rec["rate"], nreq=rec["nreq"], block_enc=rec["block_enc"])
+for B in (1, 70):
+    Wb = np.repeat(np.frombuffer(wit, np.uint8)[None, :], B, axis=0)
+    proofs, st = lf.ZkProver(c).prove_batch(Wb, np.repeat(coins[None, :], B, axis=0), tinit=b"test")
+    assert (st == 0).all() and proofs[B - 1] == want
+    npub = c.info["npub_in"] * c.info["kbytes"]
+    sv, _ = lf.ZkVerifier(c).verify_batch(np.ascontiguousarray(Wb[:, :npub]), proofs, tinit=b"test")
+    assert (sv == 0).all()
+    print("rfc vector", B, "ok", flush=True)
 rs = np.random.default_rng(0)
 for fid, kb in ((4, 16), (1, 32), (100, 32), (101, 16), (102, 8)):
     rows = rs.integers(0, 256, (3, 4096, kb), dtype=np.uint8)
