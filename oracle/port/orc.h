@@ -183,4 +183,19 @@ int zk_prove(const circuit* c, const uint8_t* witness_bytes, rng* r,
              const uint8_t* tinit, size_t tinit_len, size_t rate, size_t nreq,
              size_t block_enc, uint8_t* out, size_t out_cap, size_t* out_len,
              zk_dump* dump);
+/* LigeroProver::commit + ::prove on a caller-given statement (ligero/ligero_prover.h:58-146): nw witnesses,
+ * nq quadratic constraints W[x]*W[y] = W[z] (lqc: x, y, z per constraint), linear constraint terms
+ * (c, w, k): sum over terms of row c of k * W[w] = b[c] (b itself is not needed to prove), the hash of the
+ * statement.  out = root (32 bytes) | LigeroProof as ZkProof::write_com_proof serialises it. */
+typedef struct {
+  const field* F;
+  size_t nw, nq, ncons, nterms, subfield_boundary;
+  const elt* W;
+  const size_t* lqc;                /* 3 * nq */
+  const size_t *term_c, *term_w;    /* nterms */
+  const elt* term_k;                /* nterms */
+  const uint8_t* hash;              /* 32 */
+} ligero_generic;
+int ligero_prove_generic(const ligero_generic* G, rng* r, const uint8_t* tinit, size_t tinit_len, size_t rate,
+                         size_t nreq, size_t block_enc, uint8_t* out, size_t out_cap, size_t* out_len);
 #endif

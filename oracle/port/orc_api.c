@@ -219,6 +219,46 @@ void* orc_circuit_load(int fid, const uint8_t* b, size_t n) {
 }
 void orc_circuit_free(void* c) { circuit_free((circuit*)c); }
 void orc_circuit_id(void* c, uint8_t id[32]) { circuit_id((const circuit*)c, id); }
+/* the generic Ligero prover on a statement given in wire encoding (elements: to_bytes_field; indices: u64) */
+int orc_ligero_prove(int fid, size_t nw, size_t nq, size_t ncons, size_t nterms, size_t subfield_boundary,
+                     const uint8_t* w_bytes, const uint64_t* lqc, const uint64_t* term_c, const uint64_t* term_w,
+                     const uint8_t* term_k_bytes, const uint8_t* hash, const uint8_t* rngb, size_t rng_len,
+                     const uint8_t* tinit, size_t tinit_len, size_t rate, size_t nreq, size_t block_enc,
+                     uint8_t* out, size_t out_cap, size_t* out_len, size_t* rng_used) {
+  const field* F = orc_field(fid);
+  if (!F) return -1;
+  elt* W = (elt*)malloc((nw ? nw : 1) * sizeof(elt));
+  elt* K = (elt*)malloc((nterms ? nterms : 1) * sizeof(elt));
+  size_t* q = (size_t*)malloc((3 * nq + 1) * sizeof(size_t));
+  size_t* tc = (size_t*)malloc((nterms ? nterms : 1) * sizeof(size_t));
+  size_t* tw = (size_t*)malloc((nterms ? nterms : 1) * sizeof(size_t));
+  int rc = 0;
+  for (size_t i = 0; i < nw && !rc; ++i) rc = f_of_bytes(F, w_bytes + i * F->kbytes, &W[i]) ? -2 : 0;
+  for (size_t i = 0; i < nterms && !rc; ++i) {
+    rc = f_of_bytes(F, term_k_bytes + i * F->kbytes, &K[i]) ? -2 : 0;
+    tc[i] = (size_t)term_c[i];
+    tw[i] = (size_t)term_w[i];
+    if (tc[i] >= ncons || tw[i] >= nw) rc = -2;
+  }
+  for (size_t i = 0; i < 3 * nq && !rc; ++i) {
+    q[i] = (size_t)lqc[i];
+    if (q[i] >= nw) rc = -2;
+  }
+  if (!rc) {
+    ligero_generic G = {F, nw, nq, ncons, nterms, subfield_boundary, W, q, tc, tw, K, hash};
+    bufrng r;
+    bufrng_init(&r, rngb, rng_len);
+    rc = ligero_prove_generic(&G, &r.base, tinit, tinit_len, rate, nreq, block_enc, out, out_cap, out_len);
+    if (rng_used) *rng_used = r.pos;
+    if (r.overrun) rc = -20;
+  }
+  free(W);
+  free(K);
+  free(q);
+  free(tc);
+  free(tw);
+  return rc;
+}
 int orc_zk_prove(void* c, const uint8_t* wit, const uint8_t* rngb, size_t rng_len,
                  const uint8_t* tinit, size_t tinit_len, size_t rate, size_t nreq, size_t block_enc,
                  uint8_t* out, size_t out_cap, size_t* out_len, size_t* rng_used, uint8_t* d_witness,

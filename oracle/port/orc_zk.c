@@ -632,18 +632,23 @@ static void ob_u32(outbuf* o, size_t g) {
   ob_put(o, t, 4);
 }
 
-int zk_prove(const circuit* c, const uint8_t* wbytes, rng* rg, const uint8_t* tinit, size_t tinit_len,
-             size_t rate, size_t nreq, size_t block_enc, uint8_t* out, size_t out_cap, size_t* out_len,
-             zk_dump* dump) {
-  const field* F = c->F;
+/* G != NULL: LigeroProver::commit + ::prove alone (ligero/ligero_prover.h:58-146) on a caller-given
+ * statement -- witness vector, quadratic constraints, linear constraint terms, hash of the statement --
+ * with no circuit and no sumcheck in front; the output is the commitment root (32 bytes) followed by
+ * LigeroProof's serialisation (what ZkProof::write_com_proof emits, zk_proof.h:137-184).  This is the shape
+ * of the reference's C++-generated Ligero vector (rust/runtime/ligero/tests/ligero.rs:592-760). */
+static int zk_prove_ex(const circuit* c, const ligero_generic* G, const uint8_t* wbytes, rng* rg,
+                       const uint8_t* tinit, size_t tinit_len, size_t rate, size_t nreq, size_t block_enc,
+                       uint8_t* out, size_t out_cap, size_t* out_len, zk_dump* dump) {
+  const field* F = G ? G->F : c->F;
   int rc = 0;
-  if (c->logc != 0) return -10;
-  size_t ninp = c->ninputs, npub = c->npub_in, nl = c->nl;
-  size_t n_witness = ninp - npub;
+  if (!G && c->logc != 0) return -10;
+  size_t ninp = G ? 0 : c->ninputs, npub = G ? 0 : c->npub_in, nl = G ? 0 : c->nl;
+  size_t n_witness = G ? G->nw : ninp - npub;
   size_t pad_size = 0;
   for (size_t i = 0; i < nl; ++i) pad_size += 4 * c->l[i].logw + 3; /* zk_common.h:139-146 */
   ligero_param P;
-  if (ligero_param_init(&P, F, n_witness + pad_size, nl, rate, nreq, block_enc)) return -11;
+  if (ligero_param_init(&P, F, n_witness + pad_size, G ? G->nq : nl, rate, nreq, block_enc)) return -11;
 
   elt* W = (elt*)malloc(ninp * sizeof(elt));
   for (size_t i = 0; i < ninp; ++i)
@@ -654,8 +659,8 @@ int zk_prove(const circuit* c, const uint8_t* wbytes, rng* rg, const uint8_t* ti
 
   /* ---- ZkProver::commit (zk/zk_prover.h:72-100) ---- */
   elt* wit = (elt*)malloc(P.nw * sizeof(elt));
-  for (size_t i = 0; i < n_witness; ++i) wit[i] = W[i + npub];
-  size_t sb = c->subfield_boundary >= npub ? c->subfield_boundary - npub : 0;
+  for (size_t i = 0; i < n_witness; ++i) wit[i] = G ? G->W[i] : W[i + npub];
+  size_t sb = G ? G->subfield_boundary : (c->subfield_boundary >= npub ? c->subfield_boundary - npub : 0);
   /* fill_pad (zk_prover.h:152-188) */
   layer_proof* pad = (layer_proof*)calloc(nl, sizeof(layer_proof));
   layer_proof* proof = (layer_proof*)calloc(nl, sizeof(layer_proof));
@@ -680,8 +685,11 @@ int zk_prove(const circuit* c, const uint8_t* wbytes, rng* rg, const uint8_t* ti
     wit[wp++] = f_mul(F, pad[i].wc[0], pad[i].wc[1]);
   }
   /* setup_lqc (zk_common.h:149-160) */
-  size_t(*lqc)[3] = malloc(nl * sizeof(*lqc));
-  {
+  size_t(*lqc)[3] = malloc((P.nq ? P.nq : 1) * sizeof(*lqc));
+  if (G) {
+    for (size_t i = 0; i < G->nq; ++i)
+      for (int k = 0; k < 3; ++k) lqc[i][k] = G->lqc[3 * i + k];
+  } else {
     size_t pi = n_witness;
     for (size_t i = 0; i < nl; ++i) {
       size_t cp = 4 * c->l[i].logw;
@@ -770,19 +778,22 @@ int zk_prove(const circuit* c, const uint8_t* wbytes, rng* rg, const uint8_t* ti
   }
 
   /* ---- ZkProver::prove (zk/zk_prover.h:102-149) ---- */
+  transcript tst;
+  elt** in = (elt**)calloc(nl ? nl : 1, sizeof(elt*));
+  elt* finalV = NULL;
+  if (!G) {
   /* initialize_sumcheck_fiat_shamir (zk_common.h:163-180) */
   ts_write_bytes(&tp, c->id, 32);
   for (size_t i = 0; i < npub; ++i) ts_write_elt(&tp, F, W[i]);
   ts_write_elt(&tp, F, F->zero);
   ts_write0(&tp, c->nterms);
-  transcript tst = tp; /* clone(): transcript.h:86 copies only the hash */
+  tst = tp; /* clone(): transcript.h:86 copies only the hash */
   tst.have_prf = 0;
 
   /* eval_circuit */
-  elt** in = (elt**)calloc(nl, sizeof(elt*));
   in[nl - 1] = (elt*)malloc(ninp * sizeof(elt));
   memcpy(in[nl - 1], W, ninp * sizeof(elt));
-  elt* finalV = (elt*)malloc(c->nv * sizeof(elt));
+  finalV = (elt*)malloc(c->nv * sizeof(elt));
   for (size_t l = nl; l-- > 0;) {
     elt* V;
     size_t nvout;
@@ -805,8 +816,9 @@ int zk_prove(const circuit* c, const uint8_t* wbytes, rng* rg, const uint8_t* ti
     }
   for (size_t i = 0; i < c->nv; ++i)
     if (!f_is_zero(F, finalV[i])) rc = -3;
+  }  /* !G */
 
-  elt* bound_quad = (elt*)calloc(nl, sizeof(elt));
+  elt* bound_quad = (elt*)calloc(nl ? nl : 1, sizeof(elt));
   llvec A = {0, 0, 0};
   elt *y_ldt = NULL, *y_dot = NULL, *y_q = NULL, *Avec = NULL;
   size_t* idx = NULL;
@@ -814,6 +826,13 @@ int zk_prove(const circuit* c, const uint8_t* wbytes, rng* rg, const uint8_t* ti
   size_t pathlen = 0;
   outbuf ob = {out, 0, out_cap, 0};
   if (rc == 0) {
+    size_t ncons = 0;
+    uint8_t hashA[32] = {0xde, 0xad, 0xbe, 0xef};
+    if (G) {
+      for (size_t l = 0; l < G->nterms; ++l) ll_push(&A, G->term_c[l], G->term_w[l], G->term_k[l]);
+      ncons = G->ncons;
+      memcpy(hashA, G->hash, 32);
+    } else {
     /* ProverLayers::prove (prover_layers.h:114-166) */
     bindings bnd;
     bnd.logv = c->logv;
@@ -831,10 +850,10 @@ int zk_prove(const circuit* c, const uint8_t* wbytes, rng* rg, const uint8_t* ti
       free(Q.h);
       free(Q.v);
     }
-    size_t ncons = verifier_constraints(c, W, proof, bound_quad, &A, &tp, n_witness);
+    ncons = verifier_constraints(c, W, proof, bound_quad, &A, &tp, n_witness);
+    }  /* !G */
 
     /* ---- LigeroProver::prove (ligero_prover.h:84-146) ---- */
-    uint8_t hashA[32] = {0xde, 0xad, 0xbe, 0xef};
     ts_write_bytes(&tp, hashA, 32);
     /* low_degree_proof :281-291 */
     y_ldt = (elt*)malloc(P.block * sizeof(elt));
@@ -986,4 +1005,13 @@ int zk_prove(const circuit* c, const uint8_t* wbytes, rng* rg, const uint8_t* ti
   free(idx);
   free(path);
   return rc;
+}
+int zk_prove(const circuit* c, const uint8_t* wbytes, rng* rg, const uint8_t* tinit, size_t tinit_len,
+             size_t rate, size_t nreq, size_t block_enc, uint8_t* out, size_t out_cap, size_t* out_len,
+             zk_dump* dump) {
+  return zk_prove_ex(c, NULL, wbytes, rg, tinit, tinit_len, rate, nreq, block_enc, out, out_cap, out_len, dump);
+}
+int ligero_prove_generic(const ligero_generic* G, rng* rg, const uint8_t* tinit, size_t tinit_len, size_t rate,
+                         size_t nreq, size_t block_enc, uint8_t* out, size_t out_cap, size_t* out_len) {
+  return zk_prove_ex(NULL, G, NULL, rg, tinit, tinit_len, rate, nreq, block_enc, out, out_cap, out_len, NULL);
 }

@@ -186,6 +186,31 @@ def ligero_param(field_id, nw, nq, rate=7, nreq=132, block_enc=0):
     return dict(zip(LIGERO_FIELDS, [int(x) for x in out]))
 
 
+def ligero_prove(field_id, W, lqc, terms_c, terms_w, terms_k, ncons, hash32, rng, subfield_boundary=0,
+                 tinit=b"test", rate=7, nreq=132, block_enc=0):
+    """LigeroProver::commit + ::prove on a caller-given statement (orc_ligero_prove): W (nw, kB) and terms_k
+    (nterms, kB) uint8 in wire encoding, lqc (nq, 3) and terms_c / terms_w index arrays.  Returns
+    (root, LigeroProof bytes, rng bytes consumed)."""
+    W, K = _u8(W), _u8(terms_k)
+    kb = KBYTES[field_id]
+    nw, nt = W.size // kb, K.size // kb
+    q = np.ascontiguousarray(lqc, dtype=np.uint64).reshape(-1)
+    tc = np.ascontiguousarray(terms_c, dtype=np.uint64)
+    tw = np.ascontiguousarray(terms_w, dtype=np.uint64)
+    rng = _u8(np.frombuffer(rng, np.uint8) if isinstance(rng, (bytes, bytearray)) else rng)
+    out = np.zeros(1 << 22, np.uint8)
+    out_len, used = C.c_size_t(), C.c_size_t()
+    rc = lib().orc_ligero_prove(C.c_int(field_id), C.c_size_t(nw), C.c_size_t(q.size // 3), C.c_size_t(ncons),
+                                C.c_size_t(nt), C.c_size_t(subfield_boundary), _p(W), _p(q), _p(tc), _p(tw), _p(K),
+                                C.c_char_p(hash32), _p(rng), C.c_size_t(rng.size), C.c_char_p(tinit),
+                                C.c_size_t(len(tinit)), C.c_size_t(rate), C.c_size_t(nreq), C.c_size_t(block_enc),
+                                _p(out), C.c_size_t(out.size), C.byref(out_len), C.byref(used))
+    if rc != 0:
+        raise RuntimeError(f"oracle Ligero prover failed rc={rc}")
+    b = out[:out_len.value].tobytes()
+    return b[:32], b[32:], used.value
+
+
 class Circuit:
     def __init__(self, field_id, circ_bytes):
         self.field_id = field_id

@@ -5,6 +5,7 @@ holds for this path:
   * rust/runtime/merkle/tests/{merkle,commitment}_test_vector.bin (C++-generated;
     layouts per rust/runtime/merkle/tests/merkle.rs:219-299,302-417)
   * rust/runtime/random/tests/transcript_test_vector.bin (C++-generated; transcript.rs:18-67)
+  * rust/runtime/ligero/tests/ligero_test_vector.bin (C++-generated; ligero.rs:592-760)
   * tests/golden/golden.json: proofs produced by the unmodified reference
   * tests/golden/rfc_zk_vector1.json: the reference's known-answer test of the whole ZK prover
     (rust/runtime/zk/tests/zk.rs:228-558, bytes produced by the C++ prover)
@@ -193,6 +194,48 @@ def test_rust_tree_transcript_vector(oracle):
         script += b"R" + struct.pack("<I", 256)
     got = oracle.transcript_script(bytes(range(1, 9)), script, fid=1)
     assert got == want
+
+
+def test_rust_tree_ligero_vector(oracle):
+    """rust/runtime/ligero/tests/ligero.rs:592-760 `test_cpp_roundtrip_gf2_128` with the C++-generated
+    ligero_test_vector.bin: a stand-alone Ligero statement over GF(2^128) -- 1000 witnesses of which the first
+    950 lie in the subfield, 50 quadratic constraints, 1000 linear terms in 15 constraints, rate 4, nreq 36,
+    block_enc 4096, coins from the test's 64-bit LCG (seed 100) -- with the commitment root and the 55 768
+    serialised proof bytes the C++ prover produced.  The oracle's LigeroProver::commit + ::prove
+    (ligero_prove_generic: the same code the ZK prover runs behind its sumcheck) reproduces both."""
+    d = open(f"{GOLDEN}/ligero_test_vector.bin", "rb").read()
+    off = 0
+
+    def u64():
+        nonlocal off
+        v = struct.unpack_from("<Q", d, off)[0]
+        off += 8
+        return v
+    nw, nq, nreq, nl, sb = [u64() for _ in range(5)]
+    W = np.frombuffer(d, np.uint8, nw * 16, off).reshape(nw, 16)
+    off += 2 * nw * 16          # W, then the (unused) inner-product vector A
+    lqc = np.array([[u64(), u64(), u64()] for _ in range(nq)], np.uint64)
+    tc, tw, tk = [], [], []
+    for _ in range(u64()):
+        tc.append(u64())
+        tw.append(u64())
+        tk.append(d[off:off + 16])
+        off += 16
+    off += nl * 16              # b: the verifier's side
+    h, root = d[off:off + 32], d[off + 32:off + 64]
+    off += 64
+    plen = u64()
+    proof = d[off:off + plen]
+    assert off + plen == len(d) and (nw, nq, nreq, nl, sb) == (1000, 50, 36, 15, 950)
+    st, coins = 100, bytearray(1 << 18)
+    for i in range(len(coins)):   # SimpleRng of ligero.rs:28-42
+        st = (st * 6364136223846793005 + 1442695040888963407) & ((1 << 64) - 1)
+        coins[i] = (st >> 32) & 0xFF
+    r, p, used = oracle.ligero_prove(4, W, lqc, tc, tw, np.frombuffer(b"".join(tk), np.uint8), nl, h, bytes(coins),
+                                     subfield_boundary=sb, rate=4, nreq=nreq, block_enc=4096)
+    assert r == root
+    assert p == proof
+    assert used == 144360
 
 
 def test_transcript_key_and_prf_blocks(oracle):
