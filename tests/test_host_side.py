@@ -148,3 +148,22 @@ def test_host_transcript_helpers_match_oracle(oracle):
     s = (b"B" + u32(5) + b"hello" + b"R" + u32(40) + b"R" + u32(5) + b"R" + u32(20) + b"B" + u32(100) +
          bytes(range(100)) + b"R" + u32(16) + b"B" + u32(0) + b"R" + u32(1))
     assert got == oracle.transcript_script(b"test", s)
+
+
+def test_reference_arm_prints_the_contract_line(ref):
+    """`bench.py --impl reference` (the unmodified reference on the host cores, no GPU involved) prints ONE JSON
+    line on stdout with the keys of the bench contract: metric / unit / value of the headline workload,
+    `impl: reference`, a `cpu_baseline` describing the run and an `e2e` object with zero copy bytes."""
+    import json
+    import sys
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1",
+                          "--warmup", "1"], capture_output=True, text=True, check=True, timeout=600).stdout
+    lines = [l for l in out.splitlines() if l.strip()]
+    assert len(lines) == 1, lines
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "sha256_zk_prover_throughput" and d["unit"] == "proofs/s"
+    assert d["higher_is_better"] is True and d["value"] > 0 and d["n_gpus"] == 1
+    assert d["cpu_baseline"]["kind"] == "reference" and d["cpu_baseline"]["cores"] >= 1
+    assert abs(d["cpu_baseline"]["value"] - d["value"]) < 1e-6 * d["value"]
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
+    assert "BM_ShaZK_fp2_128/1" in d["config"]["workload"]
